@@ -1,0 +1,276 @@
+/*
+ * otters_b200.h — C ABI of libotters_b200.so, the B200-native (sm_100a) implementation of the
+ * otters exact-search hot path.
+ *
+ * The reference (AtharvBhat/otters, Rust) has no FFI seam of its own: the drop-in boundary is its
+ * public Rust API, and these entry points are what a thin `otters-sys` crate binds directly beneath
+ * `VecQueryPlan::collect` (src/vec.rs:206-311), `MetaStoreBuilder::build` (src/meta.rs:151-305) and
+ * `MetaQueryPlan::collect` (src/meta.rs:632-829).  INTEGRATION.md shows that binding.  Each entry
+ * point below cites the reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - every function returns an int status (OTTERS_OK == 0); on failure a thread-local message is
+ *    available from otters_last_error().  Validation messages reproduce the reference's strings
+ *    (src/vec.rs:170-203, :357-363).
+ *  - plain pointers and sizes only; the caller owns all in/out buffers; the library copies inputs
+ *    before returning; opaque handles are released with the matching *_destroy.
+ *  - enum codes follow the reference's declaration order.
+ *  - there is NO CPU fallback: every query runs on the CUDA device of the context.
+ */
+#ifndef OTTERS_B200_H
+#define OTTERS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define OTTERS_API __attribute__((visibility("default")))
+#else
+#define OTTERS_API
+#endif
+
+#define OTTERS_OK 0
+#define OTTERS_ERR_INVALID 1     /* validation error; message mirrors the reference's Err(String) */
+#define OTTERS_ERR_CUDA 2        /* CUDA runtime failure */
+#define OTTERS_ERR_NOMEM 3       /* host or device allocation failure */
+#define OTTERS_ERR_UNSUPPORTED 4 /* configuration outside what the kernels support */
+
+/* src/vec.rs:11-16 */
+#define OTTERS_METRIC_COSINE 0
+#define OTTERS_METRIC_EUCLIDEAN 1 /* SQUARED euclidean, no sqrt (src/vec_compute.rs:35-54) */
+#define OTTERS_METRIC_DOT 2
+/* src/vec.rs:18-22 */
+#define OTTERS_TAKE_MIN 0
+#define OTTERS_TAKE_MAX 1
+/* src/vec.rs:24-31 */
+#define OTTERS_CMP_LT 0
+#define OTTERS_CMP_GT 1
+#define OTTERS_CMP_LTE 2
+#define OTTERS_CMP_GTE 3
+#define OTTERS_CMP_EQ 4
+/* src/expr.rs:83-91 */
+#define OTTERS_OP_EQ 0
+#define OTTERS_OP_NEQ 1
+#define OTTERS_OP_LT 2
+#define OTTERS_OP_LTE 3
+#define OTTERS_OP_GT 4
+#define OTTERS_OP_GTE 5
+/* src/type_utils.rs:11-19 */
+#define OTTERS_DTYPE_INT32 0
+#define OTTERS_DTYPE_INT64 1
+#define OTTERS_DTYPE_FLOAT32 2
+#define OTTERS_DTYPE_FLOAT64 3
+#define OTTERS_DTYPE_STRING 4
+#define OTTERS_DTYPE_DATETIME 5 /* i64 epoch milliseconds UTC (src/col.rs:18) */
+/* src/expr.rs:192-210 (NumericLiteral::{I64,F64} / ColumnFilter::String) */
+#define OTTERS_LIT_I64 0
+#define OTTERS_LIT_F64 1
+#define OTTERS_LIT_STR 2
+
+typedef struct otters_ctx otters_ctx;
+typedef struct otters_vecstore otters_vecstore;
+typedef struct otters_metastore otters_metastore;
+
+/* ---------------------------------------------------------------------------------------------
+ * context: one CUDA device + one stream.  `cuda_stream` may be NULL (the library creates its own
+ * non-blocking stream) or an existing cudaStream_t on `device` that all work is enqueued on.
+ * ------------------------------------------------------------------------------------------- */
+OTTERS_API int otters_ctx_create(int device, void *cuda_stream, otters_ctx **out);
+OTTERS_API int otters_ctx_destroy(otters_ctx *ctx);
+OTTERS_API int otters_ctx_synchronize(otters_ctx *ctx);
+OTTERS_API const char *otters_last_error(void);
+OTTERS_API const char *otters_version(void);
+
+/* Tuning knobs of the scan kernel (0 = automatic).  For profiling sweeps; results never change. */
+typedef struct {
+    uint32_t warps_per_cta;
+    uint32_t slots_per_warp;
+    uint32_t kc_floats;    /* columns staged per slot (multiple of 8) */
+    uint32_t ctas_per_sm;
+    uint32_t unit_rows;    /* reserved */
+} otters_scan_tuning;
+OTTERS_API int otters_ctx_set_tuning(otters_ctx *ctx, const otters_scan_tuning *t);
+
+/* Counters of the work enqueued by the LAST query on this context (for bench.py's gpu_launches and
+ * the roofline numerator). */
+typedef struct {
+    uint64_t kernel_launches;   /* kernels of this library launched by the last query */
+    uint64_t rows_scored;       /* rows whose vector was streamed from HBM (x queries) */
+    uint64_t scan_bytes;        /* algorithmic bytes of the scan kernel: rows_scored*(dim*4 [+4 cosine]) */
+    uint64_t meta_bytes;        /* algorithmic bytes of prune + row-mask kernels */
+    float scan_ms;              /* device time of the scan kernel(s) of the last query (CUDA events) */
+    float prune_ms, rowmask_ms, select_ms;
+} otters_last_work;
+OTTERS_API int otters_ctx_last_work(otters_ctx *ctx, otters_last_work *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * VecStore — src/vec.rs:338-411.  Rows live in HBM (row-major f32, 16-byte aligned rows) with the
+ * per-row inverse L2 norm precomputed exactly as add_vector does (serial f32 sum of squares,
+ * 1/sqrt, 0.0 for a zero row; src/vec.rs:357-371).
+ * ------------------------------------------------------------------------------------------- */
+OTTERS_API int otters_vecstore_create(otters_ctx *ctx, uint32_t dim, otters_vecstore **out); /* VecStore::new */
+OTTERS_API int otters_vecstore_destroy(otters_vecstore *vs);
+OTTERS_API int otters_vecstore_reserve(otters_vecstore *vs, uint64_t n_rows);
+/* VecStore::add_vectors with contiguous row-major host rows (n * dim floats). */
+OTTERS_API int otters_vecstore_add(otters_vecstore *vs, const float *rows, uint64_t n);
+/* Same, rows already in device memory on the context's device. */
+OTTERS_API int otters_vecstore_add_device(otters_vecstore *vs, const float *d_rows, uint64_t n);
+/* Appends n rows of the counter-based synthetic generator x = (splitmix64(seed ^ (row*dim+col)) >> 40) * 2^-23 - 1
+ * (row = absolute row id starting at first_row), generated on the device.  Bench/test utility. */
+OTTERS_API int otters_vecstore_add_synthetic(otters_vecstore *vs, uint64_t first_row, uint64_t n, uint64_t seed);
+OTTERS_API uint64_t otters_vecstore_len(const otters_vecstore *vs); /* VecStore::len */
+OTTERS_API uint32_t otters_vecstore_dim(const otters_vecstore *vs);
+/* debug/parity: copies inverse norms [first, first+n) to host */
+OTTERS_API int otters_vecstore_inv_norms(const otters_vecstore *vs, uint64_t first, uint64_t n, float *out);
+
+/* The inputs of VecQueryPlan::collect (src/vec.rs:55-66, :206-219).  The host-side plan builder
+ * resolves the defaults before the call: k = n_vecs when no take*() was given (:213), take_type =
+ * Max when none (:214) / inferred from the metric by take() (:92-116). */
+typedef struct {
+    const float *queries;            /* nq * dim, row-major, host memory */
+    uint32_t nq;
+    uint32_t dim;                    /* must equal the store's dim, else the reference's error string */
+    int32_t metric;                  /* OTTERS_METRIC_* */
+    int32_t take_type;               /* OTTERS_TAKE_* */
+    uint64_t k;                      /* take count */
+    int32_t has_filter;              /* .filter(thr, cmp) / .vec_filter(thr, cmp) present */
+    float thr;
+    int32_t cmp;                     /* OTTERS_CMP_* */
+    const uint64_t *row_mask_words;  /* .with_row_mask(BitVec): Lsb0 words, bit = 1 keep; NULL = none */
+    uint64_t row_mask_bits;          /* mask length in bits; rows >= this are kept (src/vec.rs:234,297) */
+} otters_vec_query;
+
+/* VecQueryPlan::collect (src/vec.rs:206-311).  Writes min(*out_len, cap) results best-first;
+ * *out_len is the full result count.  One merged list for a batch (src/vec.rs:217-219); out_qid
+ * (nullable, extension) receives the query index of each result.  Ties: better score, then lower
+ * row, then lower query index. */
+OTTERS_API int otters_vecstore_query(otters_vecstore *vs, const otters_vec_query *q, uint64_t *out_idx, float *out_score,
+                          uint32_t *out_qid, uint64_t cap, uint64_t *out_len);
+
+/* ---------------------------------------------------------------------------------------------
+ * MetaStore — src/meta.rs:48-60, :151-305.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const char *name;               /* UTF-8, NUL-terminated */
+    int32_t dtype;                  /* OTTERS_DTYPE_* */
+    const void *values;             /* typed array of n_rows entries (src/col.rs:11-19); NULL for String */
+    const uint64_t *null_words;     /* Lsb0 words, bit = 1 NULL (src/col.rs:26); NULL = no nulls */
+    const uint64_t *str_offsets;    /* String: n_rows + 1 byte offsets into str_bytes */
+    const uint8_t *str_bytes;       /* String: concatenated bytes */
+} otters_column;
+
+#define OTTERS_VECTORS_HOST 0
+#define OTTERS_VECTORS_DEVICE 1
+#define OTTERS_VECTORS_SYNTHETIC 2
+
+typedef struct {
+    uint64_t n_rows;
+    uint32_t dim;
+    uint64_t chunk_size;            /* with_chunk_size; 0 -> 1 (src/meta.rs:86-89); default 1024 */
+    int32_t bloom_mode;             /* 0 = Fpr(bloom_fpr) (src/meta.rs:92-101), 1 = Bits(bloom_bits) (:106-110) */
+    double bloom_fpr;
+    uint64_t bloom_bits;
+    int32_t vectors_kind;           /* OTTERS_VECTORS_* */
+    const float *vectors;           /* host or device pointer, n_rows * dim floats row-major */
+    uint64_t synthetic_seed;        /* OTTERS_VECTORS_SYNTHETIC */
+    uint64_t synthetic_first_row;
+    const otters_column *columns;
+    uint32_t n_columns;
+} otters_build_params;
+
+/* src/meta.rs:844-852 (durations in seconds) */
+typedef struct {
+    uint64_t n_rows;
+    uint64_t dim;
+    uint64_t n_chunks;
+    double vectors_ingest_s;
+    double zonemap_build_s;
+    double build_total_s;
+} otters_build_stats;
+
+/* src/meta.rs:832-842 (durations in seconds) */
+typedef struct {
+    uint64_t total_chunks;
+    uint64_t pruned_chunks;
+    uint64_t evaluated_chunks;
+    uint64_t vectors_compared;
+    double prune_s;
+    double score_s;
+    double merge_s;
+    double total_s;
+} otters_query_stats;
+
+/* MetaStoreBuilder::build (src/meta.rs:151-305): chunking, per-chunk zonemaps (min/max/non-null,
+ * src/meta_compute.rs:32-132), per-chunk string Bloom filters, dictionary codes for strings. */
+OTTERS_API int otters_metastore_build(otters_ctx *ctx, const otters_build_params *p, otters_metastore **out,
+                           otters_build_stats *stats /* nullable */);
+OTTERS_API int otters_metastore_destroy(otters_metastore *ms);
+OTTERS_API uint64_t otters_metastore_n_chunks(const otters_metastore *ms); /* MetaStore::n_chunks */
+OTTERS_API uint64_t otters_metastore_chunk_size(const otters_metastore *ms);
+OTTERS_API uint64_t otters_metastore_len(const otters_metastore *ms);
+
+/* One leaf of the compiled filter (ColumnFilter, src/expr.rs:192-210). */
+typedef struct {
+    uint32_t col;       /* index into otters_build_params.columns */
+    int32_t op;         /* OTTERS_OP_* */
+    int32_t kind;       /* OTTERS_LIT_* */
+    int64_t i;          /* NumericLiteral::I64 (DateTime literals: epoch millis) */
+    double f;           /* NumericLiteral::F64 */
+    const uint8_t *s;   /* string literal bytes */
+    uint64_t slen;
+} otters_leaf;
+
+/* CompiledFilter (src/expr.rs:212-226): AND over clauses of OR over leaves. */
+typedef struct {
+    uint32_t n_clauses;
+    const uint32_t *clause_offsets; /* n_clauses + 1 offsets into leaves */
+    const otters_leaf *leaves;
+} otters_filter;
+
+/* MetaQueryPlan::collect (src/meta.rs:632-721): zonemap/Bloom chunk pruning (:407-544), per-row CNF
+ * predicate (src/meta_compute.rs:194-318), scoring, top-k, stats.  `q->row_mask_words` must be NULL.
+ * `filter` may be NULL (no meta_filter).  Result-column gathering (src/meta.rs:723-828) stays on
+ * the host side of the boundary. */
+OTTERS_API int otters_metastore_query(otters_metastore *ms, const otters_vec_query *q, const otters_filter *filter,
+                           uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap, uint64_t *out_len,
+                           otters_query_stats *stats /* nullable */);
+/* MetaStore::last_query_stats (src/meta.rs:395-397); returns OTTERS_ERR_INVALID if no query ran yet */
+OTTERS_API int otters_metastore_last_stats(const otters_metastore *ms, otters_query_stats *out);
+
+/* parity/debug exports: results of the prune and row-mask kernels for `filter` (one byte per chunk /
+ * per row, 1 = keep) and the zonemap tables built on the device side of the boundary */
+OTTERS_API int otters_metastore_chunk_mask(otters_metastore *ms, const otters_filter *filter, uint8_t *keep);
+OTTERS_API int otters_metastore_row_mask(otters_metastore *ms, const otters_filter *filter, uint8_t *keep);
+OTTERS_API int otters_metastore_zonemap_i64(const otters_metastore *ms, uint32_t col, int64_t *mn, int64_t *mx, uint64_t *non_null);
+OTTERS_API int otters_metastore_zonemap_f64(const otters_metastore *ms, uint32_t col, double *mn, double *mx, uint64_t *non_null);
+OTTERS_API int otters_metastore_inv_norms(const otters_metastore *ms, uint64_t first, uint64_t n, float *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded multi-GPU search: every rank holds a contiguous row range, computes a
+ * local top-k that stays in device memory as fixed 16-byte records, the ranks all-gather the
+ * records (NCCL), and every rank runs the same final merge.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t row;   /* global row id (row_base + local row); UINT64_MAX = empty slot */
+    float score;
+    uint32_t qid;
+} otters_topk_record;
+
+/* Local query whose result stays on the device: writes exactly k records to d_records (device
+ * memory, padded with empty slots).  `filter`/`ms` semantics as above; pass vs for a VecStore or ms
+ * for a MetaStore (exactly one non-NULL).  Stats counters are local to the shard. */
+OTTERS_API int otters_query_local_device(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q,
+                              const otters_filter *filter, uint64_t row_base, void *d_records,
+                              otters_query_stats *stats /* nullable */);
+/* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k. */
+OTTERS_API int otters_topk_merge_device(otters_ctx *ctx, const void *d_records, uint64_t n_records, uint64_t k, int32_t take_type,
+                             uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap, uint64_t *out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTTERS_B200_H */

@@ -1,0 +1,62 @@
+"""Device context: one CUDA device + one stream (``otters_ctx`` in include/otters_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+from . import _ffi
+from .types import OttersError
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise OttersError(_ffi.last_error())
+
+
+class Context:
+    """Owns an ``otters_ctx``.  ``stream`` may be a raw ``cudaStream_t`` handle (e.g.
+    ``torch.cuda.current_stream().cuda_stream``) so that work interleaves with the caller's."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        h = C.c_void_p()
+        check(_ffi.otters_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self) -> None:
+        check(_ffi.otters_ctx_synchronize(self._h))
+
+    def set_tuning(self, warps_per_cta=0, slots_per_warp=0, kc_floats=0, ctas_per_sm=0, unit_rows=0) -> None:
+        t = _ffi.ScanTuning(warps_per_cta, slots_per_warp, kc_floats, ctas_per_sm, unit_rows)
+        check(_ffi.otters_ctx_set_tuning(self._h, C.byref(t)))
+
+    def last_work(self) -> Dict[str, float]:
+        w = _ffi.LastWork()
+        check(_ffi.otters_ctx_last_work(self._h, C.byref(w)))
+        return {f: getattr(w, f) for f, _ in _ffi.LastWork._fields_}
+
+    def close(self) -> None:
+        if self._h:
+            _ffi.otters_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default: Dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device, created on first use (fails loudly without a B200)."""
+    ctx = _default.get(device)
+    if ctx is None:
+        ctx = _default[device] = Context(device)
+    return ctx

@@ -1,0 +1,1476 @@
+// api.cu — the C ABI of libotters_b200.so (include/otters_b200.h): contexts, device-resident stores,
+// query orchestration.  Everything that touches rows runs in the CUDA kernels of scan.cu / select.cu
+// / meta.cu / store.cu; there is no CPU fallback.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "internal.h"
+
+namespace otters {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static inline double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+static inline uint64_t pow2_at_least(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace otters
+
+using namespace otters;
+
+// =================================================================================================
+// context
+// =================================================================================================
+struct otters_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    otters_scan_tuning tuning{};
+    otters_last_work last{};
+
+    // device scratch
+    float* d_query = nullptr;
+    size_t d_query_floats = 0;
+    uint32_t* d_counter = nullptr;      // [0] unit counter, [1] emit count
+    uint64_t* d_cta_keys = nullptr;     // [grid_max][kMaxFusedK]
+    uint32_t* d_cta_counts = nullptr;
+    uint32_t grid_max = 0;
+    Cand* d_list[2] = {nullptr, nullptr};  // running / result lists
+    size_t list_cap = 0;
+    uint32_t* d_list_count = nullptr;   // [2]
+    uint64_t* d_tau = nullptr;
+    uint64_t* d_scratch_keys = nullptr;
+    uint32_t* d_scratch_src = nullptr;
+    uint32_t scratch_elems = 0;
+    unsigned long long* d_rows_scored = nullptr;
+    uint32_t* d_mask = nullptr;         // uploaded VecStore row mask
+    size_t d_mask_words = 0;
+    Cand* d_emit = nullptr;             // emit-all path
+    size_t emit_cap = 0;
+    otters_topk_record* d_records = nullptr;
+    size_t records_cap = 0;
+
+    // pinned staging
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+
+    cudaEvent_t ev[8]{};
+    bool stage_pending = false;   // an async H2D copy out of h_stage is in flight (ev[7] marks its end)
+    bool timed_single = false;    // ev[3]/ev[4] bracket the single scan kernel of the last query
+    bool timed_meta = false;      // ev[0]/ev[1]/ev[6] bracket prune / row-mask of the last query
+};
+
+namespace otters {
+
+static int ensure_stage(otters_ctx* c, size_t bytes) {
+    if (c->stage_pending) {  // the staging buffer is about to be rewritten
+        OTTERS_CUDA(cudaEventSynchronize(c->ev[7]));
+        c->stage_pending = false;
+    }
+    if (bytes <= c->h_stage_bytes) return OTTERS_OK;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_bytes = 0;
+    size_t nb = std::max<size_t>(round_up(bytes, 4096), 1 << 16);
+    OTTERS_CUDA(cudaMallocHost((void**)&c->h_stage, nb));
+    c->h_stage_bytes = nb;
+    return OTTERS_OK;
+}
+
+template <typename T>
+static int ensure_dev(T** ptr, size_t* cap, size_t need, cudaStream_t s) {
+    if (need <= *cap && *ptr) return OTTERS_OK;
+    if (*ptr) {
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        *cap = 0;
+    }
+    size_t n = std::max<size_t>(need, 16);
+    OTTERS_CUDA(cudaMalloc((void**)ptr, n * sizeof(T)));
+    *cap = n;
+    return OTTERS_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- device vector storage shared by VecStore and MetaStore ---------------------------------------
+struct VecStorage {
+    otters_ctx* ctx = nullptr;
+    uint32_t dim = 0;
+    uint32_t pitch = 0;  // floats per stored row: dim rounded up to 4 (16-byte rows for TMA bulk copies)
+    uint64_t n = 0, cap = 0;
+    float* d_rows = nullptr;
+    float* d_inv = nullptr;
+
+    int reserve(uint64_t want) {
+        if (want <= cap) return OTTERS_OK;
+        uint64_t ncap = std::max<uint64_t>(want, cap ? cap + cap / 2 : 0);
+        if (ncap == want && cap != 0 && want < cap * 2) ncap = want;
+        float *nr = nullptr, *ni = nullptr;
+        if (cudaMalloc((void**)&nr, std::max<uint64_t>(ncap * pitch, 4) * sizeof(float)) != cudaSuccess)
+            return fail(OTTERS_ERR_NOMEM, "device allocation for vectors failed");
+        if (cudaMalloc((void**)&ni, std::max<uint64_t>(ncap, 4) * sizeof(float)) != cudaSuccess) {
+            cudaFree(nr);
+            return fail(OTTERS_ERR_NOMEM, "device allocation for inverse norms failed");
+        }
+        if (n) {
+            OTTERS_CUDA(cudaMemcpyAsync(nr, d_rows, n * pitch * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+            OTTERS_CUDA(cudaMemcpyAsync(ni, d_inv, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_rows);
+        cudaFree(d_inv);
+        d_rows = nr;
+        d_inv = ni;
+        cap = ncap;
+        return OTTERS_OK;
+    }
+    int add(const float* rows, uint64_t cnt, cudaMemcpyKind kind) {
+        if (cnt == 0) return OTTERS_OK;
+        if (n + cnt >= 0xFFFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "a store shard is limited to 2^32-16 rows");
+        int rc = reserve(n + cnt);
+        if (rc) return rc;
+        if (pitch == dim) {
+            OTTERS_CUDA(cudaMemcpyAsync(d_rows + n * pitch, rows, cnt * dim * sizeof(float), kind, ctx->stream));
+        } else {
+            OTTERS_CUDA(cudaMemsetAsync(d_rows + n * pitch, 0, cnt * pitch * sizeof(float), ctx->stream));
+            OTTERS_CUDA(cudaMemcpy2DAsync(d_rows + n * pitch, pitch * sizeof(float), rows, dim * sizeof(float),
+                                          dim * sizeof(float), cnt, kind, ctx->stream));
+        }
+        rc = launch_inv_norms(d_rows, pitch, dim, n, cnt, d_inv, ctx->stream);
+        if (rc) return rc;
+        OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be reused after return
+        n += cnt;
+        return OTTERS_OK;
+    }
+    int add_synth(uint64_t first_row, uint64_t cnt, uint64_t seed) {
+        if (cnt == 0) return OTTERS_OK;
+        if (n + cnt >= 0xFFFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "a store shard is limited to 2^32-16 rows");
+        int rc = reserve(n + cnt);
+        if (rc) return rc;
+        rc = launch_synth_fill(d_rows, pitch, dim, n, first_row, cnt, seed, ctx->stream);
+        if (rc) return rc;
+        rc = launch_inv_norms(d_rows, pitch, dim, n, cnt, d_inv, ctx->stream);
+        if (rc) return rc;
+        OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        n += cnt;
+        return OTTERS_OK;
+    }
+    void release() {
+        cudaFree(d_rows);
+        cudaFree(d_inv);
+        d_rows = d_inv = nullptr;
+        n = cap = 0;
+    }
+};
+
+// ---- scan planning ---------------------------------------------------------------------------------
+struct ScanPlan {
+    ScanLaunch launch;
+    uint32_t kc, nkc, pitch_s, slots, unit_rows, n_units, cap;
+    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_list, off_w_slots;
+};
+
+static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, ScanPlan* out) {
+    ScanPlan pl{};
+    const otters_scan_tuning& t = c->tuning;
+    pl.cap = k_fused ? (uint32_t)pow2_at_least(std::max<uint32_t>(2 * k_fused, 64)) : 0;
+    const uint32_t hdr = (uint32_t)round_up(16 + (uint64_t)pl.cap * 8, 128);
+    pl.off_query = hdr;
+    pl.off_warps = (uint32_t)round_up((uint64_t)hdr + (uint64_t)dim_pad * 4, 128);
+    const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
+    if (pl.off_warps + 4096 > budget) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
+
+    uint32_t dim8 = (uint32_t)round_up(dim_pad, 8);
+    uint32_t kc_target = t.kc_floats ? (uint32_t)round_up(t.kc_floats, 8) : 512;
+    uint32_t nkc = (dim_pad + kc_target - 1) / kc_target;
+    if (nkc < 1) nkc = 1;
+    uint32_t kc = (uint32_t)round_up((dim8 + nkc - 1) / nkc, 8);
+    nkc = (dim_pad + kc - 1) / kc;
+    pl.kc = kc;
+    pl.nkc = nkc;
+    pl.pitch_s = (uint32_t)round_up(kc, 32) + 8;
+    const uint32_t slot_bytes = kTileRows * pl.pitch_s * 4;
+
+    auto warp_bytes_for = [&](uint32_t S, uint32_t* o_rows, uint32_t* o_info, uint32_t* o_list, uint32_t* o_slots) {
+        uint32_t o = 0;
+        o += S * 8;
+        *o_rows = o;
+        o += S * kTileRows * 4;
+        *o_info = o;
+        o += (uint32_t)round_up(S * 4, 16);
+        *o_list = o;
+        o += kMaxUnitRows;
+        o = (uint32_t)round_up(o, 128);
+        *o_slots = o;
+        o += S * slot_bytes;
+        return (uint32_t)round_up(o, 128);
+    };
+    uint32_t dummy[4];
+    const size_t avail = budget - pl.off_warps;
+    uint32_t total_slots = (uint32_t)(avail / (slot_bytes + 256));
+    if (total_slots < 1) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
+    uint32_t S = t.slots_per_warp ? t.slots_per_warp : (total_slots >= 4 ? 2 : 1);
+    uint32_t W = t.warps_per_cta ? t.warps_per_cta : std::min<uint32_t>(total_slots / S, 16);
+    if (W < 1) W = 1;
+    if (W > 16) W = 16;
+    while (W > 1 && (size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3) > avail) --W;
+    while (S > 1 && (size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3) > avail) --S;
+    if ((size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3) > avail)
+        return fail(OTTERS_ERR_UNSUPPORTED, "scan tuning does not fit in shared memory");
+    pl.slots = S;
+    pl.warp_bytes = warp_bytes_for(S, &pl.off_w_rows, &pl.off_w_info, &pl.off_w_list, &pl.off_w_slots);
+
+    uint32_t ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : 1;
+    uint32_t grid = (uint32_t)c->sm_count * ctas_per_sm;
+    uint32_t unit_rows = t.unit_rows ? t.unit_rows : kMaxUnitRows;
+    if (unit_rows != 32 && unit_rows != 64 && unit_rows != 128) unit_rows = kMaxUnitRows;
+    if (!t.unit_rows)
+        while (unit_rows > 32 && n_rows / unit_rows < (uint64_t)grid * W * 2) unit_rows >>= 1;
+    pl.unit_rows = unit_rows;
+    pl.n_units = (uint32_t)((n_rows + unit_rows - 1) / unit_rows);
+    uint32_t need_ctas = (pl.n_units + W - 1) / W;
+    if (need_ctas < 1) need_ctas = 1;
+    if (grid > need_ctas) grid = need_ctas;
+    if (grid > c->grid_max) grid = c->grid_max;
+    pl.launch.grid = grid;
+    pl.launch.block = W * 32;
+    pl.launch.smem_bytes = pl.off_warps + W * pl.warp_bytes;
+    *out = pl;
+    return OTTERS_OK;
+}
+
+// ---- the query core: scan + select for every query of the batch --------------------------------------
+struct QueryRun {
+    uint32_t result_list = 0;  // index into ctx->d_list holding the final ordered candidates
+    uint64_t k_eff = 0;
+    bool big = false;          // result lives in ctx->d_emit-sized list (emit-all path)
+};
+
+static float host_inv_norm(const float* v, uint32_t dim) {
+    // src/vec.rs:390-397: serial f32 sum of squares, sqrt, reciprocal (0 for a zero vector).
+    // volatile keeps the compiler from contracting or reassociating.
+    volatile float s = -0.0f;
+    for (uint32_t i = 0; i < dim; ++i) {
+        volatile float p = v[i] * v[i];
+        s = s + p;
+    }
+    float norm = sqrtf(s);
+    return norm != 0.0f ? 1.0f / norm : 0.0f;
+}
+
+static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const uint32_t* d_row_mask,
+                       uint32_t row_mask_words, otters_topk_record* d_records_out, uint64_t row_base, QueryRun* run) {
+    const uint32_t dim_pad = st->pitch;
+    const uint64_t n_rows = st->n;
+    const uint64_t k_eff = std::min<uint64_t>(q->k, n_rows * (uint64_t)q->nq);
+    run->k_eff = k_eff;
+    run->result_list = 0;
+    c->last.kernel_launches = 0;
+    c->last.rows_scored = 0;
+    c->last.scan_bytes = 0;
+    cudaStream_t s = c->stream;
+
+    // stage queries (zero padded to the stored pitch) and their inverse norms
+    const size_t qfloats = (size_t)q->nq * dim_pad;
+    int rc = ensure_stage(c, qfloats * 4 + 64);
+    if (rc) return rc;
+    rc = ensure_dev(&c->d_query, &c->d_query_floats, qfloats, s);
+    if (rc) return rc;
+    std::vector<float> q_inv(q->nq);
+    float* hq = reinterpret_cast<float*>(c->h_stage);
+    for (uint32_t i = 0; i < q->nq; ++i) {
+        const float* src = q->queries + (size_t)i * q->dim;
+        memcpy(hq + (size_t)i * dim_pad, src, (size_t)q->dim * 4);
+        for (uint32_t j = q->dim; j < dim_pad; ++j) hq[(size_t)i * dim_pad + j] = 0.f;
+        q_inv[i] = host_inv_norm(src, q->dim);
+    }
+    OTTERS_CUDA(cudaMemcpyAsync(c->d_query, hq, qfloats * 4, cudaMemcpyHostToDevice, s));
+    OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
+    c->stage_pending = true;
+    c->timed_single = false;
+    OTTERS_CUDA(cudaMemsetAsync(c->d_list_count, 0, 2 * sizeof(uint32_t), s));
+    OTTERS_CUDA(cudaMemsetAsync(c->d_tau, 0, sizeof(uint64_t), s));
+    OTTERS_CUDA(cudaMemsetAsync(c->d_rows_scored, 0, sizeof(unsigned long long), s));
+
+    const bool fused = k_eff <= kMaxFusedK;
+    ScanPlan pl;
+    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, &pl);
+    if (rc) return rc;
+
+    ScanParams sp{};
+    sp.vectors = st->d_rows;
+    sp.inv_norms = st->d_inv;
+    sp.pitch_g = st->pitch;
+    sp.dim = st->dim;
+    sp.dim_pad = dim_pad;
+    sp.n_rows = (uint32_t)n_rows;
+    sp.row_mask = d_row_mask;
+    sp.row_mask_words = row_mask_words;
+    sp.n_units = pl.n_units;
+    sp.unit_rows = pl.unit_rows;
+    sp.unit_counter = c->d_counter;
+    sp.k = (uint32_t)std::min<uint64_t>(k_eff, kMaxFusedK);
+    sp.cap = pl.cap;
+    sp.take_max = q->take_type == OTTERS_TAKE_MAX;
+    sp.has_filter = q->has_filter;
+    sp.thr = q->thr;
+    sp.cmp = q->cmp;
+    sp.kc = pl.kc;
+    sp.nkc = pl.nkc;
+    sp.pitch_s = pl.pitch_s;
+    sp.slots = pl.slots;
+    sp.off_query = pl.off_query;
+    sp.off_warps = pl.off_warps;
+    sp.warp_bytes = pl.warp_bytes;
+    sp.off_w_rows = pl.off_w_rows;
+    sp.off_w_info = pl.off_w_info;
+    sp.off_w_list = pl.off_w_list;
+    sp.off_w_slots = pl.off_w_slots;
+    sp.cta_keys = c->d_cta_keys;
+    sp.cta_counts = c->d_cta_counts;
+    sp.rows_scored = c->d_rows_scored;
+
+    uint32_t cur = 0;
+    if (fused) {
+        rc = ensure_dev(&c->d_list[0], &c->list_cap, (size_t)kMaxFusedK, s);
+        if (rc) return rc;
+        cudaEventRecord(c->ev[2], s);
+        for (uint32_t qi = 0; qi < q->nq; ++qi) {
+            OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(uint32_t), s));
+            sp.query = c->d_query + (size_t)qi * dim_pad;
+            sp.q_inv = q_inv[qi];
+            sp.qid = qi;
+            sp.tau_in = qi ? c->d_tau : nullptr;
+            if (qi == 0 && q->nq == 1) cudaEventRecord(c->ev[3], s);
+            rc = launch_scan(sp, pl.launch, q->metric, false, s);
+            if (rc) return rc;
+            if (qi == 0 && q->nq == 1) {
+                cudaEventRecord(c->ev[4], s);
+                c->timed_single = true;
+            }
+            SelectParams se{};
+            se.cta_keys = c->d_cta_keys;
+            se.cta_counts = c->d_cta_counts;
+            se.n_lists = pl.launch.grid;
+            se.list_stride = sp.k;
+            se.qid = qi;
+            se.prev = qi ? c->d_list[cur] : nullptr;
+            se.prev_count = qi ? c->d_list_count + cur : nullptr;
+            se.out = c->d_list[cur ^ 1];
+            se.out_count = c->d_list_count + (cur ^ 1);
+            se.tau_out = c->d_tau;
+            se.k = sp.k;
+            se.scratch_keys = c->d_scratch_keys;
+            se.scratch_src = c->d_scratch_src;
+            se.scratch_elems = c->scratch_elems;
+            se.records = (qi + 1 == q->nq) ? d_records_out : nullptr;
+            se.row_base = row_base;
+            se.take_max = sp.take_max;
+            rc = launch_select(se, s);
+            if (rc) return rc;
+            cur ^= 1;
+            c->last.kernel_launches += 2;
+        }
+        cudaEventRecord(c->ev[5], s);
+        run->result_list = cur;
+        run->big = false;
+    } else {
+        // large k: emit every passing candidate, sort everything, keep the best k (per query, with the
+        // running list appended before the sort)
+        if (k_eff >= 0x7FFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "take count too large");
+        const uint64_t n_sort = std::max<uint64_t>(pow2_at_least(n_rows + k_eff), 2048);
+        if (c->emit_cap < n_sort) {
+            OTTERS_CUDA(cudaStreamSynchronize(s));
+            cudaFree(c->d_emit);
+            c->d_emit = nullptr;
+            c->emit_cap = 0;
+            if (cudaMalloc((void**)&c->d_emit, n_sort * sizeof(Cand)) != cudaSuccess)
+                return fail(OTTERS_ERR_NOMEM, "device allocation for the candidate sort failed");
+            c->emit_cap = n_sort;
+        }
+        if (c->list_cap < k_eff) {
+            OTTERS_CUDA(cudaStreamSynchronize(s));
+            cudaFree(c->d_list[0]);
+            c->d_list[0] = nullptr;
+            c->list_cap = 0;
+        }
+        rc = ensure_dev(&c->d_list[0], &c->list_cap, (size_t)std::max<uint64_t>(k_eff, kMaxFusedK), s);
+        if (rc) return rc;
+        sp.emit = c->d_emit;
+        sp.emit_count = c->d_counter + 1;
+        sp.emit_cap = (uint32_t)std::min<uint64_t>(n_sort, 0xFFFFFFFFull);
+        cudaEventRecord(c->ev[2], s);
+        for (uint32_t qi = 0; qi < q->nq; ++qi) {
+            OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(uint32_t), s));
+            sp.query = c->d_query + (size_t)qi * dim_pad;
+            sp.q_inv = q_inv[qi];
+            sp.qid = qi;
+            sp.tau_in = qi ? c->d_tau : nullptr;
+            rc = launch_scan(sp, pl.launch, q->metric, true, s);
+            if (rc) return rc;
+            // the running list lives in d_list[0] (single buffer: it is copied into the sort array first)
+            rc = launch_append_prev(c->d_emit, c->d_counter + 1, qi ? c->d_list[0] : nullptr, qi ? c->d_list_count : nullptr,
+                                    n_sort, s);
+            if (rc) return rc;
+            rc = launch_global_sort(c->d_emit, n_sort, s);
+            if (rc) return rc;
+            rc = launch_take_sorted(c->d_emit, c->d_counter + 1, qi ? c->d_list_count : nullptr, k_eff, c->d_list[0],
+                                    c->d_list_count, c->d_tau, s);
+            if (rc) return rc;
+            c->last.kernel_launches += 4;
+        }
+        if (d_records_out) {
+            rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, row_base, sp.take_max, d_records_out, s);
+            if (rc) return rc;
+        }
+        cudaEventRecord(c->ev[5], s);
+        run->result_list = 0;
+        run->big = true;
+    }
+    return OTTERS_OK;
+}
+
+// copies the result list to the host and decodes it; synchronizes the stream
+static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint64_t row_base, uint64_t* out_idx,
+                         float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, const void* extra_dev,
+                         size_t extra_bytes, void* extra_host) {
+    cudaStream_t s = c->stream;
+    const size_t list_bytes = (size_t)run.k_eff * sizeof(Cand);
+    int rc = ensure_stage(c, list_bytes + 64 + extra_bytes + 64);
+    if (rc) return rc;
+    uint8_t* h = c->h_stage;
+    const size_t off_cnt = round_up(list_bytes, 16);
+    const size_t off_scored = off_cnt + 16;
+    const size_t off_extra = off_scored + 16;
+    if (list_bytes)
+        OTTERS_CUDA(cudaMemcpyAsync(h, c->d_list[run.result_list], list_bytes, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaMemcpyAsync(h + off_cnt, c->d_list_count + run.result_list, 4, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaMemcpyAsync(h + off_scored, c->d_rows_scored, 8, cudaMemcpyDeviceToHost, s));
+    if (extra_bytes) OTTERS_CUDA(cudaMemcpyAsync(h + off_extra, extra_dev, extra_bytes, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaStreamSynchronize(s));
+    uint32_t n = *reinterpret_cast<uint32_t*>(h + off_cnt);
+    c->last.rows_scored = *reinterpret_cast<unsigned long long*>(h + off_scored);
+    if (extra_bytes) memcpy(extra_host, h + off_extra, extra_bytes);
+    const Cand* list = reinterpret_cast<const Cand*>(h);
+    uint64_t m = std::min<uint64_t>(n, cap);
+    for (uint64_t i = 0; i < m; ++i) {
+        if (out_idx) out_idx[i] = row_base + key_row(list[i].key);
+        if (out_score) out_score[i] = key_score(list[i].key, take_max);
+        if (out_qid) out_qid[i] = list[i].qid;
+    }
+    *out_len = n;
+    return OTTERS_OK;
+}
+
+static void finish_work_stats(otters_ctx* c, const VecStorage* st, const otters_vec_query* q) {
+    // only called after the stream was synchronised, so all events have completed
+    float ms = 0.f;
+    if (c->timed_single && cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) c->last.scan_ms = ms;
+    else if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[5]) == cudaSuccess) c->last.scan_ms = ms;
+    if (c->timed_single && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last.select_ms = ms;
+    const uint64_t per_row = (uint64_t)st->dim * 4 + (q->metric == OTTERS_METRIC_COSINE ? 4 : 0);
+    c->last.scan_bytes = c->last.rows_scored * per_row;
+}
+
+static int validate_query(const otters_vec_query* q, uint32_t store_dim, bool meta) {
+    if (!q) return fail(OTTERS_ERR_INVALID, "Query vectors or their norms are not set");
+    if (q->metric < 0 || q->metric > 2) return fail(OTTERS_ERR_INVALID, "Search metric is not set");
+    if (q->take_type != OTTERS_TAKE_MIN && q->take_type != OTTERS_TAKE_MAX) return fail(OTTERS_ERR_INVALID, "invalid take type");
+    if (q->has_filter && (q->cmp < 0 || q->cmp > 4)) return fail(OTTERS_ERR_INVALID, "invalid filter comparator");
+    if (meta) return OTTERS_OK;  // MetaStore swallows the per-chunk validation errors (src/meta_compute.rs:182)
+    if (q->nq == 0) return fail(OTTERS_ERR_INVALID, "No queries provided");  // src/vec.rs:186-188
+    if (!q->queries) return fail(OTTERS_ERR_INVALID, "Query vectors or their norms are not set");
+    if (q->dim != store_dim)  // src/vec.rs:190-198
+        return fail(OTTERS_ERR_INVALID, "Query vector length " + std::to_string(q->dim) + " does not match expected dimension " +
+                                            std::to_string(store_dim));
+    return OTTERS_OK;
+}
+
+}  // namespace otters
+
+// =================================================================================================
+// context API
+// =================================================================================================
+extern "C" const char* otters_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* otters_version(void) { return "otters_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out) {
+    if (!out) return fail(OTTERS_ERR_INVALID, "null output pointer");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(OTTERS_ERR_CUDA, "no CUDA device available: libotters_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(OTTERS_ERR_INVALID, "invalid CUDA device index");
+    OTTERS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OTTERS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(OTTERS_ERR_UNSUPPORTED, std::string("libotters_b200 is built for sm_100a only; device is sm_") +
+                                                std::to_string(prop.major) + std::to_string(prop.minor));
+    std::unique_ptr<otters_ctx> c(new otters_ctx());
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        OTTERS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->grid_max = (uint32_t)c->sm_count * 2;
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_counter, 4 * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMemset(c->d_counter, 0, 4 * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_keys, (size_t)c->grid_max * kMaxFusedK * sizeof(uint64_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_counts, (size_t)c->grid_max * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_list[0], (size_t)kMaxFusedK * sizeof(Cand)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_list[1], (size_t)kMaxFusedK * sizeof(Cand)));
+    c->list_cap = kMaxFusedK;
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_list_count, 2 * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMemset(c->d_list_count, 0, 2 * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_tau, sizeof(uint64_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_rows_scored, sizeof(unsigned long long)));
+    c->scratch_elems = (uint32_t)pow2_at_least((uint64_t)(c->grid_max + 1) * kMaxFusedK);
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_scratch_keys, (size_t)c->scratch_elems * sizeof(uint64_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_scratch_src, (size_t)c->scratch_elems * sizeof(uint32_t)));
+    for (auto& e : c->ev) OTTERS_CUDA(cudaEventCreate(&e));
+    int rc = ensure_stage(c.get(), 1 << 16);
+    if (rc) return rc;
+    *out = c.release();
+    return OTTERS_OK;
+}
+
+extern "C" int otters_ctx_destroy(otters_ctx* c) {
+    if (!c) return OTTERS_OK;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_query);
+    cudaFree(c->d_counter);
+    cudaFree(c->d_cta_keys);
+    cudaFree(c->d_cta_counts);
+    cudaFree(c->d_list[0]);
+    cudaFree(c->d_list[1]);
+    cudaFree(c->d_list_count);
+    cudaFree(c->d_tau);
+    cudaFree(c->d_scratch_keys);
+    cudaFree(c->d_scratch_src);
+    cudaFree(c->d_rows_scored);
+    cudaFree(c->d_mask);
+    cudaFree(c->d_emit);
+    cudaFree(c->d_records);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return OTTERS_OK;
+}
+
+extern "C" int otters_ctx_synchronize(otters_ctx* c) {
+    if (!c) return fail(OTTERS_ERR_INVALID, "null context");
+    DeviceGuard g(c->device);
+    OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+    return OTTERS_OK;
+}
+
+extern "C" int otters_ctx_set_tuning(otters_ctx* c, const otters_scan_tuning* t) {
+    if (!c) return fail(OTTERS_ERR_INVALID, "null context");
+    c->tuning = t ? *t : otters_scan_tuning{};
+    return OTTERS_OK;
+}
+
+extern "C" int otters_ctx_last_work(otters_ctx* c, otters_last_work* out) {
+    if (!c || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    *out = c->last;
+    return OTTERS_OK;
+}
+
+// =================================================================================================
+// VecStore
+// =================================================================================================
+struct otters_vecstore {
+    VecStorage st;
+};
+
+extern "C" int otters_vecstore_create(otters_ctx* c, uint32_t dim, otters_vecstore** out) {
+    if (!c || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    auto* vs = new otters_vecstore();
+    vs->st.ctx = c;
+    vs->st.dim = dim;
+    vs->st.pitch = (uint32_t)round_up(std::max<uint32_t>(dim, 1), 4);
+    *out = vs;
+    return OTTERS_OK;
+}
+
+extern "C" int otters_vecstore_destroy(otters_vecstore* vs) {
+    if (!vs) return OTTERS_OK;
+    DeviceGuard g(vs->st.ctx->device);
+    cudaStreamSynchronize(vs->st.ctx->stream);
+    vs->st.release();
+    delete vs;
+    return OTTERS_OK;
+}
+
+extern "C" int otters_vecstore_reserve(otters_vecstore* vs, uint64_t n_rows) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    DeviceGuard g(vs->st.ctx->device);
+    return vs->st.reserve(n_rows);
+}
+
+extern "C" int otters_vecstore_add(otters_vecstore* vs, const float* rows, uint64_t n) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    if (n && !rows) return fail(OTTERS_ERR_INVALID, "null rows");
+    if (n && vs->st.dim == 0) return fail(OTTERS_ERR_INVALID, "Input vector length 0 does not match expected dimension 0");
+    DeviceGuard g(vs->st.ctx->device);
+    return vs->st.add(rows, n, cudaMemcpyHostToDevice);
+}
+
+extern "C" int otters_vecstore_add_device(otters_vecstore* vs, const float* d_rows, uint64_t n) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    if (n && !d_rows) return fail(OTTERS_ERR_INVALID, "null rows");
+    DeviceGuard g(vs->st.ctx->device);
+    return vs->st.add(d_rows, n, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int otters_vecstore_add_synthetic(otters_vecstore* vs, uint64_t first_row, uint64_t n, uint64_t seed) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    DeviceGuard g(vs->st.ctx->device);
+    return vs->st.add_synth(first_row, n, seed);
+}
+
+extern "C" uint64_t otters_vecstore_len(const otters_vecstore* vs) { return vs ? vs->st.n : 0; }
+extern "C" uint32_t otters_vecstore_dim(const otters_vecstore* vs) { return vs ? vs->st.dim : 0; }
+
+extern "C" int otters_vecstore_inv_norms(const otters_vecstore* vs, uint64_t first, uint64_t n, float* out) {
+    if (!vs || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    if (first + n > vs->st.n) return fail(OTTERS_ERR_INVALID, "row range out of bounds");
+    DeviceGuard g(vs->st.ctx->device);
+    OTTERS_CUDA(cudaStreamSynchronize(vs->st.ctx->stream));
+    if (n) OTTERS_CUDA(cudaMemcpy(out, vs->st.d_inv + first, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return OTTERS_OK;
+}
+
+namespace otters {
+// uploads a user row mask (Lsb0 u64 words) as 32-bit words, bits past row_mask_bits set to "keep"
+static int upload_row_mask(otters_ctx* c, const otters_vec_query* q, uint64_t n_rows, const uint32_t** d_mask, uint32_t* words) {
+    *d_mask = nullptr;
+    *words = 0;
+    if (!q->row_mask_words) return OTTERS_OK;
+    const uint64_t bits = std::min<uint64_t>(q->row_mask_bits, n_rows);
+    const uint64_t w32 = (bits + 31) / 32;
+    if (w32 == 0) return OTTERS_OK;
+    int rc = ensure_stage(c, w32 * 4 + 64);
+    if (rc) return rc;
+    rc = ensure_dev(&c->d_mask, &c->d_mask_words, w32, c->stream);
+    if (rc) return rc;
+    uint32_t* h = reinterpret_cast<uint32_t*>(c->h_stage);
+    for (uint64_t i = 0; i < w32; ++i) {
+        uint64_t w = q->row_mask_words[i >> 1];
+        h[i] = (uint32_t)(i & 1 ? (w >> 32) : w);
+    }
+    if (bits & 31) h[w32 - 1] |= ~0u << (bits & 31);  // rows >= mask length are kept (src/vec.rs:234,297)
+    OTTERS_CUDA(cudaMemcpyAsync(c->d_mask, h, w32 * 4, cudaMemcpyHostToDevice, c->stream));
+    // the staging buffer is reused by run_queries: make sure the copy has been consumed
+    OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+    *d_mask = c->d_mask;
+    *words = (uint32_t)w32;
+    return OTTERS_OK;
+}
+}  // namespace otters
+
+extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query* q, uint64_t* out_idx, float* out_score,
+                                     uint32_t* out_qid, uint64_t cap, uint64_t* out_len) {
+    if (!vs || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
+    int rc = validate_query(q, vs->st.dim, false);
+    if (rc) return rc;
+    otters_ctx* c = vs->st.ctx;
+    DeviceGuard g(c->device);
+    *out_len = 0;
+    c->last = otters_last_work{};
+    if (q->k == 0 || vs->st.n == 0) return OTTERS_OK;  // take(0) / empty store (tests/vec_store_tests.rs:430-445,488-499)
+    const uint32_t* d_mask = nullptr;
+    uint32_t mask_words = 0;
+    rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
+    if (rc) return rc;
+    QueryRun run;
+    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, 0, &run);
+    if (rc) return rc;
+    rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr, 0, nullptr);
+    if (rc) return rc;
+    finish_work_stats(c, &vs->st, q);
+    return OTTERS_OK;
+}
+
+// =================================================================================================
+// MetaStore
+// =================================================================================================
+namespace otters {
+
+struct MetaColumn {
+    std::string name;
+    int32_t dtype = 0;
+    // device
+    void* d_values = nullptr;
+    uint32_t* d_nulls = nullptr;
+    void* d_zmin = nullptr;
+    void* d_zmax = nullptr;
+    uint32_t* d_non_null = nullptr;
+    uint64_t* d_bloom = nullptr;
+    uint64_t bloom_stride = 0;
+    uint64_t* d_bloom_mbits = nullptr;
+    uint32_t* d_bloom_k = nullptr;
+    // host copies kept for the parity exports
+    std::vector<int64_t> zmin_i, zmax_i;
+    std::vector<double> zmin_f, zmax_f;
+    std::vector<uint32_t> non_null;
+    // string dictionary
+    std::unordered_map<std::string, uint32_t> dict;
+    size_t value_bytes = 0;
+};
+
+// Bloom filter spec of this repo (fastbloom's layout is not reproducible offline)
+static inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static void bloom_hash(const uint8_t* s, uint64_t len, uint64_t* h1, uint64_t* h2) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (uint64_t i = 0; i < len; ++i) {
+        h ^= s[i];
+        h *= 0x100000001B3ull;
+    }
+    *h1 = mix64(h);
+    *h2 = mix64(h ^ 0x9E3779B97F4A7C15ull) | 1ull;
+}
+static void bloom_params(uint64_t n_items, int mode, double fpr, uint64_t bits, uint64_t* m_bits, uint32_t* k_hashes) {
+    const uint64_t n = n_items ? n_items : 1;
+    uint64_t m;
+    if (mode == 0) {
+        const double ln2 = 0.6931471805599453;
+        double mm = ceil(-(double)n * log(fpr) / (ln2 * ln2));
+        m = mm < 64.0 ? 64 : (uint64_t)mm;
+    } else {
+        m = bits < 64 ? 64 : bits;
+    }
+    m = (m + 63) / 64 * 64;
+    double kk = floor((double)m / (double)n * 0.6931471805599453 + 0.5);
+    *k_hashes = kk < 1.0 ? 1u : (kk > 16.0 ? 16u : (uint32_t)kk);
+    *m_bits = m;
+}
+
+// Rust `as` casts used by the reference when it narrows literals (src/meta_compute.rs:244-288)
+static inline int32_t i64_as_i32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }
+
+}  // namespace otters
+
+struct otters_metastore {
+    otters_ctx* ctx = nullptr;
+    VecStorage st;
+    uint64_t chunk_size = 1024;
+    uint64_t n_chunks = 0;
+    std::vector<MetaColumn> cols;
+    DevColumn* d_cols = nullptr;
+    uint32_t* d_chunk_keep = nullptr;
+    uint32_t* d_row_mask = nullptr;
+    unsigned long long* d_stats = nullptr;
+    uint8_t* d_filter = nullptr;
+    size_t d_filter_bytes = 0;
+    bool has_stats = false;
+    otters_query_stats last{};
+};
+
+extern "C" int otters_metastore_destroy(otters_metastore* ms) {
+    if (!ms) return OTTERS_OK;
+    DeviceGuard g(ms->ctx->device);
+    cudaStreamSynchronize(ms->ctx->stream);
+    for (auto& c : ms->cols) {
+        cudaFree(c.d_values);
+        cudaFree(c.d_nulls);
+        cudaFree(c.d_zmin);
+        cudaFree(c.d_zmax);
+        cudaFree(c.d_non_null);
+        cudaFree(c.d_bloom);
+        cudaFree(c.d_bloom_mbits);
+        cudaFree(c.d_bloom_k);
+    }
+    cudaFree(ms->d_cols);
+    cudaFree(ms->d_chunk_keep);
+    cudaFree(ms->d_row_mask);
+    cudaFree(ms->d_stats);
+    cudaFree(ms->d_filter);
+    ms->st.release();
+    delete ms;
+    return OTTERS_OK;
+}
+
+namespace otters {
+
+template <typename T>
+static int upload(T** dptr, const void* src, size_t bytes) {
+    *dptr = nullptr;
+    if (cudaMalloc((void**)dptr, std::max<size_t>(bytes, 16)) != cudaSuccess)
+        return fail(OTTERS_ERR_NOMEM, "device allocation for metadata failed");
+    if (bytes) OTTERS_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+    return OTTERS_OK;
+}
+
+static inline bool host_is_null(const otters_column& c, uint64_t row) {
+    return c.null_words ? ((c.null_words[row >> 6] >> (row & 63)) & 1ull) != 0 : false;
+}
+
+// build_zone_stat_for_range (reference src/meta_compute.rs:32-132) + packed ranges (src/meta.rs:237-271)
+static int build_column(otters_metastore* ms, const otters_column& in, const otters_build_params* p, double bloom_fpr,
+                        uint64_t bloom_bits, MetaColumn* mc) {
+    const uint64_t n = p->n_rows, cs = ms->chunk_size, nc = ms->n_chunks;
+    mc->name = in.name ? in.name : "";
+    mc->dtype = in.dtype;
+    mc->non_null.assign(nc, 0);
+    int rc;
+    // null bitmap: same bytes, viewed as 32-bit words on the device
+    if (in.null_words) {
+        const size_t w64 = (n + 63) / 64;
+        rc = upload(&mc->d_nulls, in.null_words, w64 * 8);
+        if (rc) return rc;
+    }
+    auto chunk_range = [&](uint64_t ch, uint64_t* s, uint64_t* e) {
+        *s = ch * cs;
+        *e = std::min<uint64_t>(*s + cs, n);
+    };
+    switch (in.dtype) {
+    case OTTERS_DTYPE_INT32: {
+        if (n && !in.values) return fail(OTTERS_ERR_INVALID, "expected Int32 column");
+        const int32_t* v = (const int32_t*)in.values;
+        std::vector<int32_t> mn(nc), mx(nc);
+        mc->zmin_i.resize(nc);
+        mc->zmax_i.resize(nc);
+        for (uint64_t ch = 0; ch < nc; ++ch) {
+            uint64_t s, e;
+            chunk_range(ch, &s, &e);
+            int64_t lo = INT64_MAX, hi = INT64_MIN;
+            uint32_t cnt = 0;
+            for (uint64_t i = s; i < e; ++i)
+                if (!host_is_null(in, i)) {
+                    lo = std::min<int64_t>(lo, v[i]);
+                    hi = std::max<int64_t>(hi, v[i]);
+                    ++cnt;
+                }
+            mn[ch] = i64_as_i32(lo);  // `*min as i32` (src/meta.rs:254-255)
+            mx[ch] = i64_as_i32(hi);
+            mc->zmin_i[ch] = mn[ch];
+            mc->zmax_i[ch] = mx[ch];
+            mc->non_null[ch] = cnt;
+        }
+        if ((rc = upload(&mc->d_values, v, n * 4))) return rc;
+        if ((rc = upload(&mc->d_zmin, mn.data(), nc * 4))) return rc;
+        if ((rc = upload(&mc->d_zmax, mx.data(), nc * 4))) return rc;
+        mc->value_bytes = 4;
+        break;
+    }
+    case OTTERS_DTYPE_INT64:
+    case OTTERS_DTYPE_DATETIME: {
+        if (n && !in.values) return fail(OTTERS_ERR_INVALID, "expected Int64/DateTime column");
+        const int64_t* v = (const int64_t*)in.values;
+        mc->zmin_i.resize(nc);
+        mc->zmax_i.resize(nc);
+        for (uint64_t ch = 0; ch < nc; ++ch) {
+            uint64_t s, e;
+            chunk_range(ch, &s, &e);
+            int64_t lo = INT64_MAX, hi = INT64_MIN;
+            uint32_t cnt = 0;
+            for (uint64_t i = s; i < e; ++i)
+                if (!host_is_null(in, i)) {
+                    lo = std::min(lo, v[i]);
+                    hi = std::max(hi, v[i]);
+                    ++cnt;
+                }
+            mc->zmin_i[ch] = lo;
+            mc->zmax_i[ch] = hi;
+            mc->non_null[ch] = cnt;
+        }
+        if ((rc = upload(&mc->d_values, v, n * 8))) return rc;
+        if ((rc = upload(&mc->d_zmin, mc->zmin_i.data(), nc * 8))) return rc;
+        if ((rc = upload(&mc->d_zmax, mc->zmax_i.data(), nc * 8))) return rc;
+        mc->value_bytes = 8;
+        break;
+    }
+    case OTTERS_DTYPE_FLOAT32: {
+        if (n && !in.values) return fail(OTTERS_ERR_INVALID, "expected Float32 column");
+        const float* v = (const float*)in.values;
+        std::vector<float> mn(nc), mx(nc);
+        mc->zmin_f.resize(nc);
+        mc->zmax_f.resize(nc);
+        for (uint64_t ch = 0; ch < nc; ++ch) {
+            uint64_t s, e;
+            chunk_range(ch, &s, &e);
+            double lo = INFINITY, hi = -INFINITY;  // f64::min/max ignore NaN (src/meta_compute.rs:69-83)
+            uint32_t cnt = 0;
+            for (uint64_t i = s; i < e; ++i)
+                if (!host_is_null(in, i)) {
+                    lo = fmin(lo, (double)v[i]);
+                    hi = fmax(hi, (double)v[i]);
+                    ++cnt;
+                }
+            mn[ch] = (float)lo;
+            mx[ch] = (float)hi;
+            mc->zmin_f[ch] = mn[ch];
+            mc->zmax_f[ch] = mx[ch];
+            mc->non_null[ch] = cnt;
+        }
+        if ((rc = upload(&mc->d_values, v, n * 4))) return rc;
+        if ((rc = upload(&mc->d_zmin, mn.data(), nc * 4))) return rc;
+        if ((rc = upload(&mc->d_zmax, mx.data(), nc * 4))) return rc;
+        mc->value_bytes = 4;
+        break;
+    }
+    case OTTERS_DTYPE_FLOAT64: {
+        if (n && !in.values) return fail(OTTERS_ERR_INVALID, "expected Float64 column");
+        const double* v = (const double*)in.values;
+        mc->zmin_f.resize(nc);
+        mc->zmax_f.resize(nc);
+        for (uint64_t ch = 0; ch < nc; ++ch) {
+            uint64_t s, e;
+            chunk_range(ch, &s, &e);
+            double lo = INFINITY, hi = -INFINITY;
+            uint32_t cnt = 0;
+            for (uint64_t i = s; i < e; ++i)
+                if (!host_is_null(in, i)) {
+                    lo = fmin(lo, v[i]);
+                    hi = fmax(hi, v[i]);
+                    ++cnt;
+                }
+            mc->zmin_f[ch] = lo;
+            mc->zmax_f[ch] = hi;
+            mc->non_null[ch] = cnt;
+        }
+        if ((rc = upload(&mc->d_values, v, n * 8))) return rc;
+        if ((rc = upload(&mc->d_zmin, mc->zmin_f.data(), nc * 8))) return rc;
+        if ((rc = upload(&mc->d_zmax, mc->zmax_f.data(), nc * 8))) return rc;
+        mc->value_bytes = 8;
+        break;
+    }
+    case OTTERS_DTYPE_STRING: {
+        if (n && (!in.str_offsets || (!in.str_bytes && in.str_offsets[n] != 0)))
+            return fail(OTTERS_ERR_INVALID, "expected String column");
+        // dictionary codes (device compares u32 codes; byte equality <=> code equality)
+        std::vector<uint32_t> codes(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            if (host_is_null(in, i)) {
+                codes[i] = 0xFFFFFFFFu;
+                continue;
+            }
+            std::string sv((const char*)in.str_bytes + in.str_offsets[i], in.str_offsets[i + 1] - in.str_offsets[i]);
+            auto it = mc->dict.find(sv);
+            if (it == mc->dict.end()) it = mc->dict.emplace(std::move(sv), (uint32_t)mc->dict.size()).first;
+            codes[i] = it->second;
+        }
+        // per-chunk Bloom filters sized for the chunk length (src/meta_compute.rs:99-116)
+        uint64_t m0;
+        uint32_t k0;
+        bloom_params(std::min<uint64_t>(cs, std::max<uint64_t>(n, 1)), p->bloom_mode, bloom_fpr, bloom_bits, &m0, &k0);
+        mc->bloom_stride = m0 / 64;
+        std::vector<uint64_t> words(std::max<uint64_t>(nc, 1) * mc->bloom_stride, 0);
+        std::vector<uint64_t> mbits(std::max<uint64_t>(nc, 1), 64);
+        std::vector<uint32_t> kh(std::max<uint64_t>(nc, 1), 1);
+        for (uint64_t ch = 0; ch < nc; ++ch) {
+            uint64_t s, e;
+            chunk_range(ch, &s, &e);
+            bloom_params(e - s, p->bloom_mode, bloom_fpr, bloom_bits, &mbits[ch], &kh[ch]);
+            uint64_t* w = words.data() + ch * mc->bloom_stride;
+            uint32_t cnt = 0;
+            for (uint64_t i = s; i < e; ++i)
+                if (!host_is_null(in, i)) {
+                    uint64_t h1, h2;
+                    bloom_hash(in.str_bytes + in.str_offsets[i], in.str_offsets[i + 1] - in.str_offsets[i], &h1, &h2);
+                    for (uint32_t j = 0; j < kh[ch]; ++j) {
+                        uint64_t bit = (h1 + (uint64_t)j * h2) % mbits[ch];
+                        w[bit >> 6] |= 1ull << (bit & 63);
+                    }
+                    ++cnt;
+                }
+            mc->non_null[ch] = cnt;
+        }
+        if ((rc = upload(&mc->d_values, codes.data(), n * 4))) return rc;
+        if ((rc = upload(&mc->d_bloom, words.data(), words.size() * 8))) return rc;
+        if ((rc = upload(&mc->d_bloom_mbits, mbits.data(), mbits.size() * 8))) return rc;
+        if ((rc = upload(&mc->d_bloom_k, kh.data(), kh.size() * 4))) return rc;
+        mc->value_bytes = 4;
+        break;
+    }
+    default: return fail(OTTERS_ERR_INVALID, "unknown column dtype");
+    }
+    if ((rc = upload(&mc->d_non_null, mc->non_null.data(), nc * 4))) return rc;
+    return OTTERS_OK;
+}
+
+}  // namespace otters
+
+extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* p, otters_metastore** out,
+                                      otters_build_stats* stats) {
+    if (!c || !p || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    DeviceGuard g(c->device);
+    const double t_build = now_s();
+    if (p->vectors_kind != OTTERS_VECTORS_SYNTHETIC && p->n_rows && !p->vectors)
+        return fail(OTTERS_ERR_INVALID, "vectors must be provided to build MetaStore");  // src/meta.rs:153-155
+    if (p->dim == 0 && p->n_rows > 0) return fail(OTTERS_ERR_INVALID, "vector dimension cannot be zero");  // :177-179
+    if (p->n_columns && !p->columns) return fail(OTTERS_ERR_INVALID, "null columns");
+    std::unique_ptr<otters_metastore> ms(new otters_metastore());
+    ms->ctx = c;
+    ms->chunk_size = std::max<uint64_t>(p->chunk_size, 1);  // src/meta.rs:86-89
+    if (ms->chunk_size > 0xFFFFFFFFull) ms->chunk_size = 0xFFFFFFFFull;
+    ms->n_chunks = (p->n_rows + ms->chunk_size - 1) / ms->chunk_size;
+    double fpr = p->bloom_fpr;
+    uint64_t bits = p->bloom_bits;
+    if (p->bloom_mode == 0) {  // src/meta.rs:92-101
+        if (!std::isfinite(fpr)) fpr = 0.01;
+        fpr = std::min(std::max(fpr, 1e-2), 0.5);
+    } else {
+        bits = std::max<uint64_t>(bits, 64);  // src/meta.rs:106-110
+    }
+    ms->st.ctx = c;
+    ms->st.dim = p->dim;
+    ms->st.pitch = (uint32_t)round_up(std::max<uint32_t>(p->dim, 1), 4);
+
+    auto cleanup = [&](int rc) {
+        otters_metastore_destroy(ms.release());
+        return rc;
+    };
+    // vectors ingest (VecStore::add_vectors per chunk in the reference, src/meta.rs:209-212)
+    const double t_ing = now_s();
+    int rc = OTTERS_OK;
+    if (p->vectors_kind == OTTERS_VECTORS_HOST) rc = ms->st.add(p->vectors, p->n_rows, cudaMemcpyHostToDevice);
+    else if (p->vectors_kind == OTTERS_VECTORS_DEVICE) rc = ms->st.add(p->vectors, p->n_rows, cudaMemcpyDeviceToDevice);
+    else if (p->vectors_kind == OTTERS_VECTORS_SYNTHETIC) rc = ms->st.add_synth(p->synthetic_first_row, p->n_rows, p->synthetic_seed);
+    else rc = fail(OTTERS_ERR_INVALID, "invalid vectors_kind");
+    if (rc) return cleanup(rc);
+    const double ingest_s = now_s() - t_ing;
+
+    // zonemaps, Bloom filters, dictionary codes
+    const double t_zone = now_s();
+    ms->cols.resize(p->n_columns);
+    std::vector<DevColumn> dcols(std::max<uint32_t>(p->n_columns, 1));
+    for (uint32_t i = 0; i < p->n_columns; ++i) {
+        rc = build_column(ms.get(), p->columns[i], p, fpr, bits, &ms->cols[i]);
+        if (rc) return cleanup(rc);
+        const MetaColumn& mc = ms->cols[i];
+        DevColumn& d = dcols[i];
+        d.dtype = mc.dtype;
+        d.values = mc.d_values;
+        d.null_words = mc.d_nulls;
+        d.zmin = mc.d_zmin;
+        d.zmax = mc.d_zmax;
+        d.non_null = mc.d_non_null;
+        d.bloom = mc.d_bloom;
+        d.bloom_stride = mc.bloom_stride;
+        d.bloom_mbits = mc.d_bloom_mbits;
+        d.bloom_k = mc.d_bloom_k;
+    }
+    if ((rc = upload(&ms->d_cols, dcols.data(), dcols.size() * sizeof(DevColumn)))) return cleanup(rc);
+    const double zone_s = now_s() - t_zone;
+
+    const size_t keep_words = (ms->n_chunks + 31) / 32 + 1, mask_words = (p->n_rows + 31) / 32 + 1;
+    if (cudaMalloc((void**)&ms->d_chunk_keep, keep_words * 4) != cudaSuccess ||
+        cudaMalloc((void**)&ms->d_row_mask, mask_words * 4) != cudaSuccess ||
+        cudaMalloc((void**)&ms->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess)
+        return cleanup(fail(OTTERS_ERR_NOMEM, "device allocation for masks failed"));
+    if (stats) {  // src/meta.rs:292-299
+        stats->n_rows = p->n_rows;
+        stats->dim = p->dim;
+        stats->n_chunks = ms->n_chunks;
+        stats->vectors_ingest_s = ingest_s;
+        stats->zonemap_build_s = zone_s;
+        stats->build_total_s = now_s() - t_build;
+    }
+    *out = ms.release();
+    return OTTERS_OK;
+}
+
+extern "C" uint64_t otters_metastore_n_chunks(const otters_metastore* ms) { return ms ? ms->n_chunks : 0; }
+extern "C" uint64_t otters_metastore_chunk_size(const otters_metastore* ms) { return ms ? ms->chunk_size : 0; }
+extern "C" uint64_t otters_metastore_len(const otters_metastore* ms) { return ms ? ms->st.n : 0; }
+
+namespace otters {
+
+// Lowers the caller's CompiledFilter into device leaves: literal casts follow the reference
+// (src/meta.rs:431-521 for zonemaps, src/meta_compute.rs:244-288 for rows).  Leaf/column type
+// combinations that Expr::compile can never produce (src/expr.rs:385-466) are rejected.
+static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vector<uint32_t>* offs, std::vector<DevLeaf>* leaves) {
+    offs->clear();
+    leaves->clear();
+    if (!f->clause_offsets || (!f->leaves && f->n_clauses && f->clause_offsets[f->n_clauses]))
+        return fail(OTTERS_ERR_INVALID, "malformed filter");
+    for (uint32_t ci = 0; ci <= f->n_clauses; ++ci) offs->push_back(f->clause_offsets[ci]);
+    const uint32_t nl = f->clause_offsets[f->n_clauses];
+    for (uint32_t li = 0; li < nl; ++li) {
+        const otters_leaf& in = f->leaves[li];
+        if (in.col >= ms->cols.size()) return fail(OTTERS_ERR_INVALID, "Unknown column '" + std::to_string(in.col) + "'");
+        if (in.op < 0 || in.op > 5) return fail(OTTERS_ERR_INVALID, "invalid comparison operator");
+        MetaColumn& mc = ms->cols[in.col];
+        DevLeaf d{};
+        d.col = in.col;
+        d.op = in.op;
+        switch (mc.dtype) {
+        case OTTERS_DTYPE_INT32:
+            if (in.kind != OTTERS_LIT_I64)
+                return fail(OTTERS_ERR_INVALID, "Type mismatch for column '" + mc.name + "': expected Int32, got literal " +
+                                                    (in.kind == OTTERS_LIT_F64 ? "float" : "string"));
+            d.exec = LEAF_I32;
+            d.i32 = i64_as_i32(in.i);
+            break;
+        case OTTERS_DTYPE_INT64:
+        case OTTERS_DTYPE_DATETIME:
+            if (in.kind != OTTERS_LIT_I64)
+                return fail(OTTERS_ERR_INVALID, "Type mismatch for column '" + mc.name + "': expected " +
+                                                    (mc.dtype == OTTERS_DTYPE_INT64 ? "Int64" : "DateTime") + ", got literal " +
+                                                    (in.kind == OTTERS_LIT_F64 ? "float" : "string"));
+            d.exec = LEAF_I64;
+            d.i64 = in.i;
+            break;
+        case OTTERS_DTYPE_FLOAT32:
+            if (in.kind != OTTERS_LIT_F64)
+                return fail(OTTERS_ERR_INVALID, "Type mismatch for column '" + mc.name + "': expected Float32 literal widened to f64");
+            d.exec = LEAF_F32;
+            d.f32 = (float)in.f;
+            break;
+        case OTTERS_DTYPE_FLOAT64:
+            if (in.kind != OTTERS_LIT_F64)
+                return fail(OTTERS_ERR_INVALID, "Type mismatch for column '" + mc.name + "': expected Float64 literal widened to f64");
+            d.exec = LEAF_F64;
+            d.f64 = in.f;
+            break;
+        case OTTERS_DTYPE_STRING: {
+            if (in.kind != OTTERS_LIT_STR)
+                return fail(OTTERS_ERR_INVALID, "Type mismatch for column '" + mc.name + "': expected String, got literal string");
+            if (in.op != OTTERS_OP_EQ && in.op != OTTERS_OP_NEQ)
+                return fail(OTTERS_ERR_INVALID, "Unsupported comparator for string column '" + mc.name + "'");
+            d.exec = LEAF_STR;
+            std::string lit((const char*)in.s, in.slen);
+            auto it = mc.dict.find(lit);
+            d.code_valid = it != mc.dict.end();
+            d.code = d.code_valid ? it->second : 0;
+            bloom_hash((const uint8_t*)lit.data(), lit.size(), &d.h1, &d.h2);
+            break;
+        }
+        default: return fail(OTTERS_ERR_INVALID, "unknown column dtype");
+        }
+        leaves->push_back(d);
+    }
+    return OTTERS_OK;
+}
+
+// enqueues K0 (+K0b); leaves chunk_keep / row_mask / stats on the device
+static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_t nq, bool want_row_mask, uint64_t* meta_bytes) {
+    otters_ctx* c = ms->ctx;
+    cudaStream_t s = c->stream;
+    MetaKernelParams mp{};
+    mp.cols = ms->d_cols;
+    mp.n_rows = (uint32_t)ms->st.n;
+    mp.chunk_size = (uint32_t)ms->chunk_size;
+    mp.n_chunks = (uint32_t)ms->n_chunks;
+    mp.nq = nq;
+    mp.chunk_keep = ms->d_chunk_keep;
+    mp.row_mask = ms->d_row_mask;
+    mp.stats = ms->d_stats;
+    *meta_bytes = 0;
+    OTTERS_CUDA(cudaMemsetAsync(ms->d_stats, 0, 4 * sizeof(unsigned long long), s));
+    if (!f) {
+        c->last.kernel_launches += 1;
+        return launch_count_all_chunks(mp, s);
+    }
+    std::vector<uint32_t> offs;
+    std::vector<DevLeaf> leaves;
+    int rc = lower_filter(ms, f, &offs, &leaves);
+    if (rc) return rc;
+    const size_t off_bytes = round_up(offs.size() * 4, 16);
+    const size_t total = off_bytes + leaves.size() * sizeof(DevLeaf);
+    rc = ensure_stage(c, total + 64);
+    if (rc) return rc;
+    rc = ensure_dev(&ms->d_filter, &ms->d_filter_bytes, total + 16, s);
+    if (rc) return rc;
+    // the staging buffer may still be in flight for a previous async copy on this stream only if the
+    // previous call did not synchronise; every query path synchronises before returning.
+    memcpy(c->h_stage, offs.data(), offs.size() * 4);
+    if (!leaves.empty()) memcpy(c->h_stage + off_bytes, leaves.data(), leaves.size() * sizeof(DevLeaf));
+    OTTERS_CUDA(cudaMemcpyAsync(ms->d_filter, c->h_stage, total, cudaMemcpyHostToDevice, s));
+    OTTERS_CUDA(cudaStreamSynchronize(s));  // staging buffer is reused for the queries next
+    mp.clause_off = reinterpret_cast<const uint32_t*>(ms->d_filter);
+    mp.leaves = reinterpret_cast<const DevLeaf*>(ms->d_filter + off_bytes);
+    mp.n_clauses = f->n_clauses;
+    cudaEventRecord(c->ev[0], s);
+    rc = launch_prune(mp, s);
+    if (rc) return rc;
+    cudaEventRecord(c->ev[1], s);
+    c->last.kernel_launches += 1;
+    if (want_row_mask) {
+        rc = launch_rowmask(mp, s);
+        if (rc) return rc;
+        c->last.kernel_launches += 1;
+        cudaEventRecord(c->ev[6], s);
+    }
+    // algorithmic metadata bytes: zonemap entries per leaf + column values/null bits of evaluated rows are
+    // accounted by the caller once the evaluated-chunk count is known
+    return OTTERS_OK;
+}
+
+static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                           otters_topk_record* d_records, uint64_t row_base, uint64_t* out_idx, float* out_score,
+                           uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
+    const double t_total = now_s();
+    otters_ctx* c = ms->ctx;
+    int rc = validate_query(q, ms->st.dim, true);
+    if (rc) return rc;
+    if (q->row_mask_words) return fail(OTTERS_ERR_INVALID, "row masks are not part of MetaQueryPlan");
+    c->last = otters_last_work{};
+    if (out_len) *out_len = 0;
+    cudaStream_t s = c->stream;
+    // per-chunk collect() errors are swallowed by the reference (src/meta_compute.rs:182): an empty
+    // batch or a wrong-dimension query returns no rows but still reports stats
+    const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
+    const bool scan = !chunk_err && q->k > 0 && ms->st.n > 0;
+    uint64_t meta_bytes = 0;
+    rc = run_meta_filter(ms, filter, q->nq, scan && filter, &meta_bytes);
+    if (rc) return rc;
+    unsigned long long hstats[4] = {0, 0, 0, 0};
+    uint64_t n_out = 0;
+    if (scan) {
+        QueryRun run;
+        rc = run_queries(c, &ms->st, q, filter ? ms->d_row_mask : nullptr, filter ? (uint32_t)((ms->st.n + 31) / 32) : 0,
+                         d_records, row_base, &run);
+        if (rc) return rc;
+        if (!d_records || stats || out_len) {
+            if (d_records) {
+                // device-resident result: only the stats come back
+                OTTERS_CUDA(cudaMemcpyAsync(c->h_stage, ms->d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
+                OTTERS_CUDA(cudaStreamSynchronize(s));
+                memcpy(hstats, c->h_stage, sizeof(hstats));
+            } else {
+                rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, row_base, out_idx, out_score, out_qid, cap, &n_out,
+                                   ms->d_stats, sizeof(hstats), hstats);
+                if (rc) return rc;
+                finish_work_stats(c, &ms->st, q);
+            }
+        }
+    } else {
+        if (d_records) {
+            // no scan: the record buffer must still hold k empty slots
+            const uint64_t k_eff = std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq);
+            if (k_eff) {
+                OTTERS_CUDA(cudaMemsetAsync(c->d_list_count, 0, 2 * sizeof(uint32_t), s));
+                rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, row_base, 1, d_records, s);
+                if (rc) return rc;
+            }
+        }
+        OTTERS_CUDA(cudaMemcpyAsync(c->h_stage, ms->d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        memcpy(hstats, c->h_stage, sizeof(hstats));
+    }
+    if (out_len) *out_len = n_out;
+    // stats (src/meta.rs:711-721)
+    otters_query_stats st{};
+    st.total_chunks = ms->n_chunks;
+    st.evaluated_chunks = hstats[0];
+    st.pruned_chunks = st.total_chunks - st.evaluated_chunks;
+    st.vectors_compared = hstats[1];
+    // every path above synchronised the stream unless the result stays on the device without stats
+    const bool synced = !(d_records && !stats && !out_len && scan);
+    float ms_f = 0.f;
+    if (synced && filter) {
+        if (cudaEventElapsedTime(&ms_f, c->ev[0], c->ev[1]) == cudaSuccess) {
+            st.prune_s = ms_f * 1e-3;
+            c->last.prune_ms = ms_f;
+        }
+        if (scan && cudaEventElapsedTime(&ms_f, c->ev[1], c->ev[6]) == cudaSuccess) c->last.rowmask_ms = ms_f;
+    }
+    if (synced && scan) {
+        if (cudaEventElapsedTime(&ms_f, c->ev[2], c->ev[5]) == cudaSuccess) st.score_s = ms_f * 1e-3 + c->last.rowmask_ms * 1e-3;
+        if (c->timed_single && cudaEventElapsedTime(&ms_f, c->ev[4], c->ev[5]) == cudaSuccess) {
+            st.merge_s = ms_f * 1e-3;
+            st.score_s -= st.merge_s;
+            c->last.select_ms = ms_f;
+        }
+    }
+    // algorithmic bytes of the metadata kernels
+    if (filter) {
+        uint64_t leaf_zm = 0, leaf_row = 0;
+        const uint32_t nl = filter->clause_offsets[filter->n_clauses];
+        for (uint32_t li = 0; li < nl; ++li) {
+            const MetaColumn& mc = ms->cols[filter->leaves[li].col];
+            leaf_zm += 2 * mc.value_bytes + 4;
+            leaf_row += mc.value_bytes;
+        }
+        const uint64_t rows_eval = q->nq ? st.vectors_compared / q->nq : 0;
+        c->last.meta_bytes = ms->n_chunks * leaf_zm + (scan ? rows_eval * leaf_row + rows_eval / 8 * nl + ms->st.n / 8 : 0);
+    }
+    st.total_s = now_s() - t_total;
+    ms->last = st;
+    ms->has_stats = true;
+    if (stats) *stats = st;
+    return OTTERS_OK;
+}
+
+}  // namespace otters
+
+extern "C" int otters_metastore_query(otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                                      uint64_t* out_idx, float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len,
+                                      otters_query_stats* stats) {
+    if (!ms || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
+    DeviceGuard g(ms->ctx->device);
+    return meta_query_impl(ms, q, filter, nullptr, 0, out_idx, out_score, out_qid, cap, out_len, stats);
+}
+
+extern "C" int otters_metastore_last_stats(const otters_metastore* ms, otters_query_stats* out) {
+    if (!ms || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    if (!ms->has_stats) return fail(OTTERS_ERR_INVALID, "(no query stats)");
+    *out = ms->last;
+    return OTTERS_OK;
+}
+
+namespace otters {
+static int export_mask(otters_metastore* ms, const otters_filter* filter, bool rows, uint8_t* keep) {
+    otters_ctx* c = ms->ctx;
+    uint64_t mb;
+    int rc = run_meta_filter(ms, filter, 1, rows, &mb);
+    if (rc) return rc;
+    const uint64_t n = rows ? ms->st.n : ms->n_chunks;
+    if (!filter) {
+        OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+        memset(keep, 1, n);
+        return OTTERS_OK;
+    }
+    std::vector<uint32_t> words((n + 31) / 32 + 1);
+    OTTERS_CUDA(cudaMemcpyAsync(words.data(), rows ? ms->d_row_mask : ms->d_chunk_keep, ((n + 31) / 32) * 4,
+                                cudaMemcpyDeviceToHost, c->stream));
+    OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint64_t i = 0; i < n; ++i) keep[i] = (words[i >> 5] >> (i & 31)) & 1u;
+    return OTTERS_OK;
+}
+}  // namespace otters
+
+extern "C" int otters_metastore_chunk_mask(otters_metastore* ms, const otters_filter* filter, uint8_t* keep) {
+    if (!ms || !keep) return fail(OTTERS_ERR_INVALID, "null argument");
+    DeviceGuard g(ms->ctx->device);
+    return export_mask(ms, filter, false, keep);
+}
+extern "C" int otters_metastore_row_mask(otters_metastore* ms, const otters_filter* filter, uint8_t* keep) {
+    if (!ms || !keep) return fail(OTTERS_ERR_INVALID, "null argument");
+    DeviceGuard g(ms->ctx->device);
+    return export_mask(ms, filter, true, keep);
+}
+
+extern "C" int otters_metastore_zonemap_i64(const otters_metastore* ms, uint32_t col, int64_t* mn, int64_t* mx, uint64_t* non_null) {
+    if (!ms || col >= ms->cols.size() || ms->cols[col].zmin_i.size() != ms->n_chunks || !mn || !mx || !non_null)
+        return fail(OTTERS_ERR_INVALID, "column has no integer zonemap");
+    for (uint64_t i = 0; i < ms->n_chunks; ++i) {
+        mn[i] = ms->cols[col].zmin_i[i];
+        mx[i] = ms->cols[col].zmax_i[i];
+        non_null[i] = ms->cols[col].non_null[i];
+    }
+    return OTTERS_OK;
+}
+extern "C" int otters_metastore_zonemap_f64(const otters_metastore* ms, uint32_t col, double* mn, double* mx, uint64_t* non_null) {
+    if (!ms || col >= ms->cols.size() || ms->cols[col].zmin_f.size() != ms->n_chunks || !mn || !mx || !non_null)
+        return fail(OTTERS_ERR_INVALID, "column has no float zonemap");
+    for (uint64_t i = 0; i < ms->n_chunks; ++i) {
+        mn[i] = ms->cols[col].zmin_f[i];
+        mx[i] = ms->cols[col].zmax_f[i];
+        non_null[i] = ms->cols[col].non_null[i];
+    }
+    return OTTERS_OK;
+}
+extern "C" int otters_metastore_inv_norms(const otters_metastore* ms, uint64_t first, uint64_t n, float* out) {
+    if (!ms || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    if (first + n > ms->st.n) return fail(OTTERS_ERR_INVALID, "row range out of bounds");
+    DeviceGuard g(ms->ctx->device);
+    OTTERS_CUDA(cudaStreamSynchronize(ms->ctx->stream));
+    if (n) OTTERS_CUDA(cudaMemcpy(out, ms->st.d_inv + first, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return OTTERS_OK;
+}
+
+// =================================================================================================
+// row-sharded multi-GPU helpers
+// =================================================================================================
+extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q,
+                                         const otters_filter* filter, uint64_t row_base, void* d_records,
+                                         otters_query_stats* stats) {
+    if ((!vs && !ms) || (vs && ms) || !d_records) return fail(OTTERS_ERR_INVALID, "pass exactly one store and a record buffer");
+    if (ms) {
+        DeviceGuard g(ms->ctx->device);
+        return meta_query_impl(ms, q, filter, (otters_topk_record*)d_records, row_base, nullptr, nullptr, nullptr, 0, nullptr,
+                               stats);
+    }
+    if (filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
+    int rc = validate_query(q, vs->st.dim, false);
+    if (rc) return rc;
+    otters_ctx* c = vs->st.ctx;
+    DeviceGuard g(c->device);
+    c->last = otters_last_work{};
+    const uint64_t k_eff = std::min<uint64_t>(q->k, vs->st.n * (uint64_t)q->nq);
+    if (q->k == 0) return OTTERS_OK;
+    if (k_eff == 0) return OTTERS_OK;
+    const uint32_t* d_mask = nullptr;
+    uint32_t mask_words = 0;
+    rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
+    if (rc) return rc;
+    QueryRun run;
+    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, row_base, &run);
+}
+
+extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, uint64_t n_records, uint64_t k, int32_t take_type,
+                                        uint64_t* out_idx, float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len) {
+    if (!c || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
+    DeviceGuard g(c->device);
+    *out_len = 0;
+    if (n_records == 0 || k == 0) return OTTERS_OK;
+    if (!d_records) return fail(OTTERS_ERR_INVALID, "null records");
+    if (n_records > c->scratch_elems) return fail(OTTERS_ERR_UNSUPPORTED, "merge: too many records for the device merge");
+    const uint64_t k_eff = std::min<uint64_t>(k, n_records);
+    cudaStream_t s = c->stream;
+    if (c->list_cap < k_eff) {
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_list[0]);
+        c->d_list[0] = nullptr;
+        c->list_cap = 0;
+    }
+    int rc = ensure_dev(&c->d_list[0], &c->list_cap, (size_t)std::max<uint64_t>(k_eff, kMaxFusedK), s);
+    if (rc) return rc;
+    rc = launch_merge_records((const otters_topk_record*)d_records, (uint32_t)n_records, (uint32_t)k_eff, take_type == OTTERS_TAKE_MAX,
+                              c->d_list[0], c->d_list_count, c->d_scratch_keys, c->d_scratch_src, c->scratch_elems, s);
+    if (rc) return rc;
+    c->last.kernel_launches += 1;
+    QueryRun run;
+    run.result_list = 0;
+    run.k_eff = k_eff;
+    OTTERS_CUDA(cudaMemsetAsync(c->d_rows_scored, 0, sizeof(unsigned long long), s));
+    return fetch_results(c, run, take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr, 0, nullptr);
+}

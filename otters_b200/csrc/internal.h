@@ -1,0 +1,173 @@
+// internal.h — host-side structures and kernel launch prototypes of libotters_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/otters_b200.h"
+#include "common.cuh"
+
+namespace otters {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+#define OTTERS_CUDA(expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return ::otters::fail(OTTERS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+constexpr uint32_t kTileRows = 16;     // rows per staged tile (2 threads per row, one warp per tile)
+constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work unit
+constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
+constexpr uint32_t kSelectSmemElems = 8192;
+
+// ---- scan kernel ------------------------------------------------------------------------------
+struct ScanParams {
+    const float* vectors;       // [n_rows][pitch_g]
+    const float* inv_norms;     // [n_rows]
+    const float* query;         // [dim_pad] zero padded, device
+    float q_inv;                // 1/|q| (0 for a zero query), computed like src/vec.rs:390-397
+    uint64_t pitch_g;           // floats per stored row (dim rounded up to 4)
+    uint32_t dim;
+    uint32_t dim_pad;
+    uint32_t n_rows;
+    const uint32_t* row_mask;   // Lsb0 32-bit words, bit=1 keep; null = all rows
+    uint32_t row_mask_words;    // words available; rows past them are kept
+    uint32_t n_units;
+    uint32_t unit_rows;         // 32, 64 or 128
+    uint32_t* unit_counter;
+    // selection
+    uint32_t k;
+    uint32_t cap;               // per-CTA candidate buffer capacity (power of two >= 2k)
+    int32_t take_max;
+    int32_t has_filter;
+    float thr;
+    int32_t cmp;
+    const uint64_t* tau_in;     // device: running threshold key from earlier queries of a batch (0 = none)
+    uint32_t qid;
+    // staging layout
+    uint32_t kc;                // columns per slot
+    uint32_t nkc;               // slots steps per tile
+    uint32_t pitch_s;           // floats per staged row in shared memory (== 8 mod 32)
+    uint32_t slots;             // slots per warp
+    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_list, off_w_slots;
+    // outputs (fused mode)
+    uint64_t* cta_keys;         // [grid][k]
+    uint32_t* cta_counts;       // [grid]
+    // outputs (emit-all mode)
+    Cand* emit;                 // candidate array
+    uint32_t* emit_count;
+    uint32_t emit_cap;
+    // instrumentation
+    unsigned long long* rows_scored;
+};
+
+struct ScanLaunch {
+    uint32_t grid, block, smem_bytes;
+};
+
+int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, cudaStream_t s);
+
+// ---- selection kernels ------------------------------------------------------------------------
+struct SelectParams {
+    const uint64_t* cta_keys;
+    const uint32_t* cta_counts;
+    uint32_t n_lists;
+    uint32_t list_stride;
+    uint32_t qid;
+    const Cand* prev;           // running list of a batch (may be null)
+    const uint32_t* prev_count;
+    Cand* out;
+    uint32_t* out_count;
+    uint64_t* tau_out;
+    uint32_t k;
+    // global scratch for the rare case where the working set exceeds shared memory
+    uint64_t* scratch_keys;
+    uint32_t* scratch_src;
+    uint32_t scratch_elems;     // power of two
+    // optional fixed-size record output (sharded search)
+    otters_topk_record* records;
+    uint64_t row_base;
+    int32_t take_max;
+};
+int launch_select(const SelectParams& p, cudaStream_t s);
+
+// records (after all-gather) -> global best k
+int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out,
+                         uint32_t* out_count, uint64_t* scratch_keys, uint32_t* scratch_src, uint32_t scratch_elems,
+                         cudaStream_t s);
+// full sort of a candidate array (emit-all path); n_pow2 elements, padded with key = 0
+int launch_global_sort(Cand* buf, uint64_t n_pow2, cudaStream_t s);
+int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, const uint32_t* prev_count, uint64_t n_pow2,
+                       cudaStream_t s);
+int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
+                       uint32_t* out_count, uint64_t* tau_out, cudaStream_t s);
+int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
+                            otters_topk_record* recs, cudaStream_t s);
+
+// ---- store kernels ----------------------------------------------------------------------------
+int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t first, uint64_t n, float* out,
+                     cudaStream_t s);
+int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, uint64_t gen_first, uint64_t n,
+                      uint64_t seed, cudaStream_t s);
+
+// ---- metadata kernels -------------------------------------------------------------------------
+struct DevColumn {
+    int32_t dtype;
+    int32_t pad;
+    const void* values;          // i32 / i64 / f32 / f64 / u32 dictionary codes
+    const uint32_t* null_words;  // Lsb0 32-bit words, bit=1 null; may be null
+    const void* zmin;            // per chunk, typed like the reference's PackedRanges (src/meta.rs:71-76)
+    const void* zmax;
+    const uint32_t* non_null;    // per chunk
+    const uint64_t* bloom;       // per chunk Bloom words, stride bloom_stride
+    uint64_t bloom_stride;
+    const uint64_t* bloom_mbits; // per chunk
+    const uint32_t* bloom_k;     // per chunk
+};
+
+enum LeafExec : int32_t { LEAF_I32 = 0, LEAF_I64 = 1, LEAF_F32 = 2, LEAF_F64 = 3, LEAF_STR = 4 };
+
+struct DevLeaf {
+    uint32_t col;
+    int32_t op;
+    int32_t exec;        // LeafExec
+    int32_t code_valid;  // LEAF_STR: literal present in the dictionary
+    int64_t i64;
+    double f64;
+    float f32;
+    int32_t i32;
+    uint32_t code;
+    uint32_t pad;
+    uint64_t h1, h2;     // LEAF_STR: Bloom probe hashes of the literal
+};
+
+struct DevFilter {       // variable-length: header, clause offsets, leaves (all in one device buffer)
+    uint32_t n_clauses;
+    uint32_t n_leaves;
+};
+
+struct MetaKernelParams {
+    const DevColumn* cols;
+    const uint32_t* clause_off;  // n_clauses + 1
+    const DevLeaf* leaves;
+    uint32_t n_clauses;
+    uint32_t n_rows;
+    uint32_t chunk_size;
+    uint32_t n_chunks;
+    uint32_t nq;
+    uint32_t* chunk_keep;        // words
+    uint32_t* row_mask;          // words
+    unsigned long long* stats;   // [0] evaluated chunks, [1] vectors_compared
+};
+int launch_prune(const MetaKernelParams& p, cudaStream_t s);
+int launch_rowmask(const MetaKernelParams& p, cudaStream_t s);
+int launch_count_all_chunks(const MetaKernelParams& p, cudaStream_t s);
+
+}  // namespace otters

@@ -1,0 +1,167 @@
+// meta.cu — K0 (chunk pruning over zonemaps + Bloom filters) and K0b (per-row CNF predicate ->
+// surviving-row bitmask that gates the scan kernel).
+//
+// K0  replaces MetaStore::build_chunk_mask_for_plan and its leaf helpers (reference
+//     src/meta.rs:407-544) and the range kernels of src/type_utils.rs:446-584,739-889.
+// K0b replaces build_row_mask_for_chunk and its leaf helpers (src/meta_compute.rs:194-318) and the
+//     row kernels of src/type_utils.rs:306-444,586-736.
+//
+// Semantics: filter = AND over clauses of OR over leaves; a NULL row
+// fails every leaf (including Neq); NaN satisfies only Neq; literals are cast to the column width
+// on the host (api.cu) exactly as the reference does.
+#include "internal.h"
+
+namespace otters {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ bool range_sat(int op, T mn, T mx, T t) {
+    switch (op) {
+    case OTTERS_OP_EQ: return mn <= t && t <= mx;
+    case OTTERS_OP_LT: return mn < t;
+    case OTTERS_OP_LTE: return mn <= t;
+    case OTTERS_OP_GT: return mx > t;
+    case OTTERS_OP_GTE: return mx >= t;
+    default: return true;  // Neq
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ bool row_sat(int op, T v, T t) {
+    switch (op) {
+    case OTTERS_OP_EQ: return v == t;
+    case OTTERS_OP_NEQ: return v != t;
+    case OTTERS_OP_LT: return v < t;
+    case OTTERS_OP_LTE: return v <= t;
+    case OTTERS_OP_GT: return v > t;
+    default: return v >= t;
+    }
+}
+
+__device__ __forceinline__ bool chunk_leaf_sat(const DevColumn& c, const DevLeaf& lf, uint32_t ch) {
+    if (c.non_null[ch] == 0) return false;  // every rule is ANDed with non_null > 0
+    switch (lf.exec) {
+    case LEAF_I32: return range_sat<int32_t>(lf.op, ((const int32_t*)c.zmin)[ch], ((const int32_t*)c.zmax)[ch], lf.i32);
+    case LEAF_I64: return range_sat<int64_t>(lf.op, ((const int64_t*)c.zmin)[ch], ((const int64_t*)c.zmax)[ch], lf.i64);
+    case LEAF_F32: return range_sat<float>(lf.op, ((const float*)c.zmin)[ch], ((const float*)c.zmax)[ch], lf.f32);
+    case LEAF_F64: return range_sat<double>(lf.op, ((const double*)c.zmin)[ch], ((const double*)c.zmax)[ch], lf.f64);
+    default: {  // LEAF_STR — src/meta.rs:523-544
+        if (lf.op == OTTERS_OP_NEQ) return true;
+        if (lf.op != OTTERS_OP_EQ) return false;
+        const uint64_t* w = c.bloom + (size_t)ch * c.bloom_stride;
+        const uint64_t m = c.bloom_mbits[ch];
+        const uint32_t kh = c.bloom_k[ch];
+        for (uint32_t i = 0; i < kh; ++i) {
+            uint64_t bit = (lf.h1 + (uint64_t)i * lf.h2) % m;
+            if (!((w[bit >> 6] >> (bit & 63)) & 1ull)) return false;
+        }
+        return true;
+    }
+    }
+}
+
+// K0: one thread per chunk
+__global__ void prune_kernel(const __grid_constant__ MetaKernelParams p) {
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    uint32_t len = 0;
+    if (ch < p.n_chunks) {
+        keep = true;
+        for (uint32_t ci = 0; ci < p.n_clauses && keep; ++ci) {
+            bool any = false;
+            for (uint32_t li = p.clause_off[ci]; li < p.clause_off[ci + 1] && !any; ++li) {
+                const DevLeaf lf = p.leaves[li];
+                any = chunk_leaf_sat(p.cols[lf.col], lf, ch);
+            }
+            keep = any;
+        }
+        const uint64_t base = (uint64_t)ch * p.chunk_size;
+        len = (uint32_t)(base + p.chunk_size <= p.n_rows ? p.chunk_size : p.n_rows - base);
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && (ch >> 5) < ((p.n_chunks + 31) >> 5)) p.chunk_keep[ch >> 5] = m;
+    // stats: evaluated chunks and vectors_compared = sum over evaluated chunks of len * nq
+    // (src/meta_compute.rs:166, src/meta.rs:666-669)
+    unsigned long long vc = keep ? (unsigned long long)len * p.nq : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vc += __shfl_xor_sync(0xFFFFFFFFu, vc, d);
+    if (lane == 0 && m) {
+        atomicAdd(&p.stats[0], (unsigned long long)__popc(m));
+        atomicAdd(&p.stats[1], vc);
+    }
+}
+
+// no meta_filter: every chunk is evaluated (src/meta.rs:658)
+__global__ void count_all_kernel(const __grid_constant__ MetaKernelParams p) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.stats[0] = p.n_chunks;
+        p.stats[1] = (unsigned long long)p.n_rows * p.nq;
+    }
+}
+
+__device__ __forceinline__ bool row_leaf_sat(const DevColumn& c, const DevLeaf& lf, uint32_t row) {
+    if (c.null_words && ((c.null_words[row >> 5] >> (row & 31)) & 1u)) return false;
+    switch (lf.exec) {
+    case LEAF_I32: return row_sat<int32_t>(lf.op, ((const int32_t*)c.values)[row], lf.i32);
+    case LEAF_I64: return row_sat<int64_t>(lf.op, ((const int64_t*)c.values)[row], lf.i64);
+    case LEAF_F32: return row_sat<float>(lf.op, ((const float*)c.values)[row], lf.f32);
+    case LEAF_F64: return row_sat<double>(lf.op, ((const double*)c.values)[row], lf.f64);
+    default: {  // dictionary-coded string equality (src/meta_compute.rs:291-318)
+        const bool eq = lf.code_valid && ((const uint32_t*)c.values)[row] == lf.code;
+        return lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
+    }
+    }
+}
+
+// K0b: one thread per row, one 32-bit mask word per warp
+__global__ void rowmask_kernel(const __grid_constant__ MetaKernelParams p) {
+    const uint32_t n_words = (p.n_rows + 31) >> 5;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps_total) {
+        const uint32_t row = (w << 5) + lane;
+        bool keep = false;
+        if (row < p.n_rows) {
+            const uint32_t ch = row / p.chunk_size;
+            keep = (p.chunk_keep[ch >> 5] >> (ch & 31)) & 1u;
+            for (uint32_t ci = 0; ci < p.n_clauses && keep; ++ci) {
+                bool any = false;
+                for (uint32_t li = p.clause_off[ci]; li < p.clause_off[ci + 1] && !any; ++li) {
+                    const DevLeaf lf = p.leaves[li];
+                    any = row_leaf_sat(p.cols[lf.col], lf, row);
+                }
+                keep = any;
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) p.row_mask[w] = m;
+    }
+}
+
+}  // namespace
+
+int launch_prune(const MetaKernelParams& p, cudaStream_t s) {
+    if (p.n_chunks == 0) return OTTERS_OK;
+    prune_kernel<<<(p.n_chunks + 255) / 256, 256, 0, s>>>(p);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_rowmask(const MetaKernelParams& p, cudaStream_t s) {
+    if (p.n_rows == 0) return OTTERS_OK;
+    uint32_t n_words = (p.n_rows + 31) >> 5;
+    uint32_t blocks = (n_words + 7) / 8;  // 8 warps per block
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    rowmask_kernel<<<blocks, 256, 0, s>>>(p);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_count_all_chunks(const MetaKernelParams& p, cudaStream_t s) {
+    count_all_kernel<<<1, 32, 0, s>>>(p);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+}  // namespace otters

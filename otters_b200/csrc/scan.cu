@@ -1,0 +1,351 @@
+// scan.cu — K1: the streaming exact-order scan kernel (sm_100a).
+//
+// Replaces the scan loop of VecQueryPlan::collect (reference src/vec.rs:222-303) and the scoring
+// kernels of src/vec_compute.rs:9-54, fused with the vec_filter threshold (src/vec_compute.rs:56-74)
+// and a per-CTA top-k (replacing TopKCollector, src/vec_compute.rs:77-294).
+//
+// Design:
+//  * persistent CTAs; every warp is an autonomous pipeline: it claims 128-row work units from a
+//    global counter, turns the unit's surviving-row bitmask into a compact row list, and streams the
+//    surviving rows HBM -> shared memory with per-row TMA bulk copies (cp.async.bulk + mbarrier
+//    complete_tx) into a ring of `slots` tiles of 16 rows x kc columns.  Masked rows are never read
+//    (as in src/vec.rs:248-252).
+//  * arithmetic is bit-identical to the reference's CPU path: two threads per row hold the eight
+//    f32x8 lane accumulators (4 each), multiply and add are separate round-to-nearest operations
+//    (no FMA), blocks of 8 columns are accumulated in order, lanes are reduced in wide's order
+//    ((l0+l1)+l2)+l3 + ((l4+l5)+l6)+l7, the dim%8 tail is a serial sum added last.
+//  * staged rows use a shared-memory pitch == 8 (mod 32) floats, so the 8 threads of a quarter warp
+//    (4 rows x 2 halves) hit 8 distinct 16-byte bank groups: conflict-free LDS.128.
+//  * candidates that beat the CTA's running threshold key are appended to a shared buffer under a
+//    lock; when the buffer fills, one warp bitonic-sorts it, keeps the best k and raises the
+//    threshold.  At exit every CTA publishes its best k keys (sorted) for K3.
+#include "internal.h"
+
+namespace otters {
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct CtaHdr {
+    unsigned long long tau;  // candidates must have key > tau
+    uint32_t count;
+    uint32_t lock;
+};
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+// one warp: sort buf[0..cap) descending (entries >= count are zero), keep the best k
+__device__ void warp_compact(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, int lane) {
+    uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(&hdr->count);
+    for (uint32_t i = cnt + lane; i < cap; i += 32) buf[i] = 0ull;
+    __syncwarp();
+    for (uint32_t size = 2; size <= cap; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < (cap >> 1); t += 32) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool desc = (lo & size) == 0;
+                uint64_t a = buf[lo], b = buf[hi];
+                if ((a < b) == desc) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        uint32_t n = cnt < k ? cnt : k;
+        hdr->count = n;
+        if (n == k) {
+            unsigned long long t = buf[k - 1];
+            if (t > hdr->tau) hdr->tau = t;
+        }
+    }
+    __syncwarp();
+}
+
+// append this warp's passing candidates to the CTA buffer
+__device__ void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, bool has, uint64_t key, int lane) {
+    if (lane == 0) {
+        while (atomicCAS(&hdr->lock, 0u, 1u) != 0u) __nanosleep(64);
+    }
+    __syncwarp();
+    __threadfence_block();
+    uint64_t tau = ld_volatile_u64(&hdr->tau);
+    has = has && key > tau;
+    unsigned m = __ballot_sync(FULL, has);
+    uint32_t n = __popc(m);
+    if (n) {
+        uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(&hdr->count);
+        if (cnt + n > cap) {
+            warp_compact(hdr, buf, cap, k, lane);
+            cnt = *reinterpret_cast<volatile uint32_t*>(&hdr->count);
+            tau = ld_volatile_u64(&hdr->tau);
+            has = has && key > tau;
+            m = __ballot_sync(FULL, has);
+            n = __popc(m);
+        }
+        if (has) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&hdr->count) = cnt + n;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(&hdr->lock, 0u);
+    __syncwarp();
+}
+
+template <int METRIC, bool EMIT_ALL>
+__global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    CtaHdr* hdr = reinterpret_cast<CtaHdr*>(smem);
+    uint64_t* cbuf = reinterpret_cast<uint64_t*>(smem + 16);
+    float* qs = reinterpret_cast<float*>(smem + p.off_query);
+    uint8_t* wbase = smem + p.off_warps + (size_t)warp * p.warp_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase);
+    uint32_t* slot_rows = reinterpret_cast<uint32_t*>(wbase + p.off_w_rows);
+    uint32_t* slot_info = reinterpret_cast<uint32_t*>(wbase + p.off_w_info);
+    uint8_t* rowlist = wbase + p.off_w_list;
+    float* slot_base = reinterpret_cast<float*>(wbase + p.off_w_slots);
+    const uint32_t slot_floats = kTileRows * p.pitch_s;
+
+    const uint64_t tau0 = p.tau_in ? *p.tau_in : 0ull;
+    if (tid == 0) {
+        hdr->tau = tau0;
+        hdr->count = 0;
+        hdr->lock = 0;
+    }
+    for (uint32_t i = tid; i < p.dim_pad; i += blockDim.x) qs[i] = p.query[i];
+    if (lane == 0) {
+        for (uint32_t s = 0; s < p.slots; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const bool take_max = p.take_max != 0;
+    const float q_inv = p.q_inv;
+    const uint32_t dim8 = p.dim & ~7u;
+    const uint32_t ntail = p.dim & 7u;
+    const uint32_t rpl = p.unit_rows >> 5;  // rows per lane when building a unit's row list (1, 2 or 4)
+    const uint64_t l2pol = policy_evict_first();
+
+    // ---- producer state ----
+    uint32_t u_pref = 0;  // lane 0: prefetched unit id
+    if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
+    uint32_t list_n = 0, list_pos = 0, unit_row0 = 0, kc_i = 0, tile_cnt = 0;
+    bool prod_done = false;
+    uint32_t prod_step = 0, cons_step = 0;
+    unsigned long long scored = 0;
+
+    auto issue = [&]() {
+        if (prod_done) return;
+        if (kc_i == 0) {
+            while (list_pos >= list_n) {
+                uint32_t u = __shfl_sync(FULL, u_pref, 0);
+                if (u >= p.n_units) {
+                    prod_done = true;
+                    return;
+                }
+                if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
+                uint32_t row0 = u * p.unit_rows;
+                uint32_t r = row0 + rpl * lane;  // this lane's first row; its rpl rows share one mask word
+                uint32_t bits = (1u << rpl) - 1u;
+                if (p.row_mask) {
+                    uint32_t w = (r >> 5) < p.row_mask_words ? __ldg(p.row_mask + (r >> 5)) : 0xFFFFFFFFu;
+                    bits &= w >> (r & 31);
+                }
+                if (r >= p.n_rows) bits = 0;
+                else if (p.n_rows - r < rpl) bits &= (1u << (p.n_rows - r)) - 1u;
+                uint32_t c = __popc(bits);
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t t = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                uint32_t pos = incl - c;
+                __syncwarp();
+                while (bits) {
+                    int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    rowlist[pos++] = (uint8_t)(rpl * lane + b);
+                }
+                list_n = __shfl_sync(FULL, incl, 31);
+                list_pos = 0;
+                unit_row0 = row0;
+                __syncwarp();
+            }
+            tile_cnt = list_n - list_pos < kTileRows ? list_n - list_pos : kTileRows;
+        }
+        const uint32_t slot = prod_step % p.slots;
+        uint32_t row = 0xFFFFFFFFu;
+        if (lane < (int)tile_cnt) row = unit_row0 + rowlist[list_pos + lane];
+        if (lane < (int)kTileRows) slot_rows[slot * kTileRows + lane] = row;
+        const uint32_t c0 = kc_i * p.kc;
+        const uint32_t ncols = p.dim_pad - c0 < p.kc ? p.dim_pad - c0 : p.kc;
+        const uint32_t bytes = ncols * 4u;
+        if (lane == 0) {
+            slot_info[slot] = tile_cnt | (kc_i << 8);
+            mbar_arrive_expect_tx(&bars[slot], tile_cnt * bytes);
+        }
+        __syncwarp();
+        if (lane < (int)tile_cnt)
+            bulk_g2s_hint(slot_base + (size_t)slot * slot_floats + (size_t)lane * p.pitch_s,
+                          p.vectors + (size_t)row * p.pitch_g + c0, bytes, &bars[slot], l2pol);
+        if (++kc_i == p.nkc) {
+            kc_i = 0;
+            list_pos += kTileRows;
+        }
+        ++prod_step;
+    };
+
+    // ---- consumer state ----
+    const int r = lane >> 1;  // row of the tile handled by this thread pair
+    const int h = lane & 1;   // which half of the 8 lanes: h=0 -> l0..l3, h=1 -> l4..l7
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    uint32_t my_row = 0xFFFFFFFFu;
+    float rinv = 0.f;
+
+    for (uint32_t s = 0; s < p.slots; ++s) issue();
+
+    while (cons_step < prod_step) {
+        const uint32_t slot = cons_step % p.slots;
+        mbar_wait(&bars[slot], (cons_step / p.slots) & 1u);
+        const uint32_t info = slot_info[slot];
+        const uint32_t cnt = info & 0xFFu;
+        const uint32_t kci = info >> 8;
+        if (kci == 0) {
+            a0 = a1 = a2 = a3 = 0.f;
+            my_row = slot_rows[slot * kTileRows + r];
+            if (METRIC == OTTERS_METRIC_COSINE) rinv = (r < (int)cnt) ? __ldg(p.inv_norms + my_row) : 0.f;
+        }
+        const uint32_t c0 = kci * p.kc;
+        const uint32_t cend = c0 + p.kc < dim8 ? c0 + p.kc : dim8;
+        const uint32_t nblk = cend > c0 ? (cend - c0) >> 3 : 0;
+        const float* vrow = slot_base + (size_t)slot * slot_floats + (size_t)r * p.pitch_s;
+        const float4* vp = reinterpret_cast<const float4*>(vrow) + h;
+        const float4* qp = reinterpret_cast<const float4*>(qs + c0) + h;
+#pragma unroll 4
+        for (uint32_t j = 0; j < nblk; ++j) {
+            const float4 v = vp[2 * j];
+            const float4 q = qp[2 * j];
+            if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
+                // src/vec_compute.rs:35-54: diff = query - row; acc += diff*diff
+                const float d0 = __fsub_rn(q.x, v.x), d1 = __fsub_rn(q.y, v.y), d2 = __fsub_rn(q.z, v.z), d3 = __fsub_rn(q.w, v.w);
+                a0 = __fadd_rn(a0, __fmul_rn(d0, d0));
+                a1 = __fadd_rn(a1, __fmul_rn(d1, d1));
+                a2 = __fadd_rn(a2, __fmul_rn(d2, d2));
+                a3 = __fadd_rn(a3, __fmul_rn(d3, d3));
+            } else {
+                // src/vec_compute.rs:9-22: acc += q*v (multiply, then add)
+                a0 = __fadd_rn(a0, __fmul_rn(q.x, v.x));
+                a1 = __fadd_rn(a1, __fmul_rn(q.y, v.y));
+                a2 = __fadd_rn(a2, __fmul_rn(q.z, v.z));
+                a3 = __fadd_rn(a3, __fmul_rn(q.w, v.w));
+            }
+        }
+        if (kci + 1 == p.nkc) {
+            // wide f32x8::reduce_add (non-AVX build): (((l0+l1)+l2)+l3) + (((l4+l5)+l6)+l7)
+            float sdot = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+            float other = __shfl_xor_sync(FULL, sdot, 1);
+            float tot = h == 0 ? __fadd_rn(sdot, other) : __fadd_rn(other, sdot);
+            // serial remainder (src/vec_compute.rs:15-21), Rust's f32 Sum starts at -0.0
+            float tail = -0.0f;
+            if (ntail) {
+                const float* vt = vrow + (dim8 - c0);
+                const float* qt = qs + dim8;
+                for (uint32_t e = 0; e < ntail; ++e) {
+                    if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
+                        float d = __fsub_rn(qt[e], vt[e]);
+                        tail = __fadd_rn(tail, __fmul_rn(d, d));
+                    } else {
+                        tail = __fadd_rn(tail, __fmul_rn(qt[e], vt[e]));
+                    }
+                }
+            }
+            float score = __fadd_rn(tot, tail);
+            if (METRIC == OTTERS_METRIC_COSINE) score = __fmul_rn(__fmul_rn(score, q_inv), rinv);  // src/vec_compute.rs:31
+            bool ok = (h == 0) && (r < (int)cnt) && !(score != score);  // NaN never returned (src/vec_compute.rs:237-239)
+            if (p.has_filter) ok = ok && score_passes(score, p.thr, p.cmp);
+            const uint64_t key = make_key(score, my_row, take_max);
+            scored += (h == 0 && r < (int)cnt) ? 1ull : 0ull;
+            if (EMIT_ALL) {
+                ok = ok && key > tau0;
+                unsigned m = __ballot_sync(FULL, ok);
+                if (m) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(p.emit_count, (uint32_t)__popc(m));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (ok) {
+                        uint32_t at = base + __popc(m & ((1u << lane) - 1u));
+                        if (at < p.emit_cap) {
+                            Cand c;
+                            c.key = key;
+                            c.qid = p.qid;
+                            c.pad = 0;
+                            p.emit[at] = c;
+                        }
+                    }
+                }
+            } else {
+                ok = ok && key > ld_volatile_u64(&hdr->tau);
+                if (__ballot_sync(FULL, ok)) warp_push(hdr, cbuf, p.cap, p.k, ok, key, lane);
+            }
+        }
+        __syncwarp();
+        ++cons_step;
+        issue();
+    }
+
+    if (p.rows_scored) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) scored += __shfl_xor_sync(FULL, scored, d);
+        if (lane == 0 && scored) atomicAdd(p.rows_scored, scored);
+    }
+
+    if (!EMIT_ALL) {
+        __syncthreads();
+        if (warp == 0) {
+            warp_compact(hdr, cbuf, p.cap, p.k, lane);
+            uint32_t n = hdr->count;
+            for (uint32_t i = lane; i < n; i += 32) p.cta_keys[(size_t)blockIdx.x * p.k + i] = cbuf[i];
+            if (lane == 0) p.cta_counts[blockIdx.x] = n;
+        }
+    }
+}
+
+template <int METRIC, bool EMIT>
+int launch_one(const ScanParams& p, const ScanLaunch& l, cudaStream_t s) {
+    auto kern = scan_kernel<METRIC, EMIT>;
+    static thread_local int configured_device = -1;
+    (void)configured_device;
+    OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+    kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+}  // namespace
+
+int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, cudaStream_t s) {
+    switch (metric) {
+    case OTTERS_METRIC_COSINE:
+        return emit_all ? launch_one<OTTERS_METRIC_COSINE, true>(p, l, s) : launch_one<OTTERS_METRIC_COSINE, false>(p, l, s);
+    case OTTERS_METRIC_EUCLIDEAN:
+        return emit_all ? launch_one<OTTERS_METRIC_EUCLIDEAN, true>(p, l, s)
+                        : launch_one<OTTERS_METRIC_EUCLIDEAN, false>(p, l, s);
+    case OTTERS_METRIC_DOT:
+        return emit_all ? launch_one<OTTERS_METRIC_DOT, true>(p, l, s) : launch_one<OTTERS_METRIC_DOT, false>(p, l, s);
+    }
+    return fail(OTTERS_ERR_INVALID, "Search metric is not set");
+}
+
+}  // namespace otters

@@ -1,0 +1,374 @@
+// select.cu — K3: final top-k selection over the per-CTA candidate lists of K1, the running-list
+// merge for query batches, the record merge of the row-sharded multi-GPU path, and the full sort of
+// the large-k (emit-all) path.
+//
+// Replaces TopKCollector::into_sorted_vec (reference src/vec_compute.rs:290-293) and the final merge
+// of MetaQueryPlan::collect (src/meta.rs:699-708: concat, sort, truncate(k)).
+//
+// Canonical order everywhere: better score, then lower row, then lower query index.
+#include "internal.h"
+
+namespace otters {
+namespace {
+
+// element of the working set: a 64-bit candidate key plus a 32-bit source tag that both breaks ties
+// (lower tag first) and lets the query index be recovered afterwards
+__device__ __forceinline__ bool before(uint64_t ka, uint32_t sa, uint64_t kb, uint32_t sb) {
+    return ka > kb || (ka == kb && sa < sb);
+}
+
+// block-wide bitonic sort of n (power of two) elements, best-first.  keys/src may live in shared or
+// global memory.
+__device__ void block_bitonic(uint64_t* keys, uint32_t* src, uint32_t n) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool fwd = (lo & size) == 0;
+                uint64_t ka = keys[lo], kb = keys[hi];
+                uint32_t sa = src[lo], sb = src[hi];
+                bool swap = fwd ? before(kb, sb, ka, sa) : before(ka, sa, kb, sb);
+                if (swap) {
+                    keys[lo] = kb;
+                    keys[hi] = ka;
+                    src[lo] = sb;
+                    src[hi] = sa;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// Source tags: list 0 is the running list of earlier queries (already ordered by key desc, qid asc,
+// so position order == qid order among equal keys); lists 1.. are this query's per-CTA lists.
+// tag = list << 11 | position  (position < 2048 because k <= 1024 in the fused path)
+constexpr uint32_t kPosBits = 11;
+
+__global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__ SelectParams p) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(sm);
+    uint32_t* s_src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
+    __shared__ uint32_t s_total, s_nel, s_retry, s_maxcount;
+
+    const uint32_t n_lists = p.n_lists + 1;  // + running list
+    const uint32_t prev_n = (p.prev && p.prev_count) ? *p.prev_count : 0;
+    auto list_count = [&](uint32_t l) -> uint32_t { return l == 0 ? prev_n : p.cta_counts[l - 1]; };
+    auto list_key = [&](uint32_t l, uint32_t i) -> uint64_t {
+        return l == 0 ? p.prev[i].key : p.cta_keys[(size_t)(l - 1) * p.list_stride + i];
+    };
+
+    if (threadIdx.x == 0) {
+        s_total = 0;
+        s_maxcount = 0;
+    }
+    __syncthreads();
+    {
+        uint32_t loc = 0, mx = 0;
+        for (uint32_t l = threadIdx.x; l < n_lists; l += blockDim.x) {
+            uint32_t c = list_count(l);
+            loc += c;
+            mx = c > mx ? c : mx;
+        }
+        if (loc) atomicAdd(&s_total, loc);
+        if (mx) atomicMax(&s_maxcount, mx);
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    const uint32_t kk = total < p.k ? total : p.k;
+    const uint32_t maxcount = s_maxcount;
+
+    // Only a short prefix of every (sorted) list can reach the global top-k.  Start with a small
+    // prefix length L, sort the union of prefixes, and grow L until no list was cut short.
+    uint32_t L = (4 * p.k) / n_lists + 8;
+    if (L > maxcount) L = maxcount;
+    uint64_t* keys = s_keys;
+    uint32_t* src = s_src;
+    uint32_t P = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_nel = 0;
+            s_retry = 0;
+        }
+        __syncthreads();
+        // gather prefixes
+        uint64_t worst = (uint64_t)n_lists * L;
+        bool use_global = worst > kSelectSmemElems;
+        keys = use_global ? p.scratch_keys : s_keys;
+        src = use_global ? p.scratch_src : s_src;
+        for (uint32_t l = threadIdx.x; l < n_lists; l += blockDim.x) {
+            uint32_t c = list_count(l);
+            uint32_t take = c < L ? c : L;
+            if (take) {
+                uint32_t base = atomicAdd(&s_nel, take);
+                for (uint32_t i = 0; i < take; ++i) {
+                    keys[base + i] = list_key(l, i);
+                    src[base + i] = (l << kPosBits) | i;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nel = s_nel;
+        P = next_pow2(nel < 2 ? 2 : nel);
+        for (uint32_t i = nel + threadIdx.x; i < P; i += blockDim.x) {
+            keys[i] = 0ull;
+            src[i] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        block_bitonic(keys, src, P);
+        // was any list cut short in a way that matters?
+        if (L < maxcount) {
+            if (nel < kk) {
+                if (threadIdx.x == 0) s_retry = 1;
+            } else if (kk > 0) {
+                const uint64_t tk = keys[kk - 1];
+                const uint32_t ts = src[kk - 1];
+                for (uint32_t l = threadIdx.x; l < n_lists; l += blockDim.x) {
+                    uint32_t c = list_count(l);
+                    if (c > L) {
+                        uint64_t nk = list_key(l, L);
+                        uint32_t ns = (l << kPosBits) | L;
+                        if (before(nk, ns, tk, ts)) s_retry = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (!s_retry) break;
+        L = L * 4 < maxcount ? L * 4 : maxcount;
+        __syncthreads();
+    }
+
+    // emit the best kk, ordered
+    for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
+        uint32_t s = src[i];
+        uint32_t l = s >> kPosBits, pos = s & ((1u << kPosBits) - 1u);
+        Cand c;
+        c.key = keys[i];
+        c.qid = l == 0 ? p.prev[pos].qid : p.qid;
+        c.pad = 0;
+        p.out[i] = c;
+        if (p.records) {
+            otters_topk_record r;
+            r.row = p.row_base + key_row(c.key);
+            r.score = key_score(c.key, p.take_max != 0);
+            r.qid = c.qid;
+            p.records[i] = r;
+        }
+    }
+    if (p.records) {
+        for (uint32_t i = kk + threadIdx.x; i < p.k; i += blockDim.x) {
+            otters_topk_record r;
+            r.row = 0xFFFFFFFFFFFFFFFFull;
+            r.score = 0.f;
+            r.qid = 0;
+            p.records[i] = r;
+        }
+    }
+    if (threadIdx.x == 0) {
+        *p.out_count = kk;
+        if (p.tau_out) *p.tau_out = (kk == p.k && kk > 0) ? keys[kk - 1] : 0ull;
+    }
+}
+
+// ---- sharded path: merge gathered records --------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
+                     uint64_t* scratch_keys, uint32_t* scratch_src) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm);
+    uint32_t* src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
+    __shared__ uint32_t s_valid;
+    uint32_t P = next_pow2(n < 2 ? 2 : n);
+    if (P > kSelectSmemElems) {
+        keys = scratch_keys;
+        src = scratch_src;
+    }
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    uint32_t loc = 0;
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t key = 0ull;
+        uint32_t tag = 0xFFFFFFFFu;
+        if (i < n && recs[i].row != 0xFFFFFFFFFFFFFFFFull) {
+            // global rows are < 2^32 (documented limit); ties: lower global row, then lower qid.
+            key = make_key(recs[i].score, (uint32_t)recs[i].row, take_max != 0);
+            tag = recs[i].qid;
+            ++loc;
+        }
+        keys[i] = key;
+        src[i] = tag;
+    }
+    if (loc) atomicAdd(&s_valid, loc);
+    __syncthreads();
+    block_bitonic(keys, src, P);
+    uint32_t kk = s_valid < k ? s_valid : k;
+    for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
+        Cand c;
+        c.key = keys[i];
+        c.qid = src[i];
+        c.pad = 0;
+        out[i] = c;
+    }
+    if (threadIdx.x == 0) *out_count = kk;
+}
+
+// ---- large-k path: full sort of a candidate array -------------------------------------------------
+__global__ void bitonic_step_kernel(Cand* buf, uint64_t n, uint64_t size, uint64_t stride) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n >> 1)) return;
+    uint64_t lo = 2 * t - (t & (stride - 1));
+    uint64_t hi = lo + stride;
+    bool fwd = (lo & size) == 0;
+    Cand a = buf[lo], b = buf[hi];
+    bool swap = fwd ? cand_before(b, a) : cand_before(a, b);
+    if (swap) {
+        buf[lo] = b;
+        buf[hi] = a;
+    }
+}
+
+// sorts 4096-element blocks entirely in shared memory for all (size, stride) with stride < 4096
+__global__ void __launch_bounds__(1024) bitonic_local_kernel(Cand* buf, uint64_t n, uint64_t size_begin, uint64_t size_end) {
+    __shared__ Cand s[2048];
+    const uint64_t base = (uint64_t)blockIdx.x * 2048;
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s[i] = buf[base + i];
+    __syncthreads();
+    for (uint64_t size = size_begin; size <= size_end; size <<= 1) {
+        uint64_t st0 = size >> 1;
+        if (st0 > 1024) st0 = 1024;
+        for (uint64_t stride = st0; stride > 0; stride >>= 1) {
+            uint32_t t = threadIdx.x;
+            uint32_t lo = 2 * t - (t & ((uint32_t)stride - 1));
+            uint32_t hi = lo + (uint32_t)stride;
+            bool fwd = ((base + lo) & size) == 0;
+            Cand a = s[lo], b = s[hi];
+            bool swap = fwd ? cand_before(b, a) : cand_before(a, b);
+            if (swap) {
+                s[lo] = b;
+                s[hi] = a;
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) buf[base + i] = s[i];
+    (void)n;
+}
+
+__global__ void append_prev_kernel(Cand* buf, const uint32_t* emit_count, const Cand* prev, const uint32_t* prev_count,
+                                   uint64_t n_pow2) {
+    const uint64_t ne = *emit_count;
+    const uint64_t np = (prev && prev_count) ? *prev_count : 0;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t strideg = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_pow2; i += strideg) {
+        if (i < ne) continue;
+        Cand c;
+        if (i < ne + np) c = prev[i - ne];
+        else {
+            c.key = 0ull;
+            c.qid = 0xFFFFFFFFu;
+            c.pad = 0;
+        }
+        buf[i] = c;
+    }
+}
+
+__global__ void take_sorted_kernel(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k,
+                                   Cand* out, uint32_t* out_count, uint64_t* tau_out) {
+    const uint64_t total = (uint64_t)*emit_count + (prev_count ? *prev_count : 0);
+    const uint64_t kk = total < k ? total : k;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t strideg = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = i; j < kk; j += strideg) out[j] = buf[j];
+    if (i == 0) {
+        *out_count = (uint32_t)kk;
+        if (tau_out) *tau_out = (kk == k && kk > 0) ? buf[kk - 1].key : 0ull;
+    }
+}
+
+__global__ void cands_to_records_kernel(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
+                                        otters_topk_record* recs) {
+    uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        otters_topk_record r;
+        if (i < n) {
+            r.row = row_base + key_row(cands[i].key);
+            r.score = key_score(cands[i].key, take_max != 0);
+            r.qid = cands[i].qid;
+        } else {
+            r.row = 0xFFFFFFFFFFFFFFFFull;
+            r.score = 0.f;
+            r.qid = 0;
+        }
+        recs[i] = r;
+    }
+}
+
+constexpr size_t kSelectSmemBytes = (size_t)kSelectSmemElems * 12;
+
+}  // namespace
+
+int launch_select(const SelectParams& p, cudaStream_t s) {
+    OTTERS_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
+    select_kernel<<<1, 1024, kSelectSmemBytes, s>>>(p);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
+                         uint64_t* scratch_keys, uint32_t* scratch_src, uint32_t scratch_elems, cudaStream_t s) {
+    uint32_t P = 2;
+    while (P < n) P <<= 1;
+    if (P > kSelectSmemElems && P > scratch_elems) return fail(OTTERS_ERR_UNSUPPORTED, "merge: too many records");
+    OTTERS_CUDA(
+        cudaFuncSetAttribute(merge_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
+    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, take_max, out, out_count, scratch_keys, scratch_src);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_global_sort(Cand* buf, uint64_t n, cudaStream_t s) {
+    // n is a power of two >= 2048
+    const uint64_t blocks_local = n / 2048;
+    bitonic_local_kernel<<<(unsigned)blocks_local, 1024, 0, s>>>(buf, n, 2, 2048);
+    for (uint64_t size = 4096; size <= n; size <<= 1) {
+        for (uint64_t stride = size >> 1; stride >= 2048; stride >>= 1) {
+            uint64_t threads = n >> 1;
+            bitonic_step_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(buf, n, size, stride);
+        }
+        bitonic_local_kernel<<<(unsigned)blocks_local, 1024, 0, s>>>(buf, n, size, size);
+    }
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, const uint32_t* prev_count, uint64_t n_pow2,
+                       cudaStream_t s) {
+    append_prev_kernel<<<1024, 256, 0, s>>>(buf, emit_count, prev, prev_count, n_pow2);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
+                       uint32_t* out_count, uint64_t* tau_out, cudaStream_t s) {
+    take_sorted_kernel<<<256, 256, 0, s>>>(buf, emit_count, prev_count, k, out, out_count, tau_out);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
+                            otters_topk_record* recs, cudaStream_t s) {
+    cands_to_records_kernel<<<(k + 255) / 256 ? (k + 255) / 256 : 1, 256, 0, s>>>(cands, count, k, row_base, take_max, recs);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+}  // namespace otters
