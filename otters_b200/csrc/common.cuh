@@ -94,8 +94,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Spins until the phase with the given parity completes.  A watchdog turns a lost transaction (a bug)
+// into a trap after ~2 s instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
 // global -> shared bulk async copy; bytes % 16 == 0, both addresses 16-byte aligned

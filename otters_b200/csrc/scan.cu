@@ -71,7 +71,11 @@ __device__ void warp_compact(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t 
 // append this warp's passing candidates to the CTA buffer
 __device__ void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, bool has, uint64_t key, int lane) {
     if (lane == 0) {
-        while (atomicCAS(&hdr->lock, 0u, 1u) != 0u) __nanosleep(64);
+        const long long t0 = clock64();
+        while (atomicCAS(&hdr->lock, 0u, 1u) != 0u) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000ll) __trap();  // watchdog: never hang the GPU on a lost lock
+        }
     }
     __syncwarp();
     __threadfence_block();
