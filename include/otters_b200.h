@@ -266,7 +266,8 @@ typedef struct {
 OTTERS_API int otters_query_local_device(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q,
                               const otters_filter *filter, uint64_t row_base, void *d_records,
                               otters_query_stats *stats /* nullable */);
-/* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k. */
+/* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k.
+ * With out_idx = out_score = out_qid = NULL and cap = 0 the call only enqueues the merge (no copy, no sync). */
 OTTERS_API int otters_topk_merge_device(otters_ctx *ctx, const void *d_records, uint64_t n_records, uint64_t k, int32_t take_type,
                              uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap, uint64_t *out_len);
 

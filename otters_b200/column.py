@@ -87,6 +87,24 @@ _NP = {
 }
 
 
+class _CatSeq:
+    """Lazy string sequence backed by a vocabulary and per-row codes (bulk synthetic columns)."""
+
+    def __init__(self, vocab, codes):
+        self.vocab = list(vocab)
+        self.codes = np.ascontiguousarray(codes, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.codes)
+
+    def __getitem__(self, i):
+        return self.vocab[int(self.codes[i])]
+
+    def __iter__(self):
+        v = self.vocab
+        return (v[int(c)] for c in self.codes)
+
+
 class Column:
     """A named, typed column with a null mask (src/col.rs:21-28)."""
 
@@ -162,6 +180,22 @@ class Column:
         if nulls is not None and dtype != DataType.String:
             c._vals = c._vals.copy()
             c._vals[c._nulls] = c._sentinel()
+        return c
+
+    @classmethod
+    def from_categories(cls, name: str, vocab, codes, nulls=None) -> "Column":
+        """String column given as vocabulary + per-row codes; NULL rows hold "" like the reference."""
+        c = cls(name, DataType.String)
+        vocab = list(vocab)
+        codes = np.ascontiguousarray(codes, dtype=np.int64)
+        n = len(codes)
+        c._nulls = np.zeros(n, dtype=bool) if nulls is None else np.ascontiguousarray(nulls, dtype=bool)
+        if c._nulls.any():
+            if "" not in vocab:
+                vocab = vocab + [""]
+            codes = codes.copy()
+            codes[c._nulls] = vocab.index("")
+        c._vals = _CatSeq(vocab, codes)
         return c
 
     def _sentinel(self):
@@ -255,6 +289,25 @@ class Column:
 
     def string_buffers(self):
         """(offsets u64[n+1], bytes u8[]) for String columns."""
+        if isinstance(self._vals, _CatSeq):
+            enc_v = [s.encode("utf-8") for s in self._vals.vocab]
+            vlen = np.array([len(b) for b in enc_v], dtype=np.uint64)
+            width = max(int(vlen.max()) if len(vlen) else 0, 1)
+            mat = np.zeros((len(enc_v), width), dtype=np.uint8)
+            for i, b in enumerate(enc_v):
+                mat[i, : len(b)] = np.frombuffer(b, dtype=np.uint8)
+            codes = self._vals.codes
+            lens = vlen[codes]
+            offsets = np.zeros(len(codes) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=offsets[1:])
+            if len(vlen) and int(vlen.min()) == width:
+                data = mat[codes].reshape(-1)
+            else:
+                data = mat[codes][np.arange(width)[None, :] < lens[:, None].astype(np.int64)]
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            if data.size == 0:
+                data = np.zeros(1, dtype=np.uint8)
+            return offsets, data
         enc = [s.encode("utf-8") for s in self._vals]
         lens = np.fromiter((len(b) for b in enc), dtype=np.uint64, count=len(enc))
         offsets = np.zeros(len(enc) + 1, dtype=np.uint64)

@@ -1471,6 +1471,11 @@ extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, ui
     QueryRun run;
     run.result_list = 0;
     run.k_eff = k_eff;
+    if (!out_idx && !out_score && !out_qid && cap == 0) {
+        // asynchronous form: the merged list stays on the device (used to time the device-only pipeline)
+        *out_len = k_eff;
+        return OTTERS_OK;
+    }
     OTTERS_CUDA(cudaMemsetAsync(c->d_rows_scored, 0, sizeof(unsigned long long), s));
     return fetch_results(c, run, take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr, 0, nullptr);
 }

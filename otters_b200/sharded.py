@@ -1,0 +1,127 @@
+"""Row-sharded multi-GPU search (one process per GPU, torch.distributed for the plumbing).
+
+Rows are split into contiguous, chunk-aligned ranges; every rank holds its shard in HBM,
+answers the query locally (``otters_query_local_device`` leaves k fixed-size records on the device), the
+ranks all-gather the records (NCCL over NVLink; k*16 bytes per rank) and every rank runs the same final
+merge kernel (``otters_topk_merge_device``).  Global row id = shard base + local row.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+RECORD_DTYPE = np.dtype([("row", "<u8"), ("score", "<f4"), ("qid", "<u4")])  # otters_topk_record
+EMPTY_ROW = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def shard_range(n_rows: int, chunk_size: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of `rank`, aligned to chunk boundaries so zonemaps and stats shard with the rows."""
+    chunk_size = max(int(chunk_size), 1)
+    n_chunks = (n_rows + chunk_size - 1) // chunk_size
+    per = (n_chunks + world - 1) // world
+    r0 = min(rank * per * chunk_size, n_rows)
+    r1 = min((rank + 1) * per * chunk_size, n_rows)
+    return r0, r1
+
+
+def merge_records_host(records: np.ndarray, k: int, take_max: bool):
+    """Reference merge of gathered records on the host (used by the CPU/gloo tests of the plumbing only;
+    the product merges on the device).  Order: better score, lower row, lower query id."""
+    rec = records[records["row"] != EMPTY_ROW]
+    score = rec["score"].astype(np.float32) + np.float32(0.0)
+    key = -score if take_max else score
+    order = np.lexsort((rec["qid"], rec["row"], key))[:k]
+    return rec["row"][order], rec["score"][order], rec["qid"][order]
+
+
+class ShardedSearcher:
+    """Local search -> all-gather -> merge.  `local_fn(k) -> records` and `merge_fn(gathered, k)` are
+    injected so the same plumbing runs on CUDA/NCCL (product) and on CPU/gloo (tests)."""
+
+    def __init__(self, world: int, rank: int, gather_fn: Callable, merge_fn: Callable):
+        self.world, self.rank = world, rank
+        self._gather = gather_fn
+        self._merge = merge_fn
+
+    def search(self, local_fn: Callable, k: int):
+        local = local_fn(k)
+        gathered = self._gather(local)
+        return self._merge(gathered, k)
+
+
+class CudaShard:
+    """Product implementation: a VecStore or MetaStore shard on this rank's GPU."""
+
+    def __init__(self, store, row_base: int, k_max: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _ffi
+        from .meta import MetaStore
+
+        self._torch, self._dist, self._ffi = torch, dist, _ffi
+        self.store = store
+        self.is_meta = isinstance(store, MetaStore)
+        self.ctx = store.ctx
+        self.row_base = int(row_base)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev = torch.device("cuda", self.ctx.device)
+        self.local = torch.empty((k_max, 16), dtype=torch.uint8, device=dev)
+        self.gathered = torch.empty((self.world * k_max, 16), dtype=torch.uint8, device=dev)
+        self.k_max = k_max
+
+    def enqueue(self, vq, fp, k: int, want_stats: bool = False):
+        """Enqueues local search + all-gather on the context's stream; returns the gathered record tensor."""
+        ffi = self._ffi
+        st = ffi.QueryStats()
+        local = self.local[:k]
+        if self.is_meta:
+            rc = ffi.otters_query_local_device(None, self.store.handle, C.byref(vq), fp.byref() if fp else None, self.row_base,
+                                               C.c_void_p(local.data_ptr()), C.byref(st) if want_stats else None)
+        else:
+            self.store._flush()
+            rc = ffi.otters_query_local_device(self.store._handle(), None, C.byref(vq), None, self.row_base,
+                                               C.c_void_p(local.data_ptr()), None)
+        if rc != 0:
+            from .types import OttersError
+
+            raise OttersError(ffi.last_error())
+        if self.world > 1:
+            gathered = self.gathered[: self.world * k]
+            self._dist.all_gather_into_tensor(gathered, local, group=self.group)
+        else:
+            gathered = local
+        return gathered, st
+
+    def merge(self, gathered, k: int, take_max: bool, fetch: bool = True):
+        ffi = self._ffi
+        n = gathered.shape[0]
+        out_len = C.c_uint64(0)
+        if not fetch:
+            rc = ffi.otters_topk_merge_device(self.ctx.handle, C.c_void_p(gathered.data_ptr()), n, k, 1 if take_max else 0,
+                                              None, None, None, 0, C.byref(out_len))
+            if rc != 0:
+                from .types import OttersError
+
+                raise OttersError(ffi.last_error())
+            return None
+        idx = np.zeros(k, np.uint64)
+        score = np.zeros(k, np.float32)
+        qid = np.zeros(k, np.uint32)
+        rc = ffi.otters_topk_merge_device(self.ctx.handle, C.c_void_p(gathered.data_ptr()), n, k, 1 if take_max else 0,
+                                          idx.ctypes.data_as(ffi.c_u64p), score.ctypes.data_as(ffi.c_f32p),
+                                          qid.ctypes.data_as(ffi.c_u32p), k, C.byref(out_len))
+        if rc != 0:
+            from .types import OttersError
+
+            raise OttersError(ffi.last_error())
+        m = min(out_len.value, k)
+        return idx[:m], score[:m], qid[:m]
+
+    def search(self, vq, fp, k: int, take_max: bool):
+        gathered, _ = self.enqueue(vq, fp, k)
+        return self.merge(gathered, k, take_max)
