@@ -260,7 +260,9 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch (events, NCCL ordering) and the library's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = ob.Context(local_rank, stream.cuda_stream)
     if args.tuning:
         w, s, kc, cps, ur = (int(x) for x in args.tuning.split(","))

@@ -19,6 +19,8 @@ class Context:
 
     def __init__(self, device: int = 0, stream: Optional[int] = None):
         h = C.c_void_p()
+        if stream is not None and int(stream) == 0:
+            raise OttersError("pass a real stream handle (the legacy default stream 0 is not supported) or None")
         check(_ffi.otters_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = int(device)

@@ -52,18 +52,24 @@ struct otters_ctx {
     // device scratch
     float* d_query = nullptr;
     size_t d_query_floats = 0;
+    // one 64-byte control block, zeroed by a single memset at the start of every query:
+    //   +0 unit counter, +4 emit count, +8 list counts[2], +16 tau, +24 rows scored, +32 stats[4]
+    uint8_t* d_ctrl = nullptr;
     uint32_t* d_counter = nullptr;      // [0] unit counter, [1] emit count
+    uint32_t* d_list_count = nullptr;   // [2]
+    uint64_t* d_tau = nullptr;
+    unsigned long long* d_rows_scored = nullptr;
+    unsigned long long* d_stats = nullptr;  // [0] evaluated chunks, [1] vectors_compared
     uint64_t* d_cta_keys = nullptr;     // [grid_max][kMaxFusedK]
     uint32_t* d_cta_counts = nullptr;
     uint32_t grid_max = 0;
-    Cand* d_list[2] = {nullptr, nullptr};  // running / result lists
-    size_t list_cap = 0;
-    uint32_t* d_list_count = nullptr;   // [2]
-    uint64_t* d_tau = nullptr;
+    uint8_t* d_list_raw[2] = {nullptr, nullptr};  // ResultHeader + entries
+    Cand* d_list[2] = {nullptr, nullptr};  // running / result lists (entries)
+    size_t list_cap = 0;                // entries of d_list[0] (d_list[1] always holds kMaxFusedK)
     uint64_t* d_scratch_keys = nullptr;
     uint32_t* d_scratch_src = nullptr;
     uint32_t scratch_elems = 0;
-    unsigned long long* d_rows_scored = nullptr;
+    uint32_t scan_smem_configured[6] = {0, 0, 0, 0, 0, 0};
     uint32_t* d_mask = nullptr;         // uploaded VecStore row mask
     size_t d_mask_words = 0;
     Cand* d_emit = nullptr;             // emit-all path
@@ -71,9 +77,13 @@ struct otters_ctx {
     otters_topk_record* d_records = nullptr;
     size_t records_cap = 0;
 
-    // pinned staging
+    // pinned staging: queries / masks, lowered filters, results
     uint8_t* h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    uint8_t* h_filter = nullptr;
+    size_t h_filter_bytes = 0;
+    uint8_t* h_result = nullptr;
+    size_t h_result_bytes = 0;
 
     cudaEvent_t ev[8]{};
     bool stage_pending = false;   // an async H2D copy out of h_stage is in flight (ev[7] marks its end)
@@ -90,6 +100,8 @@ static int ensure_stage(otters_ctx* c, size_t bytes) {
     }
     if (bytes <= c->h_stage_bytes) return OTTERS_OK;
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_filter) cudaFreeHost(c->h_filter);
+    if (c->h_result) cudaFreeHost(c->h_result);
     c->h_stage = nullptr;
     c->h_stage_bytes = 0;
     size_t nb = std::max<size_t>(round_up(bytes, 4096), 1 << 16);
@@ -97,6 +109,46 @@ static int ensure_stage(otters_ctx* c, size_t bytes) {
     c->h_stage_bytes = nb;
     return OTTERS_OK;
 }
+
+static int ensure_pinned(uint8_t** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return OTTERS_OK;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    size_t nb = std::max<size_t>(round_up(bytes, 4096), 1 << 14);
+    OTTERS_CUDA(cudaMallocHost((void**)ptr, nb));
+    *cap = nb;
+    return OTTERS_OK;
+}
+
+// one memset resets every per-query counter (unit counter, list counts, tau, rows scored, stats)
+static int begin_query(otters_ctx* c) {
+    OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl, 0, 64, c->stream));
+    c->last = otters_last_work{};
+    return OTTERS_OK;
+}
+
+static int alloc_list(otters_ctx* c, int i, size_t entries) {
+    if (c->d_list_raw[i]) cudaFree(c->d_list_raw[i]);
+    c->d_list_raw[i] = nullptr;
+    c->d_list[i] = nullptr;
+    if (cudaMalloc((void**)&c->d_list_raw[i], sizeof(ResultHeader) + entries * sizeof(Cand)) != cudaSuccess)
+        return fail(OTTERS_ERR_NOMEM, "device allocation for result lists failed");
+    c->d_list[i] = reinterpret_cast<Cand*>(c->d_list_raw[i] + sizeof(ResultHeader));
+    return OTTERS_OK;
+}
+
+static int ensure_list0(otters_ctx* c, size_t entries) {
+    entries = std::max<size_t>(entries, kMaxFusedK);
+    if (entries <= c->list_cap && c->d_list[0]) return OTTERS_OK;
+    OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = alloc_list(c, 0, entries);
+    if (rc) return rc;
+    c->list_cap = entries;
+    return OTTERS_OK;
+}
+
+static inline ResultHeader* list_hdr(otters_ctx* c, int i) { return reinterpret_cast<ResultHeader*>(c->d_list_raw[i]); }
 
 template <typename T>
 static int ensure_dev(T** ptr, size_t* cap, size_t need, cudaStream_t s) {
@@ -200,7 +252,7 @@ struct VecStorage {
 struct ScanPlan {
     ScanLaunch launch;
     uint32_t kc, nkc, pitch_s, slots, unit_rows, n_units, cap;
-    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_list, off_w_slots;
+    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
 };
 
 static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, ScanPlan* out) {
@@ -214,7 +266,9 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     if (pl.off_warps + 4096 > budget) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
 
     uint32_t dim8 = (uint32_t)round_up(dim_pad, 8);
-    uint32_t kc_target = t.kc_floats ? (uint32_t)round_up(t.kc_floats, 8) : 512;
+    // Measured on B200 (profiles/r1_sweep_*.log): many autonomous warps with one small slot each beat
+    // fewer warps with deep rings — 12-16 warps x 1 slot x 256 columns reads 7.1-7.3 TB/s at dim 768.
+    uint32_t kc_target = t.kc_floats ? (uint32_t)round_up(t.kc_floats, 8) : 256;
     uint32_t nkc = (dim_pad + kc_target - 1) / kc_target;
     if (nkc < 1) nkc = 1;
     uint32_t kc = (uint32_t)round_up((dim8 + nkc - 1) / nkc, 8);
@@ -224,13 +278,15 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     pl.pitch_s = (uint32_t)round_up(kc, 32) + 8;
     const uint32_t slot_bytes = kTileRows * pl.pitch_s * 4;
 
-    auto warp_bytes_for = [&](uint32_t S, uint32_t* o_rows, uint32_t* o_info, uint32_t* o_list, uint32_t* o_slots) {
+    auto warp_bytes_for = [&](uint32_t S, uint32_t* o_rows, uint32_t* o_info, uint32_t* o_inv, uint32_t* o_list, uint32_t* o_slots) {
         uint32_t o = 0;
         o += S * 8;
         *o_rows = o;
         o += S * kTileRows * 4;
         *o_info = o;
         o += (uint32_t)round_up(S * 4, 16);
+        *o_inv = o;
+        o += S * kTileRows * 4;
         *o_list = o;
         o += kMaxUnitRows;
         o = (uint32_t)round_up(o, 128);
@@ -238,20 +294,20 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
         o += S * slot_bytes;
         return (uint32_t)round_up(o, 128);
     };
-    uint32_t dummy[4];
+    uint32_t dummy[5];
     const size_t avail = budget - pl.off_warps;
     uint32_t total_slots = (uint32_t)(avail / (slot_bytes + 256));
     if (total_slots < 1) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
-    uint32_t S = t.slots_per_warp ? t.slots_per_warp : (total_slots >= 4 ? 2 : 1);
+    uint32_t S = t.slots_per_warp ? t.slots_per_warp : (total_slots >= 32 ? 2 : 1);
     uint32_t W = t.warps_per_cta ? t.warps_per_cta : std::min<uint32_t>(total_slots / S, 16);
     if (W < 1) W = 1;
     if (W > 16) W = 16;
-    while (W > 1 && (size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3) > avail) --W;
-    while (S > 1 && (size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3) > avail) --S;
-    if ((size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3) > avail)
+    while (W > 1 && (size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3, dummy + 4) > avail) --W;
+    while (S > 1 && (size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3, dummy + 4) > avail) --S;
+    if ((size_t)W * warp_bytes_for(S, dummy, dummy + 1, dummy + 2, dummy + 3, dummy + 4) > avail)
         return fail(OTTERS_ERR_UNSUPPORTED, "scan tuning does not fit in shared memory");
     pl.slots = S;
-    pl.warp_bytes = warp_bytes_for(S, &pl.off_w_rows, &pl.off_w_info, &pl.off_w_list, &pl.off_w_slots);
+    pl.warp_bytes = warp_bytes_for(S, &pl.off_w_rows, &pl.off_w_info, &pl.off_w_inv, &pl.off_w_list, &pl.off_w_slots);
 
     uint32_t ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : 1;
     uint32_t grid = (uint32_t)c->sm_count * ctas_per_sm;
@@ -292,15 +348,13 @@ static float host_inv_norm(const float* v, uint32_t dim) {
 }
 
 static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const uint32_t* d_row_mask,
-                       uint32_t row_mask_words, otters_topk_record* d_records_out, uint64_t row_base, QueryRun* run) {
+                       uint32_t row_mask_words, otters_topk_record* d_records_out, uint64_t row_base,
+                       const unsigned long long* stats_src, QueryRun* run) {
     const uint32_t dim_pad = st->pitch;
     const uint64_t n_rows = st->n;
     const uint64_t k_eff = std::min<uint64_t>(q->k, n_rows * (uint64_t)q->nq);
     run->k_eff = k_eff;
     run->result_list = 0;
-    c->last.kernel_launches = 0;
-    c->last.rows_scored = 0;
-    c->last.scan_bytes = 0;
     cudaStream_t s = c->stream;
 
     // stage queries (zero padded to the stored pitch) and their inverse norms
@@ -321,9 +375,6 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
     c->stage_pending = true;
     c->timed_single = false;
-    OTTERS_CUDA(cudaMemsetAsync(c->d_list_count, 0, 2 * sizeof(uint32_t), s));
-    OTTERS_CUDA(cudaMemsetAsync(c->d_tau, 0, sizeof(uint64_t), s));
-    OTTERS_CUDA(cudaMemsetAsync(c->d_rows_scored, 0, sizeof(unsigned long long), s));
 
     const bool fused = k_eff <= kMaxFusedK;
     ScanPlan pl;
@@ -357,6 +408,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.warp_bytes = pl.warp_bytes;
     sp.off_w_rows = pl.off_w_rows;
     sp.off_w_info = pl.off_w_info;
+    sp.off_w_inv = pl.off_w_inv;
     sp.off_w_list = pl.off_w_list;
     sp.off_w_slots = pl.off_w_slots;
     sp.cta_keys = c->d_cta_keys;
@@ -365,17 +417,17 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
 
     uint32_t cur = 0;
     if (fused) {
-        rc = ensure_dev(&c->d_list[0], &c->list_cap, (size_t)kMaxFusedK, s);
+        rc = ensure_list0(c, kMaxFusedK);
         if (rc) return rc;
         cudaEventRecord(c->ev[2], s);
         for (uint32_t qi = 0; qi < q->nq; ++qi) {
-            OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(uint32_t), s));
+            if (qi) OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(uint32_t), s));  // qi == 0: begin_query()
             sp.query = c->d_query + (size_t)qi * dim_pad;
             sp.q_inv = q_inv[qi];
             sp.qid = qi;
             sp.tau_in = qi ? c->d_tau : nullptr;
             if (qi == 0 && q->nq == 1) cudaEventRecord(c->ev[3], s);
-            rc = launch_scan(sp, pl.launch, q->metric, false, s);
+            rc = launch_scan(sp, pl.launch, q->metric, false, c->scan_smem_configured, s);
             if (rc) return rc;
             if (qi == 0 && q->nq == 1) {
                 cudaEventRecord(c->ev[4], s);
@@ -399,6 +451,9 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             se.records = (qi + 1 == q->nq) ? d_records_out : nullptr;
             se.row_base = row_base;
             se.take_max = sp.take_max;
+            se.hdr = list_hdr(c, cur ^ 1);
+            se.rows_scored_src = c->d_rows_scored;
+            se.stats_src = stats_src;
             rc = launch_select(se, s);
             if (rc) return rc;
             cur ^= 1;
@@ -421,25 +476,19 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
                 return fail(OTTERS_ERR_NOMEM, "device allocation for the candidate sort failed");
             c->emit_cap = n_sort;
         }
-        if (c->list_cap < k_eff) {
-            OTTERS_CUDA(cudaStreamSynchronize(s));
-            cudaFree(c->d_list[0]);
-            c->d_list[0] = nullptr;
-            c->list_cap = 0;
-        }
-        rc = ensure_dev(&c->d_list[0], &c->list_cap, (size_t)std::max<uint64_t>(k_eff, kMaxFusedK), s);
+        rc = ensure_list0(c, k_eff);
         if (rc) return rc;
         sp.emit = c->d_emit;
         sp.emit_count = c->d_counter + 1;
         sp.emit_cap = (uint32_t)std::min<uint64_t>(n_sort, 0xFFFFFFFFull);
         cudaEventRecord(c->ev[2], s);
         for (uint32_t qi = 0; qi < q->nq; ++qi) {
-            OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(uint32_t), s));
+            if (qi) OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(uint32_t), s));
             sp.query = c->d_query + (size_t)qi * dim_pad;
             sp.q_inv = q_inv[qi];
             sp.qid = qi;
             sp.tau_in = qi ? c->d_tau : nullptr;
-            rc = launch_scan(sp, pl.launch, q->metric, true, s);
+            rc = launch_scan(sp, pl.launch, q->metric, true, c->scan_smem_configured, s);
             if (rc) return rc;
             // the running list lives in d_list[0] (single buffer: it is copied into the sort array first)
             rc = launch_append_prev(c->d_emit, c->d_counter + 1, qi ? c->d_list[0] : nullptr, qi ? c->d_list_count : nullptr,
@@ -448,7 +497,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             rc = launch_global_sort(c->d_emit, n_sort, s);
             if (rc) return rc;
             rc = launch_take_sorted(c->d_emit, c->d_counter + 1, qi ? c->d_list_count : nullptr, k_eff, c->d_list[0],
-                                    c->d_list_count, c->d_tau, s);
+                                    c->d_list_count, c->d_tau, list_hdr(c, 0), c->d_rows_scored, stats_src, s);
             if (rc) return rc;
             c->last.kernel_launches += 4;
         }
@@ -463,28 +512,24 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     return OTTERS_OK;
 }
 
-// copies the result list to the host and decodes it; synchronizes the stream
+// one D2H copy (header + ordered candidates), one stream sync, decode into the caller's arrays
 static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint64_t row_base, uint64_t* out_idx,
-                         float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, const void* extra_dev,
-                         size_t extra_bytes, void* extra_host) {
+                         float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, unsigned long long* stats_out) {
     cudaStream_t s = c->stream;
-    const size_t list_bytes = (size_t)run.k_eff * sizeof(Cand);
-    int rc = ensure_stage(c, list_bytes + 64 + extra_bytes + 64);
+    const size_t bytes = sizeof(ResultHeader) + (size_t)run.k_eff * sizeof(Cand);
+    int rc = ensure_pinned(&c->h_result, &c->h_result_bytes, bytes);
     if (rc) return rc;
-    uint8_t* h = c->h_stage;
-    const size_t off_cnt = round_up(list_bytes, 16);
-    const size_t off_scored = off_cnt + 16;
-    const size_t off_extra = off_scored + 16;
-    if (list_bytes)
-        OTTERS_CUDA(cudaMemcpyAsync(h, c->d_list[run.result_list], list_bytes, cudaMemcpyDeviceToHost, s));
-    OTTERS_CUDA(cudaMemcpyAsync(h + off_cnt, c->d_list_count + run.result_list, 4, cudaMemcpyDeviceToHost, s));
-    OTTERS_CUDA(cudaMemcpyAsync(h + off_scored, c->d_rows_scored, 8, cudaMemcpyDeviceToHost, s));
-    if (extra_bytes) OTTERS_CUDA(cudaMemcpyAsync(h + off_extra, extra_dev, extra_bytes, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[run.result_list], bytes, cudaMemcpyDeviceToHost, s));
     OTTERS_CUDA(cudaStreamSynchronize(s));
-    uint32_t n = *reinterpret_cast<uint32_t*>(h + off_cnt);
-    c->last.rows_scored = *reinterpret_cast<unsigned long long*>(h + off_scored);
-    if (extra_bytes) memcpy(extra_host, h + off_extra, extra_bytes);
-    const Cand* list = reinterpret_cast<const Cand*>(h);
+    c->stage_pending = false;
+    const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
+    const uint32_t n = hdr->count;
+    c->last.rows_scored = hdr->rows_scored;
+    if (stats_out) {
+        stats_out[0] = hdr->stats[0];
+        stats_out[1] = hdr->stats[1];
+    }
+    const Cand* list = reinterpret_cast<const Cand*>(c->h_result + sizeof(ResultHeader));
     uint64_t m = std::min<uint64_t>(n, cap);
     for (uint64_t i = 0; i < m; ++i) {
         if (out_idx) out_idx[i] = row_base + key_row(list[i].key);
@@ -550,17 +595,22 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
         c->own_stream = true;
     }
     c->grid_max = (uint32_t)c->sm_count * 2;
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_counter, 4 * sizeof(uint32_t)));
-    OTTERS_CUDA(cudaMemset(c->d_counter, 0, 4 * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_ctrl, 256));
+    OTTERS_CUDA(cudaMemset(c->d_ctrl, 0, 256));
+    c->d_counter = reinterpret_cast<uint32_t*>(c->d_ctrl);
+    c->d_list_count = reinterpret_cast<uint32_t*>(c->d_ctrl + 8);
+    c->d_tau = reinterpret_cast<uint64_t*>(c->d_ctrl + 16);
+    c->d_rows_scored = reinterpret_cast<unsigned long long*>(c->d_ctrl + 24);
+    c->d_stats = reinterpret_cast<unsigned long long*>(c->d_ctrl + 32);
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_keys, (size_t)c->grid_max * kMaxFusedK * sizeof(uint64_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_counts, (size_t)c->grid_max * sizeof(uint32_t)));
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_list[0], (size_t)kMaxFusedK * sizeof(Cand)));
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_list[1], (size_t)kMaxFusedK * sizeof(Cand)));
-    c->list_cap = kMaxFusedK;
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_list_count, 2 * sizeof(uint32_t)));
-    OTTERS_CUDA(cudaMemset(c->d_list_count, 0, 2 * sizeof(uint32_t)));
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_tau, sizeof(uint64_t)));
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_rows_scored, sizeof(unsigned long long)));
+    {
+        int rc0 = alloc_list(c.get(), 0, kMaxFusedK);
+        if (rc0) return rc0;
+        rc0 = alloc_list(c.get(), 1, kMaxFusedK);
+        if (rc0) return rc0;
+        c->list_cap = kMaxFusedK;
+    }
     c->scratch_elems = (uint32_t)pow2_at_least((uint64_t)(c->grid_max + 1) * kMaxFusedK);
     OTTERS_CUDA(cudaMalloc((void**)&c->d_scratch_keys, (size_t)c->scratch_elems * sizeof(uint64_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_scratch_src, (size_t)c->scratch_elems * sizeof(uint32_t)));
@@ -576,16 +626,13 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_query);
-    cudaFree(c->d_counter);
+    cudaFree(c->d_ctrl);
     cudaFree(c->d_cta_keys);
     cudaFree(c->d_cta_counts);
-    cudaFree(c->d_list[0]);
-    cudaFree(c->d_list[1]);
-    cudaFree(c->d_list_count);
-    cudaFree(c->d_tau);
+    cudaFree(c->d_list_raw[0]);
+    cudaFree(c->d_list_raw[1]);
     cudaFree(c->d_scratch_keys);
     cudaFree(c->d_scratch_src);
-    cudaFree(c->d_rows_scored);
     cudaFree(c->d_mask);
     cudaFree(c->d_emit);
     cudaFree(c->d_records);
@@ -719,14 +766,16 @@ extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query
     *out_len = 0;
     c->last = otters_last_work{};
     if (q->k == 0 || vs->st.n == 0) return OTTERS_OK;  // take(0) / empty store (tests/vec_store_tests.rs:430-445,488-499)
+    rc = begin_query(c);
+    if (rc) return rc;
     const uint32_t* d_mask = nullptr;
     uint32_t mask_words = 0;
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
     QueryRun run;
-    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, 0, &run);
+    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, 0, nullptr, &run);
     if (rc) return rc;
-    rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr, 0, nullptr);
+    rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
     if (rc) return rc;
     finish_work_stats(c, &vs->st, q);
     return OTTERS_OK;
@@ -804,7 +853,6 @@ struct otters_metastore {
     DevColumn* d_cols = nullptr;
     uint32_t* d_chunk_keep = nullptr;
     uint32_t* d_row_mask = nullptr;
-    unsigned long long* d_stats = nullptr;
     uint8_t* d_filter = nullptr;
     size_t d_filter_bytes = 0;
     bool has_stats = false;
@@ -828,7 +876,6 @@ extern "C" int otters_metastore_destroy(otters_metastore* ms) {
     cudaFree(ms->d_cols);
     cudaFree(ms->d_chunk_keep);
     cudaFree(ms->d_row_mask);
-    cudaFree(ms->d_stats);
     cudaFree(ms->d_filter);
     ms->st.release();
     delete ms;
@@ -1101,8 +1148,7 @@ extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* 
 
     const size_t keep_words = (ms->n_chunks + 31) / 32 + 1, mask_words = (p->n_rows + 31) / 32 + 1;
     if (cudaMalloc((void**)&ms->d_chunk_keep, keep_words * 4) != cudaSuccess ||
-        cudaMalloc((void**)&ms->d_row_mask, mask_words * 4) != cudaSuccess ||
-        cudaMalloc((void**)&ms->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess)
+        cudaMalloc((void**)&ms->d_row_mask, mask_words * 4) != cudaSuccess)
         return cleanup(fail(OTTERS_ERR_NOMEM, "device allocation for masks failed"));
     if (stats) {  // src/meta.rs:292-299
         stats->n_rows = p->n_rows;
@@ -1140,6 +1186,15 @@ static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vecto
         DevLeaf d{};
         d.col = in.col;
         d.op = in.op;
+        d.values = mc.d_values;
+        d.null_words = mc.d_nulls;
+        d.zmin = mc.d_zmin;
+        d.zmax = mc.d_zmax;
+        d.non_null = mc.d_non_null;
+        d.bloom = mc.d_bloom;
+        d.bloom_stride = mc.bloom_stride;
+        d.bloom_mbits = mc.d_bloom_mbits;
+        d.bloom_k = mc.d_bloom_k;
         switch (mc.dtype) {
         case OTTERS_DTYPE_INT32:
             if (in.kind != OTTERS_LIT_I64)
@@ -1201,9 +1256,8 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     mp.nq = nq;
     mp.chunk_keep = ms->d_chunk_keep;
     mp.row_mask = ms->d_row_mask;
-    mp.stats = ms->d_stats;
+    mp.stats = c->d_stats;
     *meta_bytes = 0;
-    OTTERS_CUDA(cudaMemsetAsync(ms->d_stats, 0, 4 * sizeof(unsigned long long), s));
     if (!f) {
         c->last.kernel_launches += 1;
         return launch_count_all_chunks(mp, s);
@@ -1214,16 +1268,19 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     if (rc) return rc;
     const size_t off_bytes = round_up(offs.size() * 4, 16);
     const size_t total = off_bytes + leaves.size() * sizeof(DevLeaf);
-    rc = ensure_stage(c, total + 64);
+    if (c->stage_pending) {  // an earlier asynchronous call may still be reading the pinned staging buffers
+        OTTERS_CUDA(cudaEventSynchronize(c->ev[7]));
+        c->stage_pending = false;
+    }
+    rc = ensure_pinned(&c->h_filter, &c->h_filter_bytes, total + 64);
     if (rc) return rc;
     rc = ensure_dev(&ms->d_filter, &ms->d_filter_bytes, total + 16, s);
     if (rc) return rc;
-    // the staging buffer may still be in flight for a previous async copy on this stream only if the
-    // previous call did not synchronise; every query path synchronises before returning.
-    memcpy(c->h_stage, offs.data(), offs.size() * 4);
-    if (!leaves.empty()) memcpy(c->h_stage + off_bytes, leaves.data(), leaves.size() * sizeof(DevLeaf));
-    OTTERS_CUDA(cudaMemcpyAsync(ms->d_filter, c->h_stage, total, cudaMemcpyHostToDevice, s));
-    OTTERS_CUDA(cudaStreamSynchronize(s));  // staging buffer is reused for the queries next
+    memcpy(c->h_filter, offs.data(), offs.size() * 4);
+    if (!leaves.empty()) memcpy(c->h_filter + off_bytes, leaves.data(), leaves.size() * sizeof(DevLeaf));
+    OTTERS_CUDA(cudaMemcpyAsync(ms->d_filter, c->h_filter, total, cudaMemcpyHostToDevice, s));
+    OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
+    c->stage_pending = true;
     mp.clause_off = reinterpret_cast<const uint32_t*>(ms->d_filter);
     mp.leaves = reinterpret_cast<const DevLeaf*>(ms->d_filter + off_bytes);
     mp.n_clauses = f->n_clauses;
@@ -1233,7 +1290,7 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     cudaEventRecord(c->ev[1], s);
     c->last.kernel_launches += 1;
     if (want_row_mask) {
-        rc = launch_rowmask(mp, s);
+        rc = launch_rowmask(mp, (uint32_t)leaves.size(), s);
         if (rc) return rc;
         c->last.kernel_launches += 1;
         cudaEventRecord(c->ev[6], s);
@@ -1251,9 +1308,10 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     int rc = validate_query(q, ms->st.dim, true);
     if (rc) return rc;
     if (q->row_mask_words) return fail(OTTERS_ERR_INVALID, "row masks are not part of MetaQueryPlan");
-    c->last = otters_last_work{};
     if (out_len) *out_len = 0;
     cudaStream_t s = c->stream;
+    rc = begin_query(c);
+    if (rc) return rc;
     // per-chunk collect() errors are swallowed by the reference (src/meta_compute.rs:182): an empty
     // batch or a wrong-dimension query returns no rows but still reports stats
     const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
@@ -1263,37 +1321,41 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     if (rc) return rc;
     unsigned long long hstats[4] = {0, 0, 0, 0};
     uint64_t n_out = 0;
+    auto fetch_stats_only = [&]() -> int {
+        int r2 = ensure_pinned(&c->h_result, &c->h_result_bytes, 64);
+        if (r2) return r2;
+        OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        c->stage_pending = false;
+        memcpy(hstats, c->h_result, 2 * sizeof(unsigned long long));
+        return OTTERS_OK;
+    };
     if (scan) {
         QueryRun run;
         rc = run_queries(c, &ms->st, q, filter ? ms->d_row_mask : nullptr, filter ? (uint32_t)((ms->st.n + 31) / 32) : 0,
-                         d_records, row_base, &run);
+                         d_records, row_base, c->d_stats, &run);
         if (rc) return rc;
-        if (!d_records || stats || out_len) {
-            if (d_records) {
-                // device-resident result: only the stats come back
-                OTTERS_CUDA(cudaMemcpyAsync(c->h_stage, ms->d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
-                OTTERS_CUDA(cudaStreamSynchronize(s));
-                memcpy(hstats, c->h_stage, sizeof(hstats));
-            } else {
-                rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, row_base, out_idx, out_score, out_qid, cap, &n_out,
-                                   ms->d_stats, sizeof(hstats), hstats);
+        if (d_records) {
+            if (stats) {  // device-resident result: only the stats come back (this synchronises)
+                rc = fetch_stats_only();
                 if (rc) return rc;
-                finish_work_stats(c, &ms->st, q);
             }
+        } else {
+            rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, row_base, out_idx, out_score, out_qid, cap, &n_out, hstats);
+            if (rc) return rc;
+            finish_work_stats(c, &ms->st, q);
         }
     } else {
         if (d_records) {
             // no scan: the record buffer must still hold k empty slots
             const uint64_t k_eff = std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq);
             if (k_eff) {
-                OTTERS_CUDA(cudaMemsetAsync(c->d_list_count, 0, 2 * sizeof(uint32_t), s));
                 rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, row_base, 1, d_records, s);
                 if (rc) return rc;
             }
         }
-        OTTERS_CUDA(cudaMemcpyAsync(c->h_stage, ms->d_stats, sizeof(hstats), cudaMemcpyDeviceToHost, s));
-        OTTERS_CUDA(cudaStreamSynchronize(s));
-        memcpy(hstats, c->h_stage, sizeof(hstats));
+        rc = fetch_stats_only();
+        if (rc) return rc;
     }
     if (out_len) *out_len = n_out;
     // stats (src/meta.rs:711-721)
@@ -1303,7 +1365,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     st.pruned_chunks = st.total_chunks - st.evaluated_chunks;
     st.vectors_compared = hstats[1];
     // every path above synchronised the stream unless the result stays on the device without stats
-    const bool synced = !(d_records && !stats && !out_len && scan);
+    const bool synced = !(d_records && !stats && scan);
     float ms_f = 0.f;
     if (synced && filter) {
         if (cudaEventElapsedTime(&ms_f, c->ev[0], c->ev[1]) == cudaSuccess) {
@@ -1360,7 +1422,9 @@ namespace otters {
 static int export_mask(otters_metastore* ms, const otters_filter* filter, bool rows, uint8_t* keep) {
     otters_ctx* c = ms->ctx;
     uint64_t mb;
-    int rc = run_meta_filter(ms, filter, 1, rows, &mb);
+    int rc = begin_query(c);
+    if (rc) return rc;
+    rc = run_meta_filter(ms, filter, 1, rows, &mb);
     if (rc) return rc;
     const uint64_t n = rows ? ms->st.n : ms->n_chunks;
     if (!filter) {
@@ -1434,16 +1498,17 @@ extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* 
     if (rc) return rc;
     otters_ctx* c = vs->st.ctx;
     DeviceGuard g(c->device);
-    c->last = otters_last_work{};
     const uint64_t k_eff = std::min<uint64_t>(q->k, vs->st.n * (uint64_t)q->nq);
     if (q->k == 0) return OTTERS_OK;
     if (k_eff == 0) return OTTERS_OK;
+    rc = begin_query(c);
+    if (rc) return rc;
     const uint32_t* d_mask = nullptr;
     uint32_t mask_words = 0;
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
     QueryRun run;
-    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, row_base, &run);
+    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, row_base, nullptr, &run);
 }
 
 extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, uint64_t n_records, uint64_t k, int32_t take_type,
@@ -1456,16 +1521,10 @@ extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, ui
     if (n_records > c->scratch_elems) return fail(OTTERS_ERR_UNSUPPORTED, "merge: too many records for the device merge");
     const uint64_t k_eff = std::min<uint64_t>(k, n_records);
     cudaStream_t s = c->stream;
-    if (c->list_cap < k_eff) {
-        OTTERS_CUDA(cudaStreamSynchronize(s));
-        cudaFree(c->d_list[0]);
-        c->d_list[0] = nullptr;
-        c->list_cap = 0;
-    }
-    int rc = ensure_dev(&c->d_list[0], &c->list_cap, (size_t)std::max<uint64_t>(k_eff, kMaxFusedK), s);
+    int rc = ensure_list0(c, k_eff);
     if (rc) return rc;
     rc = launch_merge_records((const otters_topk_record*)d_records, (uint32_t)n_records, (uint32_t)k_eff, take_type == OTTERS_TAKE_MAX,
-                              c->d_list[0], c->d_list_count, c->d_scratch_keys, c->d_scratch_src, c->scratch_elems, s);
+                              c->d_list[0], c->d_list_count, list_hdr(c, 0), c->d_scratch_keys, c->d_scratch_src, c->scratch_elems, s);
     if (rc) return rc;
     c->last.kernel_launches += 1;
     QueryRun run;
@@ -1476,6 +1535,5 @@ extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, ui
         *out_len = k_eff;
         return OTTERS_OK;
     }
-    OTTERS_CUDA(cudaMemsetAsync(c->d_rows_scored, 0, sizeof(unsigned long long), s));
-    return fetch_results(c, run, take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr, 0, nullptr);
+    return fetch_results(c, run, take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
 }

@@ -56,7 +56,7 @@ struct ScanParams {
     uint32_t nkc;               // slots steps per tile
     uint32_t pitch_s;           // floats per staged row in shared memory (== 8 mod 32)
     uint32_t slots;             // slots per warp
-    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_list, off_w_slots;
+    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
     // outputs (fused mode)
     uint64_t* cta_keys;         // [grid][k]
     uint32_t* cta_counts;       // [grid]
@@ -72,9 +72,20 @@ struct ScanLaunch {
     uint32_t grid, block, smem_bytes;
 };
 
-int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, cudaStream_t s);
+int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, uint32_t* smem_configured, cudaStream_t s);
 
 // ---- selection kernels ------------------------------------------------------------------------
+// Every result list in device memory is preceded by this 64-byte header, so that one D2H copy returns
+// the count, the instrumentation counters and the ordered candidates together.
+struct ResultHeader {
+    uint32_t count;
+    uint32_t pad;
+    unsigned long long rows_scored;
+    unsigned long long stats[4];  // [0] evaluated chunks, [1] vectors_compared
+    unsigned long long pad2[2];
+};
+static_assert(sizeof(ResultHeader) == 64, "ResultHeader must be 64 bytes");
+
 struct SelectParams {
     const uint64_t* cta_keys;
     const uint32_t* cta_counts;
@@ -95,19 +106,24 @@ struct SelectParams {
     otters_topk_record* records;
     uint64_t row_base;
     int32_t take_max;
+    // header of the output list + the counters copied into it
+    ResultHeader* hdr;
+    const unsigned long long* rows_scored_src;
+    const unsigned long long* stats_src;
 };
 int launch_select(const SelectParams& p, cudaStream_t s);
 
 // records (after all-gather) -> global best k
 int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out,
-                         uint32_t* out_count, uint64_t* scratch_keys, uint32_t* scratch_src, uint32_t scratch_elems,
-                         cudaStream_t s);
+                         uint32_t* out_count, ResultHeader* hdr, uint64_t* scratch_keys, uint32_t* scratch_src,
+                         uint32_t scratch_elems, cudaStream_t s);
 // full sort of a candidate array (emit-all path); n_pow2 elements, padded with key = 0
 int launch_global_sort(Cand* buf, uint64_t n_pow2, cudaStream_t s);
 int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, const uint32_t* prev_count, uint64_t n_pow2,
                        cudaStream_t s);
 int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
-                       uint32_t* out_count, uint64_t* tau_out, cudaStream_t s);
+                       uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr, const unsigned long long* rows_scored_src,
+                       const unsigned long long* stats_src, cudaStream_t s);
 int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
                             otters_topk_record* recs, cudaStream_t s);
 
@@ -134,7 +150,7 @@ struct DevColumn {
 
 enum LeafExec : int32_t { LEAF_I32 = 0, LEAF_I64 = 1, LEAF_F32 = 2, LEAF_F64 = 3, LEAF_STR = 4 };
 
-struct DevLeaf {
+struct DevLeaf {         // one lowered leaf, self-contained: carries the device pointers of its column
     uint32_t col;
     int32_t op;
     int32_t exec;        // LeafExec
@@ -146,6 +162,15 @@ struct DevLeaf {
     uint32_t code;
     uint32_t pad;
     uint64_t h1, h2;     // LEAF_STR: Bloom probe hashes of the literal
+    const void* values;
+    const uint32_t* null_words;
+    const void* zmin;
+    const void* zmax;
+    const uint32_t* non_null;
+    const uint64_t* bloom;
+    uint64_t bloom_stride;
+    const uint64_t* bloom_mbits;
+    const uint32_t* bloom_k;
 };
 
 struct DevFilter {       // variable-length: header, clause offsets, leaves (all in one device buffer)
@@ -167,7 +192,7 @@ struct MetaKernelParams {
     unsigned long long* stats;   // [0] evaluated chunks, [1] vectors_compared
 };
 int launch_prune(const MetaKernelParams& p, cudaStream_t s);
-int launch_rowmask(const MetaKernelParams& p, cudaStream_t s);
+int launch_rowmask(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s);
 int launch_count_all_chunks(const MetaKernelParams& p, cudaStream_t s);
 
 }  // namespace otters

@@ -38,19 +38,19 @@ __device__ __forceinline__ bool row_sat(int op, T v, T t) {
     }
 }
 
-__device__ __forceinline__ bool chunk_leaf_sat(const DevColumn& c, const DevLeaf& lf, uint32_t ch) {
-    if (c.non_null[ch] == 0) return false;  // every rule is ANDed with non_null > 0
+__device__ __forceinline__ bool chunk_leaf_sat(const DevLeaf& lf, uint32_t ch) {
+    if (lf.non_null[ch] == 0) return false;  // every rule is ANDed with non_null > 0
     switch (lf.exec) {
-    case LEAF_I32: return range_sat<int32_t>(lf.op, ((const int32_t*)c.zmin)[ch], ((const int32_t*)c.zmax)[ch], lf.i32);
-    case LEAF_I64: return range_sat<int64_t>(lf.op, ((const int64_t*)c.zmin)[ch], ((const int64_t*)c.zmax)[ch], lf.i64);
-    case LEAF_F32: return range_sat<float>(lf.op, ((const float*)c.zmin)[ch], ((const float*)c.zmax)[ch], lf.f32);
-    case LEAF_F64: return range_sat<double>(lf.op, ((const double*)c.zmin)[ch], ((const double*)c.zmax)[ch], lf.f64);
+    case LEAF_I32: return range_sat<int32_t>(lf.op, ((const int32_t*)lf.zmin)[ch], ((const int32_t*)lf.zmax)[ch], lf.i32);
+    case LEAF_I64: return range_sat<int64_t>(lf.op, ((const int64_t*)lf.zmin)[ch], ((const int64_t*)lf.zmax)[ch], lf.i64);
+    case LEAF_F32: return range_sat<float>(lf.op, ((const float*)lf.zmin)[ch], ((const float*)lf.zmax)[ch], lf.f32);
+    case LEAF_F64: return range_sat<double>(lf.op, ((const double*)lf.zmin)[ch], ((const double*)lf.zmax)[ch], lf.f64);
     default: {  // LEAF_STR — src/meta.rs:523-544
         if (lf.op == OTTERS_OP_NEQ) return true;
         if (lf.op != OTTERS_OP_EQ) return false;
-        const uint64_t* w = c.bloom + (size_t)ch * c.bloom_stride;
-        const uint64_t m = c.bloom_mbits[ch];
-        const uint32_t kh = c.bloom_k[ch];
+        const uint64_t* w = lf.bloom + (size_t)ch * lf.bloom_stride;
+        const uint64_t m = lf.bloom_mbits[ch];
+        const uint32_t kh = lf.bloom_k[ch];
         for (uint32_t i = 0; i < kh; ++i) {
             uint64_t bit = (lf.h1 + (uint64_t)i * lf.h2) % m;
             if (!((w[bit >> 6] >> (bit & 63)) & 1ull)) return false;
@@ -70,8 +70,7 @@ __global__ void prune_kernel(const __grid_constant__ MetaKernelParams p) {
         for (uint32_t ci = 0; ci < p.n_clauses && keep; ++ci) {
             bool any = false;
             for (uint32_t li = p.clause_off[ci]; li < p.clause_off[ci + 1] && !any; ++li) {
-                const DevLeaf lf = p.leaves[li];
-                any = chunk_leaf_sat(p.cols[lf.col], lf, ch);
+                any = chunk_leaf_sat(p.leaves[li], ch);
             }
             keep = any;
         }
@@ -100,22 +99,40 @@ __global__ void count_all_kernel(const __grid_constant__ MetaKernelParams p) {
     }
 }
 
-__device__ __forceinline__ bool row_leaf_sat(const DevColumn& c, const DevLeaf& lf, uint32_t row) {
-    if (c.null_words && ((c.null_words[row >> 5] >> (row & 31)) & 1u)) return false;
+__device__ __forceinline__ bool row_leaf_sat(const DevLeaf& lf, uint32_t row) {
+    const bool is_null = lf.null_words && ((lf.null_words[row >> 5] >> (row & 31)) & 1u);
+    bool sat;
     switch (lf.exec) {
-    case LEAF_I32: return row_sat<int32_t>(lf.op, ((const int32_t*)c.values)[row], lf.i32);
-    case LEAF_I64: return row_sat<int64_t>(lf.op, ((const int64_t*)c.values)[row], lf.i64);
-    case LEAF_F32: return row_sat<float>(lf.op, ((const float*)c.values)[row], lf.f32);
-    case LEAF_F64: return row_sat<double>(lf.op, ((const double*)c.values)[row], lf.f64);
+    case LEAF_I32: sat = row_sat<int32_t>(lf.op, ((const int32_t*)lf.values)[row], lf.i32); break;
+    case LEAF_I64: sat = row_sat<int64_t>(lf.op, ((const int64_t*)lf.values)[row], lf.i64); break;
+    case LEAF_F32: sat = row_sat<float>(lf.op, ((const float*)lf.values)[row], lf.f32); break;
+    case LEAF_F64: sat = row_sat<double>(lf.op, ((const double*)lf.values)[row], lf.f64); break;
     default: {  // dictionary-coded string equality (src/meta_compute.rs:291-318)
-        const bool eq = lf.code_valid && ((const uint32_t*)c.values)[row] == lf.code;
-        return lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
+        const bool eq = lf.code_valid && ((const uint32_t*)lf.values)[row] == lf.code;
+        sat = lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
     }
     }
+    return sat && !is_null;
 }
 
-// K0b: one thread per row, one 32-bit mask word per warp
-__global__ void rowmask_kernel(const __grid_constant__ MetaKernelParams p) {
+// K0b: one thread per row, one 32-bit mask word per warp.  The lowered filter is staged in shared memory
+// and every leaf of a surviving row is evaluated unconditionally, so the column loads of all leaves are
+// in flight together instead of forming a dependent chain.
+__global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ MetaKernelParams p, uint32_t n_leaves, int use_smem) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    const DevLeaf* leaves = p.leaves;
+    const uint32_t* clause_off = p.clause_off;
+    if (use_smem) {
+        DevLeaf* sl = reinterpret_cast<DevLeaf*>(fsm);
+        uint32_t* so = reinterpret_cast<uint32_t*>(fsm + (size_t)n_leaves * sizeof(DevLeaf));
+        const uint32_t words = n_leaves * (uint32_t)(sizeof(DevLeaf) / 4);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(sl)[i] = reinterpret_cast<const uint32_t*>(p.leaves)[i];
+        for (uint32_t i = threadIdx.x; i <= p.n_clauses; i += blockDim.x) so[i] = p.clause_off[i];
+        __syncthreads();
+        leaves = sl;
+        clause_off = so;
+    }
     const uint32_t n_words = (p.n_rows + 31) >> 5;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -125,13 +142,12 @@ __global__ void rowmask_kernel(const __grid_constant__ MetaKernelParams p) {
         if (row < p.n_rows) {
             const uint32_t ch = row / p.chunk_size;
             keep = (p.chunk_keep[ch >> 5] >> (ch & 31)) & 1u;
-            for (uint32_t ci = 0; ci < p.n_clauses && keep; ++ci) {
-                bool any = false;
-                for (uint32_t li = p.clause_off[ci]; li < p.clause_off[ci + 1] && !any; ++li) {
-                    const DevLeaf lf = p.leaves[li];
-                    any = row_leaf_sat(p.cols[lf.col], lf, row);
+            if (keep) {
+                for (uint32_t ci = 0; ci < p.n_clauses; ++ci) {
+                    bool any = false;
+                    for (uint32_t li = clause_off[ci]; li < clause_off[ci + 1]; ++li) any |= row_leaf_sat(leaves[li], row);
+                    keep &= any;
                 }
-                keep = any;
             }
         }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
@@ -148,12 +164,14 @@ int launch_prune(const MetaKernelParams& p, cudaStream_t s) {
     return OTTERS_OK;
 }
 
-int launch_rowmask(const MetaKernelParams& p, cudaStream_t s) {
+int launch_rowmask(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s) {
     if (p.n_rows == 0) return OTTERS_OK;
     uint32_t n_words = (p.n_rows + 31) >> 5;
     uint32_t blocks = (n_words + 7) / 8;  // 8 warps per block
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    rowmask_kernel<<<blocks, 256, 0, s>>>(p);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    size_t smem = (size_t)n_leaves * sizeof(DevLeaf) + ((size_t)p.n_clauses + 1) * 4;
+    int use_smem = smem <= 40 * 1024;
+    rowmask_kernel<<<blocks, 256, use_smem ? smem : 0, s>>>(p, n_leaves, use_smem);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

@@ -16,9 +16,10 @@
 //    ((l0+l1)+l2)+l3 + ((l4+l5)+l6)+l7, the dim%8 tail is a serial sum added last.
 //  * staged rows use a shared-memory pitch == 8 (mod 32) floats, so the 8 threads of a quarter warp
 //    (4 rows x 2 halves) hit 8 distinct 16-byte bank groups: conflict-free LDS.128.
-//  * candidates that beat the CTA's running threshold key are appended to a shared buffer under a
-//    lock; when the buffer fills, one warp bitonic-sorts it, keeps the best k and raises the
-//    threshold.  At exit every CTA publishes its best k keys (sorted) for K3.
+//  * candidates that beat the CTA's running threshold key are appended lock-free to a shared buffer
+//    (one atomicAdd reserves the slots); the warp whose reservation crosses the capacity bitonic-sorts
+//    the buffer, keeps the best k and raises the threshold.  At exit every CTA publishes its best k
+//    keys (sorted) for K3.
 #include "internal.h"
 
 namespace otters {
@@ -29,17 +30,17 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct CtaHdr {
     unsigned long long tau;  // candidates must have key > tau
-    uint32_t count;
-    uint32_t lock;
+    uint32_t count;          // slots reserved in the candidate buffer (may transiently exceed cap)
+    uint32_t written;        // slots whose key has been stored
 };
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
-// one warp: sort buf[0..cap) descending (entries >= count are zero), keep the best k
-__device__ void warp_compact(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, int lane) {
-    uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(&hdr->count);
+// one warp: sort buf[0..cap) best-first (entries >= cnt are zeroed first); the best min(cnt,k) end up in front
+__device__ void warp_sort(uint64_t* buf, uint32_t cnt, uint32_t cap, int lane) {
     for (uint32_t i = cnt + lane; i < cap; i += 32) buf[i] = 0ull;
     __syncwarp();
     for (uint32_t size = 2; size <= cap; size <<= 1) {
@@ -57,50 +58,62 @@ __device__ void warp_compact(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t 
             __syncwarp();
         }
     }
-    if (lane == 0) {
-        uint32_t n = cnt < k ? cnt : k;
-        hdr->count = n;
-        if (n == k) {
-            unsigned long long t = buf[k - 1];
-            if (t > hdr->tau) hdr->tau = t;
-        }
-    }
-    __syncwarp();
 }
 
-// append this warp's passing candidates to the CTA buffer
+// Lock-free append of this warp's passing candidates to the CTA buffer.  A warp reserves slots with one
+// shared-memory atomicAdd, stores its keys and bumps `written`.  The single warp whose reservation crosses
+// the capacity becomes the compactor: it waits until every earlier reservation has been written, sorts,
+// keeps the best k, raises the threshold and reopens the buffer; later arrivals wait for the reopen and
+// retry against the new threshold.
 __device__ void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, bool has, uint64_t key, int lane) {
-    if (lane == 0) {
-        const long long t0 = clock64();
-        while (atomicCAS(&hdr->lock, 0u, 1u) != 0u) {
-            __nanosleep(64);
-            if (clock64() - t0 > 4000000000ll) __trap();  // watchdog: never hang the GPU on a lost lock
+    for (;;) {
+        const uint64_t tau = ld_volatile_u64(&hdr->tau);
+        has = has && key > tau;
+        const unsigned m = __ballot_sync(FULL, has);
+        const uint32_t n = __popc(m);
+        if (!n) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&hdr->count, n);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + n <= cap) {
+            if (has) buf[base + __popc(m & ((1u << lane) - 1u))] = key;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&hdr->written, n);
+            }
+            return;
+        }
+        if (base <= cap) {
+            // compactor: valid entries are [0, base)
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (ld_volatile_u32(&hdr->written) != base) {
+                    if (clock64() - t0 > 4000000000ll) __trap();  // watchdog
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            warp_sort(buf, base, cap, lane);
+            if (lane == 0) {
+                const unsigned long long t = buf[k - 1];  // base > cap - 32 >= k
+                if (t > hdr->tau) *reinterpret_cast<volatile unsigned long long*>(&hdr->tau) = t;
+                *reinterpret_cast<volatile uint32_t*>(&hdr->written) = k;
+                __threadfence_block();
+                atomicExch(&hdr->count, k);
+            }
+            __syncwarp();
+        } else {
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (ld_volatile_u32(&hdr->count) > cap) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > 4000000000ll) __trap();  // watchdog
+                }
+            }
+            __syncwarp();
         }
     }
-    __syncwarp();
-    __threadfence_block();
-    uint64_t tau = ld_volatile_u64(&hdr->tau);
-    has = has && key > tau;
-    unsigned m = __ballot_sync(FULL, has);
-    uint32_t n = __popc(m);
-    if (n) {
-        uint32_t cnt = *reinterpret_cast<volatile uint32_t*>(&hdr->count);
-        if (cnt + n > cap) {
-            warp_compact(hdr, buf, cap, k, lane);
-            cnt = *reinterpret_cast<volatile uint32_t*>(&hdr->count);
-            tau = ld_volatile_u64(&hdr->tau);
-            has = has && key > tau;
-            m = __ballot_sync(FULL, has);
-            n = __popc(m);
-        }
-        if (has) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&hdr->count) = cnt + n;
-    }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) atomicExch(&hdr->lock, 0u);
-    __syncwarp();
 }
 
 template <int METRIC, bool EMIT_ALL>
@@ -117,6 +130,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbase);
     uint32_t* slot_rows = reinterpret_cast<uint32_t*>(wbase + p.off_w_rows);
     uint32_t* slot_info = reinterpret_cast<uint32_t*>(wbase + p.off_w_info);
+    float* slot_inv = reinterpret_cast<float*>(wbase + p.off_w_inv);  // per-slot inverse norms of the tile's rows
     uint8_t* rowlist = wbase + p.off_w_list;
     float* slot_base = reinterpret_cast<float*>(wbase + p.off_w_slots);
     const uint32_t slot_floats = kTileRows * p.pitch_s;
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     if (tid == 0) {
         hdr->tau = tau0;
         hdr->count = 0;
-        hdr->lock = 0;
+        hdr->written = 0;
     }
     for (uint32_t i = tid; i < p.dim_pad; i += blockDim.x) qs[i] = p.query[i];
     if (lane == 0) {
@@ -201,9 +215,13 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
             mbar_arrive_expect_tx(&bars[slot], tile_cnt * bytes);
         }
         __syncwarp();
-        if (lane < (int)tile_cnt)
+        if (lane < (int)tile_cnt) {
             bulk_g2s_hint(slot_base + (size_t)slot * slot_floats + (size_t)lane * p.pitch_s,
                           p.vectors + (size_t)row * p.pitch_g + c0, bytes, &bars[slot], l2pol);
+            // the row's precomputed inverse norm rides along as a 4-byte cp.async (LDGSTS): its latency
+            // overlaps the bulk copy instead of being exposed in the epilogue
+            if (METRIC == OTTERS_METRIC_COSINE && kc_i == 0) cp_async_4(&slot_inv[slot * kTileRows + lane], p.inv_norms + row);
+        }
         if (++kc_i == p.nkc) {
             kc_i = 0;
             list_pos += kTileRows;
@@ -229,7 +247,11 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         if (kci == 0) {
             a0 = a1 = a2 = a3 = 0.f;
             my_row = slot_rows[slot * kTileRows + r];
-            if (METRIC == OTTERS_METRIC_COSINE) rinv = (r < (int)cnt) ? __ldg(p.inv_norms + my_row) : 0.f;
+            if (METRIC == OTTERS_METRIC_COSINE) {
+                cp_async_wait_all();
+                __syncwarp();
+                rinv = (r < (int)cnt) ? slot_inv[slot * kTileRows + r] : 0.f;
+            }
         }
         const uint32_t c0 = kci * p.kc;
         const uint32_t cend = c0 + p.kc < dim8 ? c0 + p.kc : dim8;
@@ -318,8 +340,9 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     if (!EMIT_ALL) {
         __syncthreads();
         if (warp == 0) {
-            warp_compact(hdr, cbuf, p.cap, p.k, lane);
-            uint32_t n = hdr->count;
+            const uint32_t cnt = hdr->count;  // every push has completed: cnt <= cap and written == cnt
+            warp_sort(cbuf, cnt, p.cap, lane);
+            const uint32_t n = cnt < p.k ? cnt : p.k;
             for (uint32_t i = lane; i < n; i += 32) p.cta_keys[(size_t)blockIdx.x * p.k + i] = cbuf[i];
             if (lane == 0) p.cta_counts[blockIdx.x] = n;
         }
@@ -327,11 +350,14 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
 }
 
 template <int METRIC, bool EMIT>
-int launch_one(const ScanParams& p, const ScanLaunch& l, cudaStream_t s) {
+int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
     auto kern = scan_kernel<METRIC, EMIT>;
-    static thread_local int configured_device = -1;
-    (void)configured_device;
-    OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+    // the opt-in shared-memory limit is sticky per function and device: raise it only when it grows
+    uint32_t& have = smem_configured[METRIC * 2 + (EMIT ? 1 : 0)];
+    if (l.smem_bytes > have) {
+        OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
+        have = l.smem_bytes;
+    }
     kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
@@ -339,15 +365,15 @@ int launch_one(const ScanParams& p, const ScanLaunch& l, cudaStream_t s) {
 
 }  // namespace
 
-int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, cudaStream_t s) {
+int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, uint32_t* smem_configured, cudaStream_t s) {
     switch (metric) {
     case OTTERS_METRIC_COSINE:
-        return emit_all ? launch_one<OTTERS_METRIC_COSINE, true>(p, l, s) : launch_one<OTTERS_METRIC_COSINE, false>(p, l, s);
+        return emit_all ? launch_one<OTTERS_METRIC_COSINE, true>(p, l, smem_configured, s) : launch_one<OTTERS_METRIC_COSINE, false>(p, l, smem_configured, s);
     case OTTERS_METRIC_EUCLIDEAN:
-        return emit_all ? launch_one<OTTERS_METRIC_EUCLIDEAN, true>(p, l, s)
-                        : launch_one<OTTERS_METRIC_EUCLIDEAN, false>(p, l, s);
+        return emit_all ? launch_one<OTTERS_METRIC_EUCLIDEAN, true>(p, l, smem_configured, s)
+                        : launch_one<OTTERS_METRIC_EUCLIDEAN, false>(p, l, smem_configured, s);
     case OTTERS_METRIC_DOT:
-        return emit_all ? launch_one<OTTERS_METRIC_DOT, true>(p, l, s) : launch_one<OTTERS_METRIC_DOT, false>(p, l, s);
+        return emit_all ? launch_one<OTTERS_METRIC_DOT, true>(p, l, smem_configured, s) : launch_one<OTTERS_METRIC_DOT, false>(p, l, smem_configured, s);
     }
     return fail(OTTERS_ERR_INVALID, "Search metric is not set");
 }

@@ -175,13 +175,19 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
     if (threadIdx.x == 0) {
         *p.out_count = kk;
         if (p.tau_out) *p.tau_out = (kk == p.k && kk > 0) ? keys[kk - 1] : 0ull;
+        if (p.hdr) {
+            p.hdr->count = kk;
+            p.hdr->rows_scored = p.rows_scored_src ? *p.rows_scored_src : 0ull;
+            p.hdr->stats[0] = p.stats_src ? p.stats_src[0] : 0ull;
+            p.hdr->stats[1] = p.stats_src ? p.stats_src[1] : 0ull;
+        }
     }
 }
 
 // ---- sharded path: merge gathered records --------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
-                     uint64_t* scratch_keys, uint32_t* scratch_src) {
+                     ResultHeader* hdr, uint64_t* scratch_keys, uint32_t* scratch_src) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm);
     uint32_t* src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
@@ -217,7 +223,14 @@ merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int
         c.pad = 0;
         out[i] = c;
     }
-    if (threadIdx.x == 0) *out_count = kk;
+    if (threadIdx.x == 0) {
+        *out_count = kk;
+        if (hdr) {
+            hdr->count = kk;
+            hdr->rows_scored = 0ull;
+            hdr->stats[0] = hdr->stats[1] = 0ull;
+        }
+    }
 }
 
 // ---- large-k path: full sort of a candidate array -------------------------------------------------
@@ -282,7 +295,8 @@ __global__ void append_prev_kernel(Cand* buf, const uint32_t* emit_count, const 
 }
 
 __global__ void take_sorted_kernel(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k,
-                                   Cand* out, uint32_t* out_count, uint64_t* tau_out) {
+                                   Cand* out, uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr,
+                                   const unsigned long long* rows_scored_src, const unsigned long long* stats_src) {
     const uint64_t total = (uint64_t)*emit_count + (prev_count ? *prev_count : 0);
     const uint64_t kk = total < k ? total : k;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,6 +305,12 @@ __global__ void take_sorted_kernel(const Cand* buf, const uint32_t* emit_count, 
     if (i == 0) {
         *out_count = (uint32_t)kk;
         if (tau_out) *tau_out = (kk == k && kk > 0) ? buf[kk - 1].key : 0ull;
+        if (hdr) {
+            hdr->count = (uint32_t)kk;
+            hdr->rows_scored = rows_scored_src ? *rows_scored_src : 0ull;
+            hdr->stats[0] = stats_src ? stats_src[0] : 0ull;
+            hdr->stats[1] = stats_src ? stats_src[1] : 0ull;
+        }
     }
 }
 
@@ -317,20 +337,26 @@ constexpr size_t kSelectSmemBytes = (size_t)kSelectSmemElems * 12;
 }  // namespace
 
 int launch_select(const SelectParams& p, cudaStream_t s) {
-    OTTERS_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        OTTERS_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
+        configured_dev = dev;
+    }
     select_kernel<<<1, 1024, kSelectSmemBytes, s>>>(p);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
 
 int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
-                         uint64_t* scratch_keys, uint32_t* scratch_src, uint32_t scratch_elems, cudaStream_t s) {
+                         ResultHeader* hdr, uint64_t* scratch_keys, uint32_t* scratch_src, uint32_t scratch_elems, cudaStream_t s) {
     uint32_t P = 2;
     while (P < n) P <<= 1;
     if (P > kSelectSmemElems && P > scratch_elems) return fail(OTTERS_ERR_UNSUPPORTED, "merge: too many records");
     OTTERS_CUDA(
         cudaFuncSetAttribute(merge_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
-    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, take_max, out, out_count, scratch_keys, scratch_src);
+    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, take_max, out, out_count, hdr, scratch_keys, scratch_src);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
@@ -358,8 +384,9 @@ int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, 
 }
 
 int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
-                       uint32_t* out_count, uint64_t* tau_out, cudaStream_t s) {
-    take_sorted_kernel<<<256, 256, 0, s>>>(buf, emit_count, prev_count, k, out, out_count, tau_out);
+                       uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr, const unsigned long long* rows_scored_src,
+                       const unsigned long long* stats_src, cudaStream_t s) {
+    take_sorted_kernel<<<256, 256, 0, s>>>(buf, emit_count, prev_count, k, out, out_count, tau_out, hdr, rows_scored_src, stats_src);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
