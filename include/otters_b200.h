@@ -91,7 +91,8 @@ typedef struct {
     uint32_t slots_per_warp;
     uint32_t kc_floats;    /* columns staged per slot (multiple of 8) */
     uint32_t ctas_per_sm;
-    uint32_t unit_rows;    /* reserved */
+    uint32_t unit_rows;    /* 32, 64 or 128 rows per dynamically scheduled work unit */
+    uint32_t disable_fused_predicate; /* 1: evaluate the row predicate in its own kernel instead of inside the scan */
 } otters_scan_tuning;
 OTTERS_API int otters_ctx_set_tuning(otters_ctx *ctx, const otters_scan_tuning *t);
 

@@ -33,6 +33,7 @@ class ScanTuning(C.Structure):
         ("kc_floats", C.c_uint32),
         ("ctas_per_sm", C.c_uint32),
         ("unit_rows", C.c_uint32),
+        ("disable_fused_predicate", C.c_uint32),
     ]
 
 

@@ -88,7 +88,10 @@ struct otters_ctx {
     cudaEvent_t ev[8]{};
     bool stage_pending = false;   // an async H2D copy out of h_stage is in flight (ev[7] marks its end)
     bool timed_single = false;    // ev[3]/ev[4] bracket the single scan kernel of the last query
-    bool timed_meta = false;      // ev[0]/ev[1]/ev[6] bracket prune / row-mask of the last query
+    bool timed_meta = false;      // ev[0]/ev[1] bracket the prune kernel of the last query
+    bool timed_rowmask = false;   // ev[1]/ev[6] bracket the stand-alone row-mask kernel of the last query
+    uint32_t last_dim = 0;        // of the last scan (for the algorithmic-bytes figure)
+    int32_t last_metric = 0;
 };
 
 namespace otters {
@@ -110,6 +113,14 @@ static int ensure_stage(otters_ctx* c, size_t bytes) {
     return OTTERS_OK;
 }
 
+// elapsed time between two recorded, completed events; never leaves a CUDA error behind
+static bool elapsed_ms(cudaEvent_t a, cudaEvent_t b, float* ms) {
+    if (cudaEventElapsedTime(ms, a, b) == cudaSuccess) return true;
+    cudaGetLastError();
+    *ms = 0.f;
+    return false;
+}
+
 static int ensure_pinned(uint8_t** ptr, size_t* cap, size_t bytes) {
     if (bytes <= *cap) return OTTERS_OK;
     if (*ptr) cudaFreeHost(*ptr);
@@ -125,6 +136,7 @@ static int ensure_pinned(uint8_t** ptr, size_t* cap, size_t bytes) {
 static int begin_query(otters_ctx* c) {
     OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl, 0, 64, c->stream));
     c->last = otters_last_work{};
+    c->timed_single = c->timed_meta = c->timed_rowmask = false;
     return OTTERS_OK;
 }
 
@@ -249,19 +261,31 @@ struct VecStorage {
 };
 
 // ---- scan planning ---------------------------------------------------------------------------------
+struct FusedFilter {  // device-side lowered filter evaluated inside the scan kernel
+    const DevLeaf* leaves = nullptr;
+    const uint32_t* clause_off = nullptr;
+    uint32_t n_clauses = 0, n_leaves = 0;
+    const uint32_t* chunk_keep = nullptr;
+    uint32_t chunk_size = 1;
+    size_t smem_bytes() const { return round_up((size_t)n_leaves * sizeof(DevLeaf) + ((size_t)n_clauses + 1) * 4, 128); }
+};
+constexpr size_t kMaxFusedFilterBytes = 16 * 1024;
+
 struct ScanPlan {
     ScanLaunch launch;
+    uint32_t off_filter;
     uint32_t kc, nkc, pitch_s, slots, unit_rows, n_units, cap;
     uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
 };
 
-static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, ScanPlan* out) {
+static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, size_t filter_bytes, ScanPlan* out) {
     ScanPlan pl{};
     const otters_scan_tuning& t = c->tuning;
     pl.cap = k_fused ? (uint32_t)pow2_at_least(std::max<uint32_t>(2 * k_fused, 64)) : 0;
     const uint32_t hdr = (uint32_t)round_up(16 + (uint64_t)pl.cap * 8, 128);
     pl.off_query = hdr;
-    pl.off_warps = (uint32_t)round_up((uint64_t)hdr + (uint64_t)dim_pad * 4, 128);
+    pl.off_filter = (uint32_t)round_up((uint64_t)hdr + (uint64_t)dim_pad * 4, 128);
+    pl.off_warps = (uint32_t)(pl.off_filter + filter_bytes);
     const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
     if (pl.off_warps + 4096 > budget) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
 
@@ -349,12 +373,14 @@ static float host_inv_norm(const float* v, uint32_t dim) {
 
 static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const uint32_t* d_row_mask,
                        uint32_t row_mask_words, otters_topk_record* d_records_out, uint64_t row_base,
-                       const unsigned long long* stats_src, QueryRun* run) {
+                       const unsigned long long* stats_src, const FusedFilter* ff, QueryRun* run) {
     const uint32_t dim_pad = st->pitch;
     const uint64_t n_rows = st->n;
     const uint64_t k_eff = std::min<uint64_t>(q->k, n_rows * (uint64_t)q->nq);
     run->k_eff = k_eff;
     run->result_list = 0;
+    c->last_dim = st->dim;
+    c->last_metric = q->metric;
     cudaStream_t s = c->stream;
 
     // stage queries (zero padded to the stored pitch) and their inverse norms
@@ -374,11 +400,10 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     OTTERS_CUDA(cudaMemcpyAsync(c->d_query, hq, qfloats * 4, cudaMemcpyHostToDevice, s));
     OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
     c->stage_pending = true;
-    c->timed_single = false;
 
     const bool fused = k_eff <= kMaxFusedK;
     ScanPlan pl;
-    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, &pl);
+    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, ff ? ff->smem_bytes() : 0, &pl);
     if (rc) return rc;
 
     ScanParams sp{};
@@ -390,6 +415,15 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.n_rows = (uint32_t)n_rows;
     sp.row_mask = d_row_mask;
     sp.row_mask_words = row_mask_words;
+    if (ff) {
+        sp.flt_leaves = ff->leaves;
+        sp.flt_clause_off = ff->clause_off;
+        sp.flt_n_clauses = ff->n_clauses;
+        sp.flt_n_leaves = ff->n_leaves;
+        sp.chunk_keep = ff->chunk_keep;
+        sp.chunk_size = ff->chunk_size;
+    }
+    sp.off_filter = pl.off_filter;
     sp.n_units = pl.n_units;
     sp.unit_rows = pl.unit_rows;
     sp.unit_counter = c->d_counter;
@@ -540,13 +574,13 @@ static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint
     return OTTERS_OK;
 }
 
-static void finish_work_stats(otters_ctx* c, const VecStorage* st, const otters_vec_query* q) {
+static void finish_work_stats(otters_ctx* c) {
     // only called after the stream was synchronised, so all events have completed
     float ms = 0.f;
-    if (c->timed_single && cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) c->last.scan_ms = ms;
-    else if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[5]) == cudaSuccess) c->last.scan_ms = ms;
-    if (c->timed_single && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->last.select_ms = ms;
-    const uint64_t per_row = (uint64_t)st->dim * 4 + (q->metric == OTTERS_METRIC_COSINE ? 4 : 0);
+    if (c->timed_single && elapsed_ms(c->ev[3], c->ev[4], &ms)) c->last.scan_ms = ms;
+    else if (elapsed_ms(c->ev[2], c->ev[5], &ms)) c->last.scan_ms = ms;
+    if (c->timed_single && elapsed_ms(c->ev[4], c->ev[5], &ms)) c->last.select_ms = ms;
+    const uint64_t per_row = (uint64_t)c->last_dim * 4 + (c->last_metric == OTTERS_METRIC_COSINE ? 4 : 0);
     c->last.scan_bytes = c->last.rows_scored * per_row;
 }
 
@@ -773,11 +807,11 @@ extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
     QueryRun run;
-    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, 0, nullptr, &run);
+    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, 0, nullptr, nullptr, &run);
     if (rc) return rc;
     rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
     if (rc) return rc;
-    finish_work_stats(c, &vs->st, q);
+    finish_work_stats(c);
     return OTTERS_OK;
 }
 
@@ -855,6 +889,7 @@ struct otters_metastore {
     uint32_t* d_row_mask = nullptr;
     uint8_t* d_filter = nullptr;
     size_t d_filter_bytes = 0;
+    FusedFilter cur_filter;       // where the last lowered filter lives on the device
     bool has_stats = false;
     otters_query_stats last{};
 };
@@ -1245,7 +1280,8 @@ static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vecto
 }
 
 // enqueues K0 (+K0b); leaves chunk_keep / row_mask / stats on the device
-static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_t nq, bool want_row_mask, uint64_t* meta_bytes) {
+static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_t nq, bool want_row_mask, bool force_row_mask,
+                           uint64_t* meta_bytes) {
     otters_ctx* c = ms->ctx;
     cudaStream_t s = c->stream;
     MetaKernelParams mp{};
@@ -1284,16 +1320,27 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     mp.clause_off = reinterpret_cast<const uint32_t*>(ms->d_filter);
     mp.leaves = reinterpret_cast<const DevLeaf*>(ms->d_filter + off_bytes);
     mp.n_clauses = f->n_clauses;
+    ms->cur_filter.leaves = mp.leaves;
+    ms->cur_filter.clause_off = mp.clause_off;
+    ms->cur_filter.n_clauses = f->n_clauses;
+    ms->cur_filter.n_leaves = (uint32_t)leaves.size();
+    ms->cur_filter.chunk_keep = ms->d_chunk_keep;
+    ms->cur_filter.chunk_size = (uint32_t)ms->chunk_size;
+    if (want_row_mask && !force_row_mask && !c->tuning.disable_fused_predicate &&
+        ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes)
+        want_row_mask = false;  // the scan kernel evaluates the predicate itself (fused K0b)
     cudaEventRecord(c->ev[0], s);
     rc = launch_prune(mp, s);
     if (rc) return rc;
     cudaEventRecord(c->ev[1], s);
+    c->timed_meta = true;
     c->last.kernel_launches += 1;
     if (want_row_mask) {
         rc = launch_rowmask(mp, (uint32_t)leaves.size(), s);
         if (rc) return rc;
         c->last.kernel_launches += 1;
         cudaEventRecord(c->ev[6], s);
+        c->timed_rowmask = true;
     }
     // algorithmic metadata bytes: zonemap entries per leaf + column values/null bits of evaluated rows are
     // accounted by the caller once the evaluated-chunk count is known
@@ -1317,7 +1364,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
     const bool scan = !chunk_err && q->k > 0 && ms->st.n > 0;
     uint64_t meta_bytes = 0;
-    rc = run_meta_filter(ms, filter, q->nq, scan && filter, &meta_bytes);
+    rc = run_meta_filter(ms, filter, q->nq, scan && filter, false, &meta_bytes);
     if (rc) return rc;
     unsigned long long hstats[4] = {0, 0, 0, 0};
     uint64_t n_out = 0;
@@ -1332,8 +1379,10 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     };
     if (scan) {
         QueryRun run;
-        rc = run_queries(c, &ms->st, q, filter ? ms->d_row_mask : nullptr, filter ? (uint32_t)((ms->st.n + 31) / 32) : 0,
-                         d_records, row_base, c->d_stats, &run);
+        const bool fuse = filter && !c->tuning.disable_fused_predicate && ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes;
+        rc = run_queries(c, &ms->st, q, (filter && !fuse) ? ms->d_row_mask : nullptr,
+                         (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, row_base, c->d_stats,
+                         fuse ? &ms->cur_filter : nullptr, &run);
         if (rc) return rc;
         if (d_records) {
             if (stats) {  // device-resident result: only the stats come back (this synchronises)
@@ -1343,7 +1392,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
         } else {
             rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, row_base, out_idx, out_score, out_qid, cap, &n_out, hstats);
             if (rc) return rc;
-            finish_work_stats(c, &ms->st, q);
+            finish_work_stats(c);
         }
     } else {
         if (d_records) {
@@ -1367,16 +1416,14 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     // every path above synchronised the stream unless the result stays on the device without stats
     const bool synced = !(d_records && !stats && scan);
     float ms_f = 0.f;
-    if (synced && filter) {
-        if (cudaEventElapsedTime(&ms_f, c->ev[0], c->ev[1]) == cudaSuccess) {
-            st.prune_s = ms_f * 1e-3;
-            c->last.prune_ms = ms_f;
-        }
-        if (scan && cudaEventElapsedTime(&ms_f, c->ev[1], c->ev[6]) == cudaSuccess) c->last.rowmask_ms = ms_f;
+    if (synced && c->timed_meta && elapsed_ms(c->ev[0], c->ev[1], &ms_f)) {
+        st.prune_s = ms_f * 1e-3;
+        c->last.prune_ms = ms_f;
     }
+    if (synced && c->timed_rowmask && elapsed_ms(c->ev[1], c->ev[6], &ms_f)) c->last.rowmask_ms = ms_f;
     if (synced && scan) {
-        if (cudaEventElapsedTime(&ms_f, c->ev[2], c->ev[5]) == cudaSuccess) st.score_s = ms_f * 1e-3 + c->last.rowmask_ms * 1e-3;
-        if (c->timed_single && cudaEventElapsedTime(&ms_f, c->ev[4], c->ev[5]) == cudaSuccess) {
+        if (elapsed_ms(c->ev[2], c->ev[5], &ms_f)) st.score_s = ms_f * 1e-3 + c->last.rowmask_ms * 1e-3;
+        if (c->timed_single && elapsed_ms(c->ev[4], c->ev[5], &ms_f)) {
             st.merge_s = ms_f * 1e-3;
             st.score_s -= st.merge_s;
             c->last.select_ms = ms_f;
@@ -1424,7 +1471,7 @@ static int export_mask(otters_metastore* ms, const otters_filter* filter, bool r
     uint64_t mb;
     int rc = begin_query(c);
     if (rc) return rc;
-    rc = run_meta_filter(ms, filter, 1, rows, &mb);
+    rc = run_meta_filter(ms, filter, 1, rows, true, &mb);
     if (rc) return rc;
     const uint64_t n = rows ? ms->st.n : ms->n_chunks;
     if (!filter) {
@@ -1508,7 +1555,7 @@ extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* 
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
     QueryRun run;
-    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, row_base, nullptr, &run);
+    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, row_base, nullptr, nullptr, &run);
 }
 
 extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, uint64_t n_records, uint64_t k, int32_t take_type,
@@ -1524,7 +1571,8 @@ extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, ui
     int rc = ensure_list0(c, k_eff);
     if (rc) return rc;
     rc = launch_merge_records((const otters_topk_record*)d_records, (uint32_t)n_records, (uint32_t)k_eff, take_type == OTTERS_TAKE_MAX,
-                              c->d_list[0], c->d_list_count, list_hdr(c, 0), c->d_scratch_keys, c->d_scratch_src, c->scratch_elems, s);
+                              c->d_list[0], c->d_list_count, list_hdr(c, 0), c->d_rows_scored, c->d_scratch_keys, c->d_scratch_src,
+                              c->scratch_elems, s);
     if (rc) return rc;
     c->last.kernel_launches += 1;
     QueryRun run;
@@ -1535,5 +1583,8 @@ extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, ui
         *out_len = k_eff;
         return OTTERS_OK;
     }
-    return fetch_results(c, run, take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
+    rc = fetch_results(c, run, take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
+    if (rc) return rc;
+    finish_work_stats(c);  // timing of this rank's local scan (the events completed with the sync above)
+    return OTTERS_OK;
 }

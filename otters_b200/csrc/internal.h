@@ -27,6 +27,8 @@ constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work un
 constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
 constexpr uint32_t kSelectSmemElems = 8192;
 
+struct DevLeaf;
+
 // ---- scan kernel ------------------------------------------------------------------------------
 struct ScanParams {
     const float* vectors;       // [n_rows][pitch_g]
@@ -39,6 +41,15 @@ struct ScanParams {
     uint32_t n_rows;
     const uint32_t* row_mask;   // Lsb0 32-bit words, bit=1 keep; null = all rows
     uint32_t row_mask_words;    // words available; rows past them are kept
+    // fused predicate (MetaStore): when flt_leaves != null the producer evaluates the CNF itself for the
+    // rows of every unit whose chunk survived pruning, instead of reading a precomputed row mask
+    const DevLeaf* flt_leaves;
+    const uint32_t* flt_clause_off;
+    uint32_t flt_n_clauses;
+    uint32_t flt_n_leaves;
+    const uint32_t* chunk_keep; // Lsb0 words, one bit per chunk
+    uint32_t chunk_size;
+    uint32_t off_filter;        // shared-memory offset of the staged filter
     uint32_t n_units;
     uint32_t unit_rows;         // 32, 64 or 128
     uint32_t* unit_counter;
@@ -115,8 +126,8 @@ int launch_select(const SelectParams& p, cudaStream_t s);
 
 // records (after all-gather) -> global best k
 int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out,
-                         uint32_t* out_count, ResultHeader* hdr, uint64_t* scratch_keys, uint32_t* scratch_src,
-                         uint32_t scratch_elems, cudaStream_t s);
+                         uint32_t* out_count, ResultHeader* hdr, const unsigned long long* rows_scored_src, uint64_t* scratch_keys,
+                         uint32_t* scratch_src, uint32_t scratch_elems, cudaStream_t s);
 // full sort of a candidate array (emit-all path); n_pow2 elements, padded with key = 0
 int launch_global_sort(Cand* buf, uint64_t n_pow2, cudaStream_t s);
 int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, const uint32_t* prev_count, uint64_t n_pow2,

@@ -10,6 +10,7 @@
 // fails every leaf (including Neq); NaN satisfies only Neq; literals are cast to the column width
 // on the host (api.cu) exactly as the reference does.
 #include "internal.h"
+#include "predicate.cuh"
 
 namespace otters {
 namespace {
@@ -23,18 +24,6 @@ __device__ __forceinline__ bool range_sat(int op, T mn, T mx, T t) {
     case OTTERS_OP_GT: return mx > t;
     case OTTERS_OP_GTE: return mx >= t;
     default: return true;  // Neq
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ bool row_sat(int op, T v, T t) {
-    switch (op) {
-    case OTTERS_OP_EQ: return v == t;
-    case OTTERS_OP_NEQ: return v != t;
-    case OTTERS_OP_LT: return v < t;
-    case OTTERS_OP_LTE: return v <= t;
-    case OTTERS_OP_GT: return v > t;
-    default: return v >= t;
     }
 }
 
@@ -99,22 +88,6 @@ __global__ void count_all_kernel(const __grid_constant__ MetaKernelParams p) {
     }
 }
 
-__device__ __forceinline__ bool row_leaf_sat(const DevLeaf& lf, uint32_t row) {
-    const bool is_null = lf.null_words && ((lf.null_words[row >> 5] >> (row & 31)) & 1u);
-    bool sat;
-    switch (lf.exec) {
-    case LEAF_I32: sat = row_sat<int32_t>(lf.op, ((const int32_t*)lf.values)[row], lf.i32); break;
-    case LEAF_I64: sat = row_sat<int64_t>(lf.op, ((const int64_t*)lf.values)[row], lf.i64); break;
-    case LEAF_F32: sat = row_sat<float>(lf.op, ((const float*)lf.values)[row], lf.f32); break;
-    case LEAF_F64: sat = row_sat<double>(lf.op, ((const double*)lf.values)[row], lf.f64); break;
-    default: {  // dictionary-coded string equality (src/meta_compute.rs:291-318)
-        const bool eq = lf.code_valid && ((const uint32_t*)lf.values)[row] == lf.code;
-        sat = lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
-    }
-    }
-    return sat && !is_null;
-}
-
 // K0b: one thread per row, one 32-bit mask word per warp.  The lowered filter is staged in shared memory
 // and every leaf of a surviving row is evaluated unconditionally, so the column loads of all leaves are
 // in flight together instead of forming a dependent chain.
@@ -142,13 +115,7 @@ __global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ Me
         if (row < p.n_rows) {
             const uint32_t ch = row / p.chunk_size;
             keep = (p.chunk_keep[ch >> 5] >> (ch & 31)) & 1u;
-            if (keep) {
-                for (uint32_t ci = 0; ci < p.n_clauses; ++ci) {
-                    bool any = false;
-                    for (uint32_t li = clause_off[ci]; li < clause_off[ci + 1]; ++li) any |= row_leaf_sat(leaves[li], row);
-                    keep &= any;
-                }
-            }
+            if (keep) keep = row_passes(leaves, clause_off, p.n_clauses, row);
         }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
         if (lane == 0) p.row_mask[w] = m;

@@ -21,6 +21,7 @@
 //    the buffer, keeps the best k and raises the threshold.  At exit every CTA publishes its best k
 //    keys (sorted) for K3.
 #include "internal.h"
+#include "predicate.cuh"
 
 namespace otters {
 
@@ -142,6 +143,15 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         hdr->written = 0;
     }
     for (uint32_t i = tid; i < p.dim_pad; i += blockDim.x) qs[i] = p.query[i];
+    // stage the lowered filter (leaves + clause offsets) in shared memory
+    const DevLeaf* f_leaves = reinterpret_cast<const DevLeaf*>(smem + p.off_filter);
+    const uint32_t* f_off = reinterpret_cast<const uint32_t*>(smem + p.off_filter + (size_t)p.flt_n_leaves * sizeof(DevLeaf));
+    if (p.flt_leaves) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + p.off_filter);
+        const uint32_t words = p.flt_n_leaves * (uint32_t)(sizeof(DevLeaf) / 4);
+        for (uint32_t i = tid; i < words; i += blockDim.x) dst[i] = reinterpret_cast<const uint32_t*>(p.flt_leaves)[i];
+        for (uint32_t i = tid; i <= p.flt_n_clauses; i += blockDim.x) dst[words + i] = p.flt_clause_off[i];
+    }
     if (lane == 0) {
         for (uint32_t s = 0; s < p.slots; ++s) mbar_init(&bars[s], 1);
         fence_mbar_init();
@@ -182,6 +192,23 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
                 }
                 if (r >= p.n_rows) bits = 0;
                 else if (p.n_rows - r < rpl) bits &= (1u << (p.n_rows - r)) - 1u;
+                if (p.flt_leaves) {
+                    // fused K0b: chunk bit from the prune kernel, then the CNF over the row's metadata
+                    uint32_t ch = r / p.chunk_size;
+                    uint64_t ch_end = (uint64_t)(ch + 1) * p.chunk_size;  // first row of the next chunk
+                    uint32_t keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                    uint32_t out = 0;
+                    for (uint32_t j = 0; j < rpl; ++j) {
+                        const uint32_t row = r + j;
+                        if ((uint64_t)row >= ch_end) {  // crossed into the next chunk
+                            ch = row / p.chunk_size;
+                            ch_end = (uint64_t)(ch + 1) * p.chunk_size;
+                            keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                        }
+                        if (((bits >> j) & 1u) && keep_ch && row_passes(f_leaves, f_off, p.flt_n_clauses, row)) out |= 1u << j;
+                    }
+                    bits = out;
+                }
                 uint32_t c = __popc(bits);
                 uint32_t incl = c;
 #pragma unroll

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
 // ---- sharded path: merge gathered records --------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
-                     ResultHeader* hdr, uint64_t* scratch_keys, uint32_t* scratch_src) {
+                     ResultHeader* hdr, const unsigned long long* rows_scored_src, uint64_t* scratch_keys, uint32_t* scratch_src) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm);
     uint32_t* src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
@@ -227,7 +227,7 @@ merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int
         *out_count = kk;
         if (hdr) {
             hdr->count = kk;
-            hdr->rows_scored = 0ull;
+            hdr->rows_scored = rows_scored_src ? *rows_scored_src : 0ull;
             hdr->stats[0] = hdr->stats[1] = 0ull;
         }
     }
@@ -350,13 +350,14 @@ int launch_select(const SelectParams& p, cudaStream_t s) {
 }
 
 int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
-                         ResultHeader* hdr, uint64_t* scratch_keys, uint32_t* scratch_src, uint32_t scratch_elems, cudaStream_t s) {
+                         ResultHeader* hdr, const unsigned long long* rows_scored_src, uint64_t* scratch_keys, uint32_t* scratch_src,
+                         uint32_t scratch_elems, cudaStream_t s) {
     uint32_t P = 2;
     while (P < n) P <<= 1;
     if (P > kSelectSmemElems && P > scratch_elems) return fail(OTTERS_ERR_UNSUPPORTED, "merge: too many records");
     OTTERS_CUDA(
         cudaFuncSetAttribute(merge_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
-    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, take_max, out, out_count, hdr, scratch_keys, scratch_src);
+    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, take_max, out, out_count, hdr, rows_scored_src, scratch_keys, scratch_src);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

@@ -1,0 +1,65 @@
+"""Run under torchrun with >= 2 GPUs: sharded VecStore and MetaStore search over NCCL vs the oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import otters_b200 as ob  # noqa: E402
+from helpers import assert_same_results  # noqa: E402
+from oracle import oracle as ora  # noqa: E402
+from otters_b200 import _ffi  # noqa: E402
+from otters_b200.meta import FilterPack  # noqa: E402
+from otters_b200.sharded import CudaShard, shard_range  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+ctx = ob.Context(local, stream.cuda_stream)
+
+n, dim, cs, k = 20000, 96, 128, 50
+vectors = ora.synth_fill(0, n, dim, 7)
+queries = ora.synth_fill(0, 2, dim, 8)
+r0, r1 = shard_range(n, cs, world, rank)
+rng = np.random.default_rng(3)
+val = (np.arange(n) // cs % 5 * 10 + rng.integers(0, 10, n)).astype(np.int32)
+nulls = rng.random(n) < 0.02
+col = ob.Column.from_numpy("val", ob.DataType.Int32, val, nulls)
+col_shard = ob.Column.from_numpy("val", ob.DataType.Int32, val[r0:r1], nulls[r0:r1])
+expr = ob.col("val").gte(20) & ob.col("val").neq(33)
+
+for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob.TakeType.Min)):
+    for nq in (1, 2):
+        vq = _ffi.VecQuery()
+        q = np.ascontiguousarray(queries[:nq])
+        vq.queries = q.ctypes.data_as(_ffi.c_f32p)
+        vq.nq, vq.dim, vq.metric, vq.take_type, vq.k = nq, dim, int(metric), int(tt), k
+        # VecStore shard
+        vs = ob.VecStore(dim, ctx)
+        vs.add_vectors(vectors[r0:r1])
+        got = CudaShard(vs, r0, k).search(vq, None, k, tt == ob.TakeType.Max)
+        want = ora.vecstore_query(vectors, q, metric, tt, k)
+        assert_same_results(got, want, f"vec {metric.name} nq={nq} rank {rank}")
+        # MetaStore shard
+        ms = ob.MetaStore.from_columns([col_shard]).with_vectors(vectors[r0:r1]).with_chunk_size(cs).with_context(ctx).build()
+        fp = FilterPack(expr.compile(ms.schema()), ms.column_index())
+        shard = CudaShard(ms, r0, k)
+        gathered, st = shard.enqueue(vq, fp, k, want_stats=True)
+        got = shard.merge(gathered, k, tt == ob.TakeType.Max)
+        ost = ora.MetaStore(vectors, [col], cs)
+        ofp = ora.FilterPack.from_compiled(expr.compile(ms.schema()), ms.column_index())
+        oi, os_, oq, ostats = ost.query(q, metric, tt, k, None, ofp)
+        assert_same_results(got, (oi, os_, oq), f"meta {metric.name} nq={nq} rank {rank}")
+        tot = torch.tensor([st.evaluated_chunks, st.vectors_compared, st.total_chunks], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        assert tot.tolist() == [ostats["evaluated_chunks"], ostats["vectors_compared"], ostats["total_chunks"]], (tot.tolist(), ostats)
+dist.barrier()
+if rank == 0:
+    print("DIST_CHECK_OK")
+dist.destroy_process_group()

@@ -333,3 +333,35 @@ def test_meta_empty_store(ctx):
     assert store.query([1, 0, 0, 0], ob.Metric.Cosine).take(3).collect().is_empty()
     st = store.last_query_stats()
     assert st.total_chunks == 0 and st.vectors_compared == 0
+
+
+def test_fused_and_unfused_predicate_paths_agree(meta_pair):
+    """The scan kernel normally evaluates the row predicate itself (fused K0b); the stand-alone row-mask kernel
+    must give the same answer."""
+    store, ost, _, _ = meta_pair
+    q = ora.synth_fill(0, 1, 64, 66)
+    try:
+        for fi in range(len(FILTERS)):
+            expr = FILTERS[fi]()
+            got = []
+            for disable in (0, 1):
+                store.ctx.set_tuning(disable_fused_predicate=disable)
+                res = store.query(q[0], ob.Metric.Cosine).meta_filter(expr).take(40).collect()
+                got.append((res.indices, res.scores))
+            assert_same_results(got[0], got[1], f"filter {fi}")
+    finally:
+        store.ctx.set_tuning()
+
+
+def test_many_leaf_filter_falls_back_to_row_mask_kernel(meta_pair):
+    """A CNF too large for the scan kernel's shared-memory staging uses the stand-alone row-mask kernel."""
+    store, ost, _, _ = meta_pair
+    q = ora.synth_fill(0, 1, 64, 67)
+    expr = ob.col("i32").gte(0)
+    for v in range(140):
+        expr = expr & (ob.col("i32").neq(1000 + v) | ob.col("price").gt(1e9))
+    fp = ora.FilterPack.from_compiled(expr.compile(store.schema()), store.column_index())
+    res = store.query(q[0], ob.Metric.DotProduct).meta_filter(expr).take(30).collect()
+    oi, os_, _, ostats = ost.query(q, ob.Metric.DotProduct, ob.TakeType.Max, 30, None, fp)
+    assert_same_results((res.indices, res.scores), (oi, os_))
+    assert store.last_query_stats().evaluated_chunks == ostats["evaluated_chunks"]
