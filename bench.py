@@ -48,11 +48,10 @@ DATA_SEED = 0x07735
 QUERY_SEED = 0xBEEF
 
 
-def meta_columns(ob, r0, r1, chunk):
-    """Synthetic metadata for absolute rows [r0, r1): clustered by chunk like examples/demo.rs:29-77.
+def meta_columns(ob, rows, chunk):
+    """Synthetic metadata for the given absolute row ids: clustered by chunk like examples/demo.rs:29-77.
     Pure functions of the absolute row id, so every shard (and the CPU sample) sees the same table."""
-    n = r1 - r0
-    row = np.arange(r0, r1, dtype=np.int64)
+    row = np.asarray(rows, dtype=np.int64)
     c = row // max(chunk, 1)
 
     def u01(salt):  # counter-based uniform in [0,1)
@@ -184,7 +183,7 @@ def cpu_arm(wl, name, budget_s, steps=None, warmup=1):
     queries = ora.synth_fill(0, 8, dim, QUERY_SEED)
     threads = ora.num_threads()
     if wl["meta"]:
-        cols = meta_columns(ob, r0, r0 + sample_rows, chunk)
+        cols = meta_columns(ob, np.arange(r0, r0 + sample_rows), chunk)
         store = ora.MetaStore(vectors, cols, chunk)
         expr, _ = meta_expr(ob, rows)
         schema = {c.name(): c.dtype() for c in cols}
@@ -251,7 +250,7 @@ def run_ours(args, wl):
 
     import otters_b200 as ob
     from otters_b200 import _ffi
-    from otters_b200.sharded import CudaShard, shard_range
+    from otters_b200.sharded import CudaShard, cyclic_global_rows, cyclic_local_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -271,13 +270,16 @@ def run_ours(args, wl):
     rows, dim, chunk, k = wl["rows"], wl["dim"], wl["chunk"], wl["k"]
     metric = getattr(ob.Metric, wl["metric"])
     tt = ob.TakeType.Min if metric == ob.Metric.Euclidean else ob.TakeType.Max
-    r0, r1 = shard_range(rows, chunk if chunk else 1024, world, rank)
+    # block-cyclic row sharding: blocks of `block` rows are dealt round-robin to the ranks, so range filters
+    # (ts >= cut) prune every shard equally
+    block = chunk if chunk else 1024
+    n_local = cyclic_local_rows(rows, block, world, rank)
     t_build = time.perf_counter()
     fp, expr_desc, vf = None, None, None
     if wl["meta"]:
-        cols = meta_columns(ob, r0, r1, chunk)
-        store = (ob.MetaStore.from_columns(cols).with_synthetic_vectors(r1 - r0, dim, DATA_SEED, r0).with_chunk_size(chunk)
-                 .with_context(ctx).build())
+        cols = meta_columns(ob, cyclic_global_rows(rows, block, world, rank), chunk)
+        store = (ob.MetaStore.from_columns(cols).with_synthetic_vectors(n_local, dim, DATA_SEED, 0, (world, rank, block))
+                 .with_chunk_size(chunk).with_context(ctx).build())
         expr, cut = meta_expr(ob, rows)
         expr_desc = f"price.gt(50.0) & item.eq('item_0000') & ts.gte('{cut}')"
         from otters_b200.meta import FilterPack
@@ -287,7 +289,7 @@ def run_ours(args, wl):
             vf = (0.0, ob.Cmp.Gt)
     else:
         store = ob.VecStore(dim, ctx)
-        store.add_synthetic(r0, r1 - r0, DATA_SEED)
+        store.add_synthetic_sharded(world, rank, block, n_local, DATA_SEED)
     build_s = time.perf_counter() - t_build
 
     nqv = 16
@@ -302,7 +304,7 @@ def run_ours(args, wl):
             vq.has_filter, vq.thr, vq.cmp = 1, vf[0], int(vf[1])
         return vq
 
-    shard = CudaShard(store, r0, k)
+    shard = CudaShard(store, 0, k, block_rows=block)
     take_max = tt == ob.TakeType.Max
 
     def barrier():
@@ -311,10 +313,24 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     # ---- e2e: public API semantics, host query in -> host top-k out, one sync per query --------------------
+    phase_ev = []
+
     def e2e_step(i):
         vq = make_vq(i)
+        if args.phase_timing:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            evs[0].record()
+            t_h0 = time.perf_counter()
         gathered, _ = shard.enqueue(vq, fp, k)
-        return shard.merge(gathered, k, take_max, fetch=True)
+        if args.phase_timing:
+            evs[1].record()
+            t_h1 = time.perf_counter()
+        out = shard.merge(gathered, k, take_max, fetch=True)
+        if args.phase_timing:
+            evs[2].record()
+            evs[2].synchronize()
+            phase_ev.append((evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), (t_h1 - t_h0) * 1e3, (time.perf_counter() - t_h1) * 1e3))
+        return out
 
     def e2e_step_single(i):
         """N == 1: the plain drop-in call (otters_metastore_query / otters_vecstore_query)."""
@@ -356,6 +372,10 @@ def run_ours(args, wl):
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if args.phase_timing and phase_ev:
+        pe = np.array(phase_ev[args.warmup:])
+        print(f"[rank {rank}] phases ms: local+gather(dev)={pe[:,0].mean():.3f} merge+fetch(dev)={pe[:,1].mean():.3f} "
+              f"host enqueue={pe[:,2].mean():.3f} host merge={pe[:,3].mean():.3f} scan={np.mean(scan_ms) if scan_ms else 0:.3f}", file=sys.stderr)
 
     # ---- value: device pipeline only (no per-step host sync, results stay in HBM) -------------------------
     def dev_step(i):
@@ -401,7 +421,7 @@ def run_ours(args, wl):
             "config": {
                 "workload": f"{args.workload}: {wl['desc']}", "rows": rows, "dim": dim, "k": k, "chunk_size": chunk,
                 "filter": expr_desc, "rows_scored_per_query": rows_scored_total,
-                "parallelism": f"row-sharded x{world}" + (" + NCCL all-gather of k records + device merge" if world > 1 else ""),
+                "parallelism": f"rows block-cyclic ({block}-row blocks) over {world} GPU(s)" + (" + NCCL all-gather of k records + device merge" if world > 1 else ""),
                 "l2": "no flush needed: every query streams >= GBs of distinct rows, far larger than the 126 MB L2",
                 "store_build_s": build_s,
             },
@@ -432,6 +452,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the row count (debugging only; invalid as a bench number)")
     ap.add_argument("--tuning", default="", help="warps,slots,kc,ctas_per_sm,unit_rows (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--phase-timing", action="store_true", help="print per-phase device/host times of the sharded step (debug)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

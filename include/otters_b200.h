@@ -179,6 +179,7 @@ typedef struct {
     const float *vectors;           /* host or device pointer, n_rows * dim floats row-major */
     uint64_t synthetic_seed;        /* OTTERS_VECTORS_SYNTHETIC */
     uint64_t synthetic_first_row;
+    const void *synthetic_map;      /* optional otters_shard_map*: global row ids of the generated rows */
     const otters_column *columns;
     uint32_t n_columns;
 } otters_build_params;
@@ -256,17 +257,32 @@ OTTERS_API int otters_metastore_inv_norms(const otters_metastore *ms, uint64_t f
  * records (NCCL), and every rank runs the same final merge.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
-    uint64_t row;   /* global row id (row_base + local row); UINT64_MAX = empty slot */
+    uint64_t row;   /* global row id (see otters_shard_map); UINT64_MAX = empty slot */
     float score;
     uint32_t qid;
 } otters_topk_record;
 
+/* How local rows of a shard map to global row ids.  world <= 1 or block_rows == 0: contiguous,
+ * global = row_base + local.  Otherwise block-cyclic: the store's blocks of block_rows rows are dealt
+ * round-robin to the ranks (block b of rank r is global block b * world + r), which keeps every shard
+ * balanced under range filters:  global = row_base + ((local / block_rows) * world + rank) * block_rows
+ * + local % block_rows. */
+typedef struct {
+    uint64_t row_base;
+    uint32_t world;
+    uint32_t rank;
+    uint64_t block_rows;
+} otters_shard_map;
+
 /* Local query whose result stays on the device: writes exactly k records to d_records (device
  * memory, padded with empty slots).  `filter`/`ms` semantics as above; pass vs for a VecStore or ms
- * for a MetaStore (exactly one non-NULL).  Stats counters are local to the shard. */
+ * for a MetaStore (exactly one non-NULL).  `map` (nullable = identity) turns local rows into global
+ * row ids.  Stats counters are local to the shard; with stats == NULL the call does not synchronise. */
 OTTERS_API int otters_query_local_device(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q,
-                              const otters_filter *filter, uint64_t row_base, void *d_records,
+                              const otters_filter *filter, const otters_shard_map *map, void *d_records,
                               otters_query_stats *stats /* nullable */);
+/* Appends n_local rows of the synthetic generator whose global row ids follow `map` (bench/test utility). */
+OTTERS_API int otters_vecstore_add_synthetic_sharded(otters_vecstore *vs, const otters_shard_map *map, uint64_t n_local, uint64_t seed);
 /* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k.
  * With out_idx = out_score = out_qid = NULL and cap = 0 the call only enqueues the merge (no copy, no sync). */
 OTTERS_API int otters_topk_merge_device(otters_ctx *ctx, const void *d_records, uint64_t n_records, uint64_t k, int32_t take_type,

@@ -89,6 +89,7 @@ class BuildParams(C.Structure):
         ("vectors", C.c_void_p),
         ("synthetic_seed", C.c_uint64),
         ("synthetic_first_row", C.c_uint64),
+        ("synthetic_map", C.c_void_p),
         ("columns", C.POINTER(Column)),
         ("n_columns", C.c_uint32),
     ]
@@ -136,6 +137,10 @@ class Filter(C.Structure):
         ("clause_offsets", c_u32p),
         ("leaves", C.POINTER(Leaf)),
     ]
+
+
+class ShardMap(C.Structure):
+    _fields_ = [("row_base", C.c_uint64), ("world", C.c_uint32), ("rank", C.c_uint32), ("block_rows", C.c_uint64)]
 
 
 class TopkRecord(C.Structure):
@@ -205,7 +210,10 @@ otters_metastore_zonemap_f64 = _sig(
 )
 otters_metastore_inv_norms = _sig("otters_metastore_inv_norms", C.c_int, _p, C.c_uint64, C.c_uint64, c_f32p)
 otters_query_local_device = _sig(
-    "otters_query_local_device", C.c_int, _p, _p, C.POINTER(VecQuery), C.POINTER(Filter), C.c_uint64, _p, C.POINTER(QueryStats)
+    "otters_query_local_device", C.c_int, _p, _p, C.POINTER(VecQuery), C.POINTER(Filter), C.POINTER(ShardMap), _p, C.POINTER(QueryStats)
+)
+otters_vecstore_add_synthetic_sharded = _sig(
+    "otters_vecstore_add_synthetic_sharded", C.c_int, _p, C.POINTER(ShardMap), C.c_uint64, C.c_uint64
 )
 otters_topk_merge_device = _sig(
     "otters_topk_merge_device", C.c_int, _p, _p, C.c_uint64, C.c_uint64, C.c_int32, c_u64p, c_f32p, c_u32p, C.c_uint64, c_u64p

@@ -239,12 +239,12 @@ struct VecStorage {
         n += cnt;
         return OTTERS_OK;
     }
-    int add_synth(uint64_t first_row, uint64_t cnt, uint64_t seed) {
+    int add_synth(ShardMap gen_map, uint64_t cnt, uint64_t seed) {
         if (cnt == 0) return OTTERS_OK;
         if (n + cnt >= 0xFFFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "a store shard is limited to 2^32-16 rows");
         int rc = reserve(n + cnt);
         if (rc) return rc;
-        rc = launch_synth_fill(d_rows, pitch, dim, n, first_row, cnt, seed, ctx->stream);
+        rc = launch_synth_fill(d_rows, pitch, dim, n, gen_map, cnt, seed, ctx->stream);
         if (rc) return rc;
         rc = launch_inv_norms(d_rows, pitch, dim, n, cnt, d_inv, ctx->stream);
         if (rc) return rc;
@@ -372,7 +372,7 @@ static float host_inv_norm(const float* v, uint32_t dim) {
 }
 
 static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const uint32_t* d_row_mask,
-                       uint32_t row_mask_words, otters_topk_record* d_records_out, uint64_t row_base,
+                       uint32_t row_mask_words, otters_topk_record* d_records_out, ShardMap map,
                        const unsigned long long* stats_src, const FusedFilter* ff, QueryRun* run) {
     const uint32_t dim_pad = st->pitch;
     const uint64_t n_rows = st->n;
@@ -483,7 +483,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             se.scratch_src = c->d_scratch_src;
             se.scratch_elems = c->scratch_elems;
             se.records = (qi + 1 == q->nq) ? d_records_out : nullptr;
-            se.row_base = row_base;
+            se.map = map;
             se.take_max = sp.take_max;
             se.hdr = list_hdr(c, cur ^ 1);
             se.rows_scored_src = c->d_rows_scored;
@@ -536,7 +536,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             c->last.kernel_launches += 4;
         }
         if (d_records_out) {
-            rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, row_base, sp.take_max, d_records_out, s);
+            rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, sp.take_max, d_records_out, s);
             if (rc) return rc;
         }
         cudaEventRecord(c->ev[5], s);
@@ -747,7 +747,26 @@ extern "C" int otters_vecstore_add_device(otters_vecstore* vs, const float* d_ro
 extern "C" int otters_vecstore_add_synthetic(otters_vecstore* vs, uint64_t first_row, uint64_t n, uint64_t seed) {
     if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
     DeviceGuard g(vs->st.ctx->device);
-    return vs->st.add_synth(first_row, n, seed);
+    ShardMap m;
+    m.row_base = first_row;
+    return vs->st.add_synth(m, n, seed);
+}
+
+static ShardMap to_map(const otters_shard_map* in) {
+    ShardMap m;
+    if (in) {
+        m.row_base = in->row_base;
+        m.world = in->world;
+        m.rank = in->rank;
+        m.block = in->block_rows;
+    }
+    return m;
+}
+
+extern "C" int otters_vecstore_add_synthetic_sharded(otters_vecstore* vs, const otters_shard_map* map, uint64_t n_local, uint64_t seed) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    DeviceGuard g(vs->st.ctx->device);
+    return vs->st.add_synth(to_map(map), n_local, seed);
 }
 
 extern "C" uint64_t otters_vecstore_len(const otters_vecstore* vs) { return vs ? vs->st.n : 0; }
@@ -807,7 +826,7 @@ extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
     QueryRun run;
-    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, 0, nullptr, nullptr, &run);
+    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, ShardMap{}, nullptr, nullptr, &run);
     if (rc) return rc;
     rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
     if (rc) return rc;
@@ -1153,7 +1172,19 @@ extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* 
     int rc = OTTERS_OK;
     if (p->vectors_kind == OTTERS_VECTORS_HOST) rc = ms->st.add(p->vectors, p->n_rows, cudaMemcpyHostToDevice);
     else if (p->vectors_kind == OTTERS_VECTORS_DEVICE) rc = ms->st.add(p->vectors, p->n_rows, cudaMemcpyDeviceToDevice);
-    else if (p->vectors_kind == OTTERS_VECTORS_SYNTHETIC) rc = ms->st.add_synth(p->synthetic_first_row, p->n_rows, p->synthetic_seed);
+    else if (p->vectors_kind == OTTERS_VECTORS_SYNTHETIC) {
+        ShardMap m;
+        if (p->synthetic_map) {
+            const otters_shard_map* in = (const otters_shard_map*)p->synthetic_map;
+            m.row_base = in->row_base;
+            m.world = in->world;
+            m.rank = in->rank;
+            m.block = in->block_rows;
+        } else {
+            m.row_base = p->synthetic_first_row;
+        }
+        rc = ms->st.add_synth(m, p->n_rows, p->synthetic_seed);
+    }
     else rc = fail(OTTERS_ERR_INVALID, "invalid vectors_kind");
     if (rc) return cleanup(rc);
     const double ingest_s = now_s() - t_ing;
@@ -1348,7 +1379,7 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
 }
 
 static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
-                           otters_topk_record* d_records, uint64_t row_base, uint64_t* out_idx, float* out_score,
+                           otters_topk_record* d_records, ShardMap map, uint64_t* out_idx, float* out_score,
                            uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
     const double t_total = now_s();
     otters_ctx* c = ms->ctx;
@@ -1381,7 +1412,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
         QueryRun run;
         const bool fuse = filter && !c->tuning.disable_fused_predicate && ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes;
         rc = run_queries(c, &ms->st, q, (filter && !fuse) ? ms->d_row_mask : nullptr,
-                         (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, row_base, c->d_stats,
+                         (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, map, c->d_stats,
                          fuse ? &ms->cur_filter : nullptr, &run);
         if (rc) return rc;
         if (d_records) {
@@ -1390,7 +1421,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
                 if (rc) return rc;
             }
         } else {
-            rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, row_base, out_idx, out_score, out_qid, cap, &n_out, hstats);
+            rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, &n_out, hstats);
             if (rc) return rc;
             finish_work_stats(c);
         }
@@ -1399,7 +1430,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
             // no scan: the record buffer must still hold k empty slots
             const uint64_t k_eff = std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq);
             if (k_eff) {
-                rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, row_base, 1, d_records, s);
+                rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, 1, d_records, s);
                 if (rc) return rc;
             }
         }
@@ -1455,7 +1486,7 @@ extern "C" int otters_metastore_query(otters_metastore* ms, const otters_vec_que
                                       otters_query_stats* stats) {
     if (!ms || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
     DeviceGuard g(ms->ctx->device);
-    return meta_query_impl(ms, q, filter, nullptr, 0, out_idx, out_score, out_qid, cap, out_len, stats);
+    return meta_query_impl(ms, q, filter, nullptr, ShardMap{}, out_idx, out_score, out_qid, cap, out_len, stats);
 }
 
 extern "C" int otters_metastore_last_stats(const otters_metastore* ms, otters_query_stats* out) {
@@ -1532,12 +1563,19 @@ extern "C" int otters_metastore_inv_norms(const otters_metastore* ms, uint64_t f
 // row-sharded multi-GPU helpers
 // =================================================================================================
 extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q,
-                                         const otters_filter* filter, uint64_t row_base, void* d_records,
+                                         const otters_filter* filter, const otters_shard_map* map_in, void* d_records,
                                          otters_query_stats* stats) {
+    ShardMap map;
+    if (map_in) {
+        map.row_base = map_in->row_base;
+        map.world = map_in->world;
+        map.rank = map_in->rank;
+        map.block = map_in->block_rows;
+    }
     if ((!vs && !ms) || (vs && ms) || !d_records) return fail(OTTERS_ERR_INVALID, "pass exactly one store and a record buffer");
     if (ms) {
         DeviceGuard g(ms->ctx->device);
-        return meta_query_impl(ms, q, filter, (otters_topk_record*)d_records, row_base, nullptr, nullptr, nullptr, 0, nullptr,
+        return meta_query_impl(ms, q, filter, (otters_topk_record*)d_records, map, nullptr, nullptr, nullptr, 0, nullptr,
                                stats);
     }
     if (filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
@@ -1555,7 +1593,7 @@ extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* 
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
     QueryRun run;
-    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, row_base, nullptr, nullptr, &run);
+    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, map, nullptr, nullptr, &run);
 }
 
 extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, uint64_t n_records, uint64_t k, int32_t take_type,

@@ -22,6 +22,18 @@ int fail(int code, const std::string& msg);
             return ::otters::fail(OTTERS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
     } while (0)
 
+// local row -> global row id (otters_shard_map)
+struct ShardMap {
+    uint64_t row_base = 0;
+    uint32_t world = 1;
+    uint32_t rank = 0;
+    uint64_t block = 0;
+    __host__ __device__ __forceinline__ uint64_t global_row(uint64_t local) const {
+        if (world <= 1 || block == 0) return row_base + local;
+        return row_base + ((local / block) * world + rank) * block + local % block;
+    }
+};
+
 constexpr uint32_t kTileRows = 16;     // rows per staged tile (2 threads per row, one warp per tile)
 constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work unit
 constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
@@ -115,7 +127,7 @@ struct SelectParams {
     uint32_t scratch_elems;     // power of two
     // optional fixed-size record output (sharded search)
     otters_topk_record* records;
-    uint64_t row_base;
+    ShardMap map;
     int32_t take_max;
     // header of the output list + the counters copied into it
     ResultHeader* hdr;
@@ -135,13 +147,13 @@ int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, 
 int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
                        uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr, const unsigned long long* rows_scored_src,
                        const unsigned long long* stats_src, cudaStream_t s);
-int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
+int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, ShardMap map, int take_max,
                             otters_topk_record* recs, cudaStream_t s);
 
 // ---- store kernels ----------------------------------------------------------------------------
 int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t first, uint64_t n, float* out,
                      cudaStream_t s);
-int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, uint64_t gen_first, uint64_t n,
+int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, ShardMap gen_map, uint64_t n,
                       uint64_t seed, cudaStream_t s);
 
 // ---- metadata kernels -------------------------------------------------------------------------

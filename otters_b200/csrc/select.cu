@@ -18,8 +18,10 @@ __device__ __forceinline__ bool before(uint64_t ka, uint32_t sa, uint64_t kb, ui
 }
 
 // block-wide bitonic sort of n (power of two) elements, best-first.  keys/src may live in shared or
-// global memory.
-__device__ void block_bitonic(uint64_t* keys, uint32_t* src, uint32_t n) {
+// global memory (force-inlined so that the shared-memory instantiation compiles to LDS/STS).
+// WITH_SRC = false sorts the keys alone (unique keys: no tie-break and no provenance needed).
+template <bool WITH_SRC>
+__device__ __forceinline__ void block_bitonic(uint64_t* keys, uint32_t* src, uint32_t n) {
     for (uint32_t size = 2; size <= n; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
@@ -27,13 +29,20 @@ __device__ void block_bitonic(uint64_t* keys, uint32_t* src, uint32_t n) {
                 uint32_t hi = lo + stride;
                 bool fwd = (lo & size) == 0;
                 uint64_t ka = keys[lo], kb = keys[hi];
-                uint32_t sa = src[lo], sb = src[hi];
-                bool swap = fwd ? before(kb, sb, ka, sa) : before(ka, sa, kb, sb);
-                if (swap) {
-                    keys[lo] = kb;
-                    keys[hi] = ka;
-                    src[lo] = sb;
-                    src[hi] = sa;
+                if (WITH_SRC) {
+                    uint32_t sa = src[lo], sb = src[hi];
+                    bool swap = fwd ? before(kb, sb, ka, sa) : before(ka, sa, kb, sb);
+                    if (swap) {
+                        keys[lo] = kb;
+                        keys[hi] = ka;
+                        src[lo] = sb;
+                        src[hi] = sa;
+                    }
+                } else {
+                    if (fwd ? (kb > ka) : (ka > kb)) {
+                        keys[lo] = kb;
+                        keys[hi] = ka;
+                    }
                 }
             }
             __syncthreads();
@@ -52,14 +61,17 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
 // tag = list << 11 | position  (position < 2048 because k <= 1024 in the fused path)
 constexpr uint32_t kPosBits = 11;
 
+// WITH_PREV = false is the single-query hot path: no running list, all keys distinct, keys sorted alone.
+template <bool WITH_PREV>
 __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__ SelectParams p) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(sm);
     uint32_t* s_src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
     __shared__ uint32_t s_total, s_nel, s_retry, s_maxcount;
 
-    const uint32_t n_lists = p.n_lists + 1;  // + running list
-    const uint32_t prev_n = (p.prev && p.prev_count) ? *p.prev_count : 0;
+    const uint32_t first = WITH_PREV ? 0u : 1u;  // list 0 = running list
+    const uint32_t n_lists = p.n_lists + 1;
+    const uint32_t prev_n = (WITH_PREV && p.prev && p.prev_count) ? *p.prev_count : 0;
     auto list_count = [&](uint32_t l) -> uint32_t { return l == 0 ? prev_n : p.cta_counts[l - 1]; };
     auto list_key = [&](uint32_t l, uint32_t i) -> uint64_t {
         return l == 0 ? p.prev[i].key : p.cta_keys[(size_t)(l - 1) * p.list_stride + i];
@@ -72,7 +84,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
     __syncthreads();
     {
         uint32_t loc = 0, mx = 0;
-        for (uint32_t l = threadIdx.x; l < n_lists; l += blockDim.x) {
+        for (uint32_t l = first + threadIdx.x; l < n_lists; l += blockDim.x) {
             uint32_t c = list_count(l);
             loc += c;
             mx = c > mx ? c : mx;
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
 
     // Only a short prefix of every (sorted) list can reach the global top-k.  Start with a small
     // prefix length L, sort the union of prefixes, and grow L until no list was cut short.
-    uint32_t L = (4 * p.k) / n_lists + 8;
+    uint32_t L = (2 * p.k + n_lists - 1) / n_lists + 3;
     if (L > maxcount) L = maxcount;
     uint64_t* keys = s_keys;
     uint32_t* src = s_src;
@@ -103,14 +115,14 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
         bool use_global = worst > kSelectSmemElems;
         keys = use_global ? p.scratch_keys : s_keys;
         src = use_global ? p.scratch_src : s_src;
-        for (uint32_t l = threadIdx.x; l < n_lists; l += blockDim.x) {
+        for (uint32_t l = first + threadIdx.x; l < n_lists; l += blockDim.x) {
             uint32_t c = list_count(l);
             uint32_t take = c < L ? c : L;
             if (take) {
                 uint32_t base = atomicAdd(&s_nel, take);
                 for (uint32_t i = 0; i < take; ++i) {
                     keys[base + i] = list_key(l, i);
-                    src[base + i] = (l << kPosBits) | i;
+                    if (WITH_PREV) src[base + i] = (l << kPosBits) | i;
                 }
             }
         }
@@ -119,23 +131,24 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
         P = next_pow2(nel < 2 ? 2 : nel);
         for (uint32_t i = nel + threadIdx.x; i < P; i += blockDim.x) {
             keys[i] = 0ull;
-            src[i] = 0xFFFFFFFFu;
+            if (WITH_PREV) src[i] = 0xFFFFFFFFu;
         }
         __syncthreads();
-        block_bitonic(keys, src, P);
+        if (use_global) block_bitonic<WITH_PREV>(p.scratch_keys, p.scratch_src, P);
+        else block_bitonic<WITH_PREV>(s_keys, s_src, P);
         // was any list cut short in a way that matters?
         if (L < maxcount) {
             if (nel < kk) {
                 if (threadIdx.x == 0) s_retry = 1;
             } else if (kk > 0) {
                 const uint64_t tk = keys[kk - 1];
-                const uint32_t ts = src[kk - 1];
-                for (uint32_t l = threadIdx.x; l < n_lists; l += blockDim.x) {
+                const uint32_t ts = WITH_PREV ? src[kk - 1] : 0u;
+                for (uint32_t l = first + threadIdx.x; l < n_lists; l += blockDim.x) {
                     uint32_t c = list_count(l);
                     if (c > L) {
                         uint64_t nk = list_key(l, L);
                         uint32_t ns = (l << kPosBits) | L;
-                        if (before(nk, ns, tk, ts)) s_retry = 1;
+                        if (WITH_PREV ? before(nk, ns, tk, ts) : (nk > tk)) s_retry = 1;
                     }
                 }
             }
@@ -148,16 +161,19 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
 
     // emit the best kk, ordered
     for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
-        uint32_t s = src[i];
-        uint32_t l = s >> kPosBits, pos = s & ((1u << kPosBits) - 1u);
         Cand c;
         c.key = keys[i];
-        c.qid = l == 0 ? p.prev[pos].qid : p.qid;
+        c.qid = p.qid;
+        if (WITH_PREV) {
+            uint32_t s = src[i];
+            uint32_t l = s >> kPosBits, pos = s & ((1u << kPosBits) - 1u);
+            if (l == 0) c.qid = p.prev[pos].qid;
+        }
         c.pad = 0;
         p.out[i] = c;
         if (p.records) {
             otters_topk_record r;
-            r.row = p.row_base + key_row(c.key);
+            r.row = p.map.global_row(key_row(c.key));
             r.score = key_score(c.key, p.take_max != 0);
             r.qid = c.qid;
             p.records[i] = r;
@@ -214,7 +230,8 @@ merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int
     }
     if (loc) atomicAdd(&s_valid, loc);
     __syncthreads();
-    block_bitonic(keys, src, P);
+    if (P > kSelectSmemElems) block_bitonic<true>(scratch_keys, scratch_src, P);
+    else block_bitonic<true>(reinterpret_cast<uint64_t*>(sm), reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8), P);
     uint32_t kk = s_valid < k ? s_valid : k;
     for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
         Cand c;
@@ -314,13 +331,13 @@ __global__ void take_sorted_kernel(const Cand* buf, const uint32_t* emit_count, 
     }
 }
 
-__global__ void cands_to_records_kernel(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
+__global__ void cands_to_records_kernel(const Cand* cands, const uint32_t* count, uint32_t k, ShardMap map, int take_max,
                                         otters_topk_record* recs) {
     uint32_t n = *count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
         otters_topk_record r;
         if (i < n) {
-            r.row = row_base + key_row(cands[i].key);
+            r.row = map.global_row(key_row(cands[i].key));
             r.score = key_score(cands[i].key, take_max != 0);
             r.qid = cands[i].qid;
         } else {
@@ -341,10 +358,18 @@ int launch_select(const SelectParams& p, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_dev != dev) {
-        OTTERS_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
+        OTTERS_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
+        OTTERS_CUDA(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
         configured_dev = dev;
     }
-    select_kernel<<<1, 1024, kSelectSmemBytes, s>>>(p);
+    // block size ~ half the first working set (one compare-exchange per thread and step)
+    const uint32_t n_lists = p.n_lists + 1;
+    const uint32_t L = (2 * p.k + n_lists - 1) / n_lists + 3;
+    uint32_t P = 2;
+    while (P < n_lists * L) P <<= 1;
+    uint32_t block = P / 2 < 128 ? 128 : (P / 2 > 1024 ? 1024 : P / 2);
+    if (p.prev) select_kernel<true><<<1, block, kSelectSmemBytes, s>>>(p);
+    else select_kernel<false><<<1, block, kSelectSmemBytes, s>>>(p);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
@@ -392,9 +417,9 @@ int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32
     return OTTERS_OK;
 }
 
-int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, uint64_t row_base, int take_max,
+int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, ShardMap map, int take_max,
                             otters_topk_record* recs, cudaStream_t s) {
-    cands_to_records_kernel<<<(k + 255) / 256 ? (k + 255) / 256 : 1, 256, 0, s>>>(cands, count, k, row_base, take_max, recs);
+    cands_to_records_kernel<<<(k + 255) / 256 ? (k + 255) / 256 : 1, 256, 0, s>>>(cands, count, k, map, take_max, recs);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 // x = (splitmix64(seed ^ (row*dim + col)) >> 40) * 2^-23 - 1   in [-1, 1)   
 __global__ void synth_fill_kernel(float* __restrict__ rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first,
-                                  uint64_t gen_first, uint64_t n, uint64_t seed) {
+                                  ShardMap gen_map, uint64_t n, uint64_t seed) {
     const uint64_t total = n * pitch_g;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -45,7 +45,7 @@ __global__ void synth_fill_kernel(float* __restrict__ rows, uint64_t pitch_g, ui
         const uint32_t c = (uint32_t)(i - r * pitch_g);
         float x = 0.f;
         if (c < dim) {
-            const uint64_t u = splitmix64(seed ^ ((gen_first + r) * (uint64_t)dim + c));
+            const uint64_t u = splitmix64(seed ^ (gen_map.global_row(r) * (uint64_t)dim + c));
             x = (float)(u >> 40) * (1.0f / 8388608.0f) - 1.0f;
         }
         rows[(dst_first + r) * pitch_g + c] = x;
@@ -62,10 +62,10 @@ int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t
     return OTTERS_OK;
 }
 
-int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, uint64_t gen_first, uint64_t n,
+int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, ShardMap gen_map, uint64_t n,
                       uint64_t seed, cudaStream_t s) {
     if (n == 0) return OTTERS_OK;
-    synth_fill_kernel<<<148 * 16, 256, 0, s>>>(rows, pitch_g, dim, dst_first, gen_first, n, seed);
+    synth_fill_kernel<<<148 * 16, 256, 0, s>>>(rows, pitch_g, dim, dst_first, gen_map, n, seed);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

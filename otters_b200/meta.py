@@ -118,9 +118,10 @@ class MetaStoreBuilder:
         self._vectors = vectors
         return self
 
-    def with_synthetic_vectors(self, n_rows: int, dim: int, seed: int, first_row: int = 0) -> "MetaStoreBuilder":
-        """Vectors from the device-side synthetic generator (bench/test utility)."""
-        self._synthetic = (int(n_rows), int(dim), int(seed), int(first_row))
+    def with_synthetic_vectors(self, n_rows: int, dim: int, seed: int, first_row: int = 0, shard=None) -> "MetaStoreBuilder":
+        """Vectors from the device-side synthetic generator (bench/test utility).  `shard` = (world, rank,
+        block_rows) generates the rows a rank holds under block-cyclic sharding."""
+        self._synthetic = (int(n_rows), int(dim), int(seed), int(first_row), shard)
         return self
 
     def with_context(self, ctx: Context) -> "MetaStoreBuilder":
@@ -216,6 +217,11 @@ class MetaStoreBuilder:
         if self._synthetic is not None:
             bp.vectors_kind = _ffi.VECTORS_SYNTHETIC
             bp.synthetic_seed, bp.synthetic_first_row = self._synthetic[2], self._synthetic[3]
+            if self._synthetic[4] is not None:
+                w, r, b = self._synthetic[4]
+                smap = _ffi.ShardMap(self._synthetic[3], w, r, b)
+                keep.append(smap)
+                bp.synthetic_map = C.cast(C.pointer(smap), C.c_void_p)
         else:
             bp.vectors_kind = _ffi.VECTORS_HOST
             bp.vectors = vec_arr.ctypes.data if vec_arr.size else None

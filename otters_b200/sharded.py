@@ -1,6 +1,7 @@
 """Row-sharded multi-GPU search (one process per GPU, torch.distributed for the plumbing).
 
-Rows are split into contiguous, chunk-aligned ranges; every rank holds its shard in HBM,
+Rows are split either into contiguous chunk-aligned ranges or block-cyclically (blocks of chunk_size rows
+dealt round-robin, which keeps shards balanced under range filters); every rank holds its shard in HBM,
 answers the query locally (``otters_query_local_device`` leaves k fixed-size records on the device), the
 ranks all-gather the records (NCCL over NVLink; k*16 bytes per rank) and every rank runs the same final
 merge kernel (``otters_topk_merge_device``).  Global row id = shard base + local row.
@@ -24,6 +25,25 @@ def shard_range(n_rows: int, chunk_size: int, world: int, rank: int) -> Tuple[in
     r0 = min(rank * per * chunk_size, n_rows)
     r1 = min((rank + 1) * per * chunk_size, n_rows)
     return r0, r1
+
+
+def cyclic_local_rows(n_rows: int, block_rows: int, world: int, rank: int) -> int:
+    """Rows held by `rank` when blocks of `block_rows` rows are dealt round-robin (block b -> rank b % world)."""
+    block_rows = max(int(block_rows), 1)
+    n_blocks = (n_rows + block_rows - 1) // block_rows
+    mine = (n_blocks - rank + world - 1) // world if n_blocks > rank else 0
+    if mine == 0:
+        return 0
+    last_block = (mine - 1) * world + rank
+    tail = n_rows - last_block * block_rows  # rows in my last block (it may be the short global tail)
+    return (mine - 1) * block_rows + min(block_rows, tail)
+
+
+def cyclic_global_rows(n_rows: int, block_rows: int, world: int, rank: int) -> np.ndarray:
+    """Global row ids of the local rows 0..n_local-1 of `rank` (same formula as otters_shard_map)."""
+    n_local = cyclic_local_rows(n_rows, block_rows, world, rank)
+    local = np.arange(n_local, dtype=np.int64)
+    return (local // block_rows * world + rank) * block_rows + local % block_rows
 
 
 def merge_records_host(records: np.ndarray, k: int, take_max: bool):
@@ -54,7 +74,7 @@ class ShardedSearcher:
 class CudaShard:
     """Product implementation: a VecStore or MetaStore shard on this rank's GPU."""
 
-    def __init__(self, store, row_base: int, k_max: int, group=None):
+    def __init__(self, store, row_base: int, k_max: int, group=None, block_rows: int = 0):
         import torch
         import torch.distributed as dist
 
@@ -69,6 +89,8 @@ class CudaShard:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # block_rows > 0: the shard holds every world-th block of block_rows rows (block-cyclic); else contiguous
+        self.map = _ffi.ShardMap(self.row_base, self.world if block_rows else 1, self.rank if block_rows else 0, int(block_rows))
         dev = torch.device("cuda", self.ctx.device)
         self.local = torch.empty((k_max, 16), dtype=torch.uint8, device=dev)
         self.gathered = torch.empty((self.world * k_max, 16), dtype=torch.uint8, device=dev)
@@ -80,11 +102,11 @@ class CudaShard:
         st = ffi.QueryStats()
         local = self.local[:k]
         if self.is_meta:
-            rc = ffi.otters_query_local_device(None, self.store.handle, C.byref(vq), fp.byref() if fp else None, self.row_base,
+            rc = ffi.otters_query_local_device(None, self.store.handle, C.byref(vq), fp.byref() if fp else None, C.byref(self.map),
                                                C.c_void_p(local.data_ptr()), C.byref(st) if want_stats else None)
         else:
             self.store._flush()
-            rc = ffi.otters_query_local_device(self.store._handle(), None, C.byref(vq), None, self.row_base,
+            rc = ffi.otters_query_local_device(self.store._handle(), None, C.byref(vq), None, C.byref(self.map),
                                                C.c_void_p(local.data_ptr()), None)
         if rc != 0:
             from .types import OttersError

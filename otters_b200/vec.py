@@ -101,6 +101,13 @@ class VecStore:
         check(_ffi.otters_vecstore_add_synthetic(self._handle(), first_row, n, seed))
         self._n += n
 
+    def add_synthetic_sharded(self, world: int, rank: int, block_rows: int, n_local: int, seed: int, row_base: int = 0) -> None:
+        """Appends the rows a rank holds under block-cyclic sharding (global ids as in otters_shard_map)."""
+        self._flush()
+        m = _ffi.ShardMap(row_base, world, rank, block_rows)
+        check(_ffi.otters_vecstore_add_synthetic_sharded(self._handle(), C.byref(m), n_local, seed))
+        self._n += n_local
+
     def reserve(self, n: int) -> None:
         check(_ffi.otters_vecstore_reserve(self._handle(), n))
 

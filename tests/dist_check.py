@@ -14,7 +14,7 @@ from helpers import assert_same_results  # noqa: E402
 from oracle import oracle as ora  # noqa: E402
 from otters_b200 import _ffi  # noqa: E402
 from otters_b200.meta import FilterPack  # noqa: E402
-from otters_b200.sharded import CudaShard, shard_range  # noqa: E402
+from otters_b200.sharded import CudaShard, cyclic_global_rows, shard_range  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -59,6 +59,21 @@ for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob
         tot = torch.tensor([st.evaluated_chunks, st.vectors_compared, st.total_chunks], dtype=torch.int64, device="cuda")
         dist.all_reduce(tot)
         assert tot.tolist() == [ostats["evaluated_chunks"], ostats["vectors_compared"], ostats["total_chunks"]], (tot.tolist(), ostats)
+        # block-cyclic sharding: blocks of cs rows dealt round-robin; global ids come back through otters_shard_map
+        g = cyclic_global_rows(n, cs, world, rank)
+        colc = ob.Column.from_numpy("val", ob.DataType.Int32, val[g], nulls[g])
+        msc = ob.MetaStore.from_columns([colc]).with_vectors(vectors[g]).with_chunk_size(cs).with_context(ctx).build()
+        shardc = CudaShard(msc, 0, k, block_rows=cs)
+        gathered, st = shardc.enqueue(vq, fp, k, want_stats=True)
+        got = shardc.merge(gathered, k, tt == ob.TakeType.Max)
+        assert_same_results(got, (oi, os_, oq), f"cyclic meta {metric.name} nq={nq} rank {rank}")
+        tot = torch.tensor([st.evaluated_chunks, st.vectors_compared, st.total_chunks], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        assert tot.tolist() == [ostats["evaluated_chunks"], ostats["vectors_compared"], ostats["total_chunks"]], (tot.tolist(), ostats)
+        vsc = ob.VecStore(dim, ctx)
+        vsc.add_vectors(vectors[g])
+        got = CudaShard(vsc, 0, k, block_rows=cs).search(vq, None, k, tt == ob.TakeType.Max)
+        assert_same_results(got, want, f"cyclic vec {metric.name} nq={nq} rank {rank}")
 dist.barrier()
 if rank == 0:
     print("DIST_CHECK_OK")

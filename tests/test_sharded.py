@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 
 from helpers import ROOT, assert_same_results, ob, ora
-from otters_b200.sharded import EMPTY_ROW, RECORD_DTYPE, ShardedSearcher, merge_records_host, shard_range
+from otters_b200.sharded import (EMPTY_ROW, RECORD_DTYPE, ShardedSearcher, cyclic_global_rows, cyclic_local_rows,
+                                 merge_records_host, shard_range)
 
 
 def test_shard_range_is_chunk_aligned_partition():
@@ -23,6 +24,17 @@ def test_shard_range_is_chunk_aligned_partition():
             assert r0 % cs == 0 or r0 == n
             prev = r1
         assert prev == n
+
+
+def test_cyclic_sharding_partitions_rows():
+    for n, b, w in [(10_000_000, 1024, 8), (1000, 96, 3), (5, 1024, 4), (0, 16, 2), (1025, 1024, 2), (777, 1, 5), (2048, 1024, 2)]:
+        parts = [cyclic_global_rows(n, b, w, r) for r in range(w)]
+        assert [len(p) for p in parts] == [cyclic_local_rows(n, b, w, r) for r in range(w)]
+        allrows = np.concatenate(parts) if n else np.zeros(0, np.int64)
+        assert len(allrows) == n and len(np.unique(allrows)) == n
+        assert all(np.all(np.diff(p) > 0) for p in parts)  # local order == global order within a shard
+        if n >= b * w * 4:
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= b
 
 
 def test_merge_records_host_order():
@@ -112,3 +124,18 @@ def test_nccl_sharded_search_world2():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_CHECK_OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_synthetic_sharded_generator_matches_global_rows(ctx):
+    n, dim, b, w = 5000, 24, 64, 3
+    full = ora.synth_fill(0, n, dim, 77)
+    q = ora.synth_fill(0, 1, dim, 78)
+    for r in range(w):
+        g = cyclic_global_rows(n, b, w, r)
+        s = ob.VecStore(dim)
+        s.add_synthetic_sharded(w, r, b, len(g), 77)
+        assert np.array_equal(s.inv_norms().view(np.uint32), ora.inv_norms(full[g]).view(np.uint32))
+        got = s.query(q[0], ob.Metric.DotProduct).take(20).collect_arrays()
+        want = ora.vecstore_query(full[g], q, ob.Metric.DotProduct, ob.TakeType.Max, 20)
+        assert_same_results(got, want, f"rank {r}")
