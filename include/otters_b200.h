@@ -93,6 +93,7 @@ typedef struct {
     uint32_t ctas_per_sm;
     uint32_t unit_rows;    /* 32, 64 or 128 rows per dynamically scheduled work unit */
     uint32_t disable_fused_predicate; /* 1: evaluate the row predicate in its own kernel instead of inside the scan */
+    uint32_t batch_mode;   /* query batches: 0 = automatic, 1 = always the tensor-core kernel (when k <= 1024), 2 = never */
 } otters_scan_tuning;
 OTTERS_API int otters_ctx_set_tuning(otters_ctx *ctx, const otters_scan_tuning *t);
 
@@ -105,6 +106,12 @@ typedef struct {
     uint64_t meta_bytes;        /* algorithmic bytes of prune + row-mask kernels */
     float scan_ms;              /* device time of the scan kernel(s) of the last query (CUDA events) */
     float prune_ms, rowmask_ms, select_ms;
+    /* query batches served by the tcgen05 kernel (K2): scan_ms is then the device time of that kernel */
+    uint32_t batch_used;        /* 1: the tensor-core kernel produced the result */
+    uint32_t batch_fallback;    /* 1: its candidate set could not be verified and the batch was re-run query by query */
+    uint64_t batch_candidates;  /* (row, query) pairs re-scored in the reference's exact arithmetic */
+    float batch_max_err;        /* largest |tensor-core score - exact score| over the re-scored pairs */
+    float batch_delta;          /* the error bound the selection assumed (must exceed batch_max_err) */
 } otters_last_work;
 OTTERS_API int otters_ctx_last_work(otters_ctx *ctx, otters_last_work *out);
 

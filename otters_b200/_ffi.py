@@ -34,6 +34,7 @@ class ScanTuning(C.Structure):
         ("ctas_per_sm", C.c_uint32),
         ("unit_rows", C.c_uint32),
         ("disable_fused_predicate", C.c_uint32),
+        ("batch_mode", C.c_uint32),
     ]
 
 
@@ -47,6 +48,11 @@ class LastWork(C.Structure):
         ("prune_ms", C.c_float),
         ("rowmask_ms", C.c_float),
         ("select_ms", C.c_float),
+        ("batch_used", C.c_uint32),
+        ("batch_fallback", C.c_uint32),
+        ("batch_candidates", C.c_uint64),
+        ("batch_max_err", C.c_float),
+        ("batch_delta", C.c_float),
     ]
 
 

@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libotters_b200.so (include/otters_b200.h): contexts, device-resident stores,
 // query orchestration.  Everything that touches rows runs in the CUDA kernels of scan.cu / select.cu
 // / meta.cu / store.cu; there is no CPU fallback.
+#include <float.h>
 #include <math.h>
 #include <string.h>
 
@@ -76,6 +77,15 @@ struct otters_ctx {
     size_t emit_cap = 0;
     otters_topk_record* d_records = nullptr;
     size_t records_cap = 0;
+    // batched (tensor-core) path
+    float* d_qh = nullptr;              // hi / lo tf32 split of the staged queries, padded to 256-query tiles
+    float* d_ql = nullptr;
+    size_t d_qh_floats = 0, d_ql_floats = 0;
+    float* d_qscal = nullptr;           // per-query scalar: 1/|q| (cosine) or |q|^2 (euclidean)
+    size_t d_qscal_floats = 0;
+    uint32_t* d_cta_qids = nullptr;     // [grid_max][kMaxFusedK]
+    unsigned long long* d_batch_info = nullptr;  // d_ctrl + 64: [0] shared threshold key, [1] flags | max error bits << 32, [2] best excluded
+    uint32_t batch_smem_configured[3] = {0, 0, 0};
 
     // pinned staging: queries / masks, lowered filters, results
     uint8_t* h_stage = nullptr;
@@ -103,8 +113,6 @@ static int ensure_stage(otters_ctx* c, size_t bytes) {
     }
     if (bytes <= c->h_stage_bytes) return OTTERS_OK;
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->h_filter) cudaFreeHost(c->h_filter);
-    if (c->h_result) cudaFreeHost(c->h_result);
     c->h_stage = nullptr;
     c->h_stage_bytes = 0;
     size_t nb = std::max<size_t>(round_up(bytes, 4096), 1 << 16);
@@ -132,9 +140,16 @@ static int ensure_pinned(uint8_t** ptr, size_t* cap, size_t bytes) {
     return OTTERS_OK;
 }
 
+// resets the scan/selection state but keeps the prune kernel's stats (fallback from the batched path)
+static int reset_scan_state(otters_ctx* c) {
+    OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl, 0, 32, c->stream));
+    OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl + 64, 0, 64, c->stream));
+    return OTTERS_OK;
+}
+
 // one memset resets every per-query counter (unit counter, list counts, tau, rows scored, stats)
 static int begin_query(otters_ctx* c) {
-    OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl, 0, 64, c->stream));
+    OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl, 0, 128, c->stream));
     c->last = otters_last_work{};
     c->timed_single = c->timed_meta = c->timed_rowmask = false;
     return OTTERS_OK;
@@ -197,6 +212,7 @@ struct VecStorage {
     uint64_t n = 0, cap = 0;
     float* d_rows = nullptr;
     float* d_inv = nullptr;
+    float max_norm = -1.f;  // largest row norm (lazily computed for the batched path's error bound); < 0 = unknown
 
     int reserve(uint64_t want) {
         if (want <= cap) return OTTERS_OK;
@@ -237,6 +253,7 @@ struct VecStorage {
         if (rc) return rc;
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be reused after return
         n += cnt;
+        max_norm = -1.f;
         return OTTERS_OK;
     }
     int add_synth(ShardMap gen_map, uint64_t cnt, uint64_t seed) {
@@ -250,6 +267,7 @@ struct VecStorage {
         if (rc) return rc;
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
         n += cnt;
+        max_norm = -1.f;
         return OTTERS_OK;
     }
     void release() {
@@ -357,6 +375,7 @@ struct QueryRun {
     uint32_t result_list = 0;  // index into ctx->d_list holding the final ordered candidates
     uint64_t k_eff = 0;
     bool big = false;          // result lives in ctx->d_emit-sized list (emit-all path)
+    bool prefetched = false;   // header + candidates already sit in ctx->h_result (batched path)
 };
 
 static float host_inv_norm(const float* v, uint32_t dim) {
@@ -369,6 +388,223 @@ static float host_inv_norm(const float* v, uint32_t dim) {
     }
     float norm = sqrtf(s);
     return norm != 0.0f ? 1.0f / norm : 0.0f;
+}
+
+
+// ---- query batches on the tensor cores (K2, batched.cu) ---------------------------------------------------
+// Selection runs on 3xTF32 tensor-core scores; every selected (row, query) pair is re-scored in the
+// reference's exact arithmetic and the result is accepted only if no excluded pair can reach it:
+//   (approximate cut score) +- delta must lie strictly outside the exact k-th score,
+// with delta a bound on |tensor-core score - exact score|.  Otherwise the caller falls back to K1 per query.
+static double host_norm(const float* v, uint32_t dim) {
+    double s = 0.0;
+    for (uint32_t i = 0; i < dim; ++i) s += (double)v[i] * (double)v[i];
+    return sqrt(s);
+}
+
+static int store_max_norm(otters_ctx* c, VecStorage* st, float* out) {
+    if (st->max_norm < 0.f) {
+        uint32_t* d_bits = reinterpret_cast<uint32_t*>(c->d_ctrl + 192);
+        int rc = launch_min_inv_norm(st->d_inv, st->n, d_bits, c->stream);
+        if (rc) return rc;
+        uint32_t bits = 0;
+        OTTERS_CUDA(cudaMemcpyAsync(&bits, d_bits, 4, cudaMemcpyDeviceToHost, c->stream));
+        OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+        float mn;
+        memcpy(&mn, &bits, 4);
+        st->max_norm = (mn > 0.f && mn < 1e30f) ? 1.0f / mn : 0.f;
+    }
+    *out = st->max_norm;
+    return OTTERS_OK;
+}
+
+static bool batch_eligible(const otters_ctx* c, const otters_vec_query* q, uint64_t n_rows, uint64_t k_eff) {
+    const uint32_t mode = c->tuning.batch_mode;
+    if (mode == 2 || q->nq < 2 || k_eff == 0 || k_eff > kMaxFusedK || n_rows == 0) return false;
+    const uint32_t cap = (uint32_t)pow2_at_least(std::max<uint64_t>(2 * k_eff, 64));
+    if (batch_smem_bytes(cap) > c->smem_optin) return false;
+    if (mode == 1) return true;
+    // one tensor-core pass costs about as much as a handful of streaming scans of the store
+    return q->nq >= 8 && n_rows >= 4096;
+}
+
+static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const std::vector<float>& q_inv,
+                       const uint32_t* d_row_mask, uint32_t row_mask_words, otters_topk_record* d_records_out, ShardMap map,
+                       const unsigned long long* stats_src, QueryRun* run, bool* accepted) {
+    *accepted = false;
+    cudaStream_t s = c->stream;
+    const uint32_t dim_pad = st->pitch;
+    const uint64_t k_eff = run->k_eff;
+    const uint32_t k = (uint32_t)k_eff;
+    const uint32_t cap = (uint32_t)pow2_at_least(std::max<uint32_t>(2 * k, 64));
+    const uint32_t nq_pad = (uint32_t)round_up(q->nq, kBatchQueries);
+    const bool take_max = q->take_type == OTTERS_TAKE_MAX;
+
+    // error bound of the tensor-core scores
+    double qmax = 0.0;
+    for (uint32_t i = 0; i < q->nq; ++i) qmax = std::max(qmax, host_norm(q->queries + (size_t)i * q->dim, q->dim));
+    const double kappa = ldexp(1.0, -15) * std::max(1.0, (double)st->dim / 1024.0);
+    float delta;
+    if (q->metric == OTTERS_METRIC_COSINE) {
+        delta = (float)(kappa * 1.01);
+    } else {
+        float vmax = 0.f;
+        int rc0 = store_max_norm(c, st, &vmax);
+        if (rc0) return rc0;
+        delta = (float)(q->metric == OTTERS_METRIC_DOT ? kappa * 1.01 * qmax * vmax : kappa * 1.01 * (qmax + vmax) * (qmax + vmax));
+    }
+    if (!(delta <= FLT_MAX)) return OTTERS_OK;  // non-finite inputs: exact path
+
+    // per-query scalars: 1/|q| (cosine, the reference's value) or |q|^2 (euclidean)
+    int rc = ensure_dev(&c->d_qscal, &c->d_qscal_floats, (size_t)q->nq, s);
+    if (rc) return rc;
+    rc = ensure_dev(&c->d_qh, &c->d_qh_floats, (size_t)nq_pad * dim_pad, s);
+    if (rc) return rc;
+    rc = ensure_dev(&c->d_ql, &c->d_ql_floats, (size_t)nq_pad * dim_pad, s);
+    if (rc) return rc;
+    float* hs = reinterpret_cast<float*>(c->h_stage) + (size_t)q->nq * dim_pad;  // after the staged queries
+    for (uint32_t i = 0; i < q->nq; ++i) {
+        if (q->metric == OTTERS_METRIC_EUCLIDEAN) {
+            const double n = host_norm(q->queries + (size_t)i * q->dim, q->dim);
+            hs[i] = (float)(n * n);
+        } else {
+            hs[i] = q_inv[i];
+        }
+    }
+    OTTERS_CUDA(cudaMemcpyAsync(c->d_qscal, hs, (size_t)q->nq * 4, cudaMemcpyHostToDevice, s));
+    OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
+    c->stage_pending = true;
+    rc = launch_split_queries(c->d_query, q->nq, nq_pad, dim_pad, c->d_qh, c->d_ql, s);
+    if (rc) return rc;
+
+    const uint32_t n_rowtiles = (uint32_t)((st->n + kBatchRows - 1) / kBatchRows);
+    const uint64_t n_tiles = (uint64_t)n_rowtiles * (nq_pad / kBatchQueries);
+    BatchLaunch bl{};
+    bl.vectors = st->d_rows;
+    bl.n_rows = st->n;
+    bl.pitch_g = st->pitch;
+    bl.dim = st->dim;
+    bl.dim_pad = dim_pad;
+    bl.q_hi = c->d_qh;
+    bl.q_lo = c->d_ql;
+    bl.nq_pad = nq_pad;
+    bl.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count, n_tiles);
+    BatchParams bp{};
+    bp.n_rows = (uint32_t)st->n;
+    bp.nq = q->nq;
+    bp.inv_norms = st->d_inv;
+    bp.q_scal = c->d_qscal;
+    bp.take_max = take_max;
+    bp.has_filter = q->has_filter;
+    bp.thr = q->thr;
+    bp.cmp = q->cmp;
+    bp.delta = delta;
+    bp.row_mask = d_row_mask;
+    bp.row_mask_words = row_mask_words;
+    bp.k = k;
+    bp.cap = cap;
+    bp.g_tau = c->d_batch_info;
+    bp.g_flags = reinterpret_cast<uint32_t*>(c->d_batch_info + 1);
+    bp.g_excl = reinterpret_cast<uint32_t*>(c->d_batch_info + 2);
+    bp.pairs_scored = c->d_rows_scored;
+    bp.cta_keys = c->d_cta_keys;
+    bp.cta_qids = c->d_cta_qids;
+    bp.cta_counts = c->d_cta_counts;
+    cudaEventRecord(c->ev[2], s);
+    cudaEventRecord(c->ev[3], s);
+    rc = launch_batch(bl, bp, q->metric, c->batch_smem_configured, s);
+    if (rc) return rc;
+    cudaEventRecord(c->ev[4], s);
+    c->timed_single = true;
+
+    // exact re-scoring of every selected pair, then a full sort of the exact candidates
+    const uint32_t total = bl.grid * k;
+    const uint64_t n_sort = std::max<uint64_t>(pow2_at_least(total), 2048);
+    if (c->emit_cap < n_sort) {
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_emit);
+        c->d_emit = nullptr;
+        c->emit_cap = 0;
+        if (cudaMalloc((void**)&c->d_emit, n_sort * sizeof(Cand)) != cudaSuccess)
+            return fail(OTTERS_ERR_NOMEM, "device allocation for the candidate sort failed");
+        c->emit_cap = n_sort;
+    }
+    rc = ensure_list0(c, k_eff);
+    if (rc) return rc;
+    RescoreParams rp{};
+    rp.vectors = st->d_rows;
+    rp.inv_norms = st->d_inv;
+    rp.queries = c->d_query;
+    rp.q_inv = c->d_qscal;
+    rp.pitch_g = st->pitch;
+    rp.dim = st->dim;
+    rp.dim_pad = dim_pad;
+    rp.cta_keys = c->d_cta_keys;
+    rp.cta_qids = c->d_cta_qids;
+    rp.cta_counts = c->d_cta_counts;
+    rp.n_lists = bl.grid;
+    rp.k = k;
+    rp.take_max = take_max;
+    rp.has_filter = q->has_filter;
+    rp.thr = q->thr;
+    rp.cmp = q->cmp;
+    rp.out = c->d_emit;
+    rp.out_slots = total;
+    rp.out_count = c->d_counter + 1;
+    rp.max_err_bits = reinterpret_cast<uint32_t*>(c->d_batch_info + 1) + 1;
+    rc = launch_rescore(rp, q->metric, (uint32_t)n_sort, s);
+    if (rc) return rc;
+    rc = launch_global_sort(c->d_emit, n_sort, s);
+    if (rc) return rc;
+    rc = launch_take_sorted(c->d_emit, c->d_counter + 1, nullptr, k_eff, c->d_list[0], c->d_list_count, c->d_tau, list_hdr(c, 0),
+                            c->d_rows_scored, stats_src, s, c->d_batch_info + 1);
+    if (rc) return rc;
+    if (d_records_out) {
+        rc = launch_cands_to_records(c->d_list[0], c->d_list_count, k, map, take_max, d_records_out, s);
+        if (rc) return rc;
+    }
+    cudaEventRecord(c->ev[5], s);
+    c->last.kernel_launches += 6 + (d_records_out ? 1 : 0);
+
+    // fetch header + candidates and verify the selection
+    const size_t bytes = sizeof(ResultHeader) + (size_t)k_eff * sizeof(Cand);
+    rc = ensure_pinned(&c->h_result, &c->h_result_bytes, bytes);
+    if (rc) return rc;
+    OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[0], bytes, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaStreamSynchronize(s));
+    c->stage_pending = false;
+    const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
+    const Cand* list = reinterpret_cast<const Cand*>(c->h_result + sizeof(ResultHeader));
+    const uint32_t flags = (uint32_t)hdr->extra[0];
+    const uint32_t err_bits = (uint32_t)(hdr->extra[0] >> 32);
+    const uint32_t excl = (uint32_t)hdr->extra[1];
+    float max_err;
+    memcpy(&max_err, &err_bits, 4);
+    bool ok = (flags & 1u) == 0 && max_err <= delta;
+    if (ok && excl != 0) {
+        // some pair was left out of the candidate lists: its exact score is within delta of its tensor-core
+        // score, so it cannot belong to the result iff even that bound stays strictly outside the k-th score
+        if (hdr->count < k_eff) ok = false;
+        else {
+            const float e_k = key_score(list[hdr->count - 1].key, take_max);
+            const float x = key_score((uint64_t)excl << 32, take_max);
+            ok = take_max ? (x + delta < e_k) : (x - delta > e_k);
+        }
+    }
+    c->last.batch_max_err = max_err;
+    c->last.batch_delta = delta;
+    c->last.batch_candidates = 0;
+    if (!ok) {
+        c->last.batch_fallback = 1;
+        c->timed_single = false;
+        return OTTERS_OK;
+    }
+    c->last.batch_used = 1;
+    run->result_list = 0;
+    run->big = false;
+    run->prefetched = true;
+    *accepted = true;
+    return OTTERS_OK;
 }
 
 static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const uint32_t* d_row_mask,
@@ -385,7 +621,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
 
     // stage queries (zero padded to the stored pitch) and their inverse norms
     const size_t qfloats = (size_t)q->nq * dim_pad;
-    int rc = ensure_stage(c, qfloats * 4 + 64);
+    int rc = ensure_stage(c, qfloats * 4 + (size_t)q->nq * 4 + 64);
     if (rc) return rc;
     rc = ensure_dev(&c->d_query, &c->d_query_floats, qfloats, s);
     if (rc) return rc;
@@ -400,6 +636,15 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     OTTERS_CUDA(cudaMemcpyAsync(c->d_query, hq, qfloats * 4, cudaMemcpyHostToDevice, s));
     OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
     c->stage_pending = true;
+
+    if (batch_eligible(c, q, n_rows, k_eff)) {
+        bool accepted = false;
+        rc = run_batched(c, st, q, q_inv, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, &accepted);
+        if (rc) return rc;
+        if (accepted) return OTTERS_OK;
+        rc = reset_scan_state(c);  // selection could not be verified: exact path, query by query
+        if (rc) return rc;
+    }
 
     const bool fused = k_eff <= kMaxFusedK;
     ScanPlan pl;
@@ -551,11 +796,13 @@ static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint
                          float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, unsigned long long* stats_out) {
     cudaStream_t s = c->stream;
     const size_t bytes = sizeof(ResultHeader) + (size_t)run.k_eff * sizeof(Cand);
-    int rc = ensure_pinned(&c->h_result, &c->h_result_bytes, bytes);
-    if (rc) return rc;
-    OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[run.result_list], bytes, cudaMemcpyDeviceToHost, s));
-    OTTERS_CUDA(cudaStreamSynchronize(s));
-    c->stage_pending = false;
+    if (!run.prefetched) {
+        int rc = ensure_pinned(&c->h_result, &c->h_result_bytes, bytes);
+        if (rc) return rc;
+        OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[run.result_list], bytes, cudaMemcpyDeviceToHost, s));
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        c->stage_pending = false;
+    }
     const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
     const uint32_t n = hdr->count;
     c->last.rows_scored = hdr->rows_scored;
@@ -638,6 +885,8 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
     c->d_stats = reinterpret_cast<unsigned long long*>(c->d_ctrl + 32);
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_keys, (size_t)c->grid_max * kMaxFusedK * sizeof(uint64_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_counts, (size_t)c->grid_max * sizeof(uint32_t)));
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_qids, (size_t)c->grid_max * kMaxFusedK * sizeof(uint32_t)));
+    c->d_batch_info = reinterpret_cast<unsigned long long*>(c->d_ctrl + 64);
     {
         int rc0 = alloc_list(c.get(), 0, kMaxFusedK);
         if (rc0) return rc0;
@@ -670,7 +919,13 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     cudaFree(c->d_mask);
     cudaFree(c->d_emit);
     cudaFree(c->d_records);
+    cudaFree(c->d_qh);
+    cudaFree(c->d_ql);
+    cudaFree(c->d_qscal);
+    cudaFree(c->d_cta_qids);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_filter) cudaFreeHost(c->h_filter);
+    if (c->h_result) cudaFreeHost(c->h_result);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1395,7 +1650,9 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
     const bool scan = !chunk_err && q->k > 0 && ms->st.n > 0;
     uint64_t meta_bytes = 0;
-    rc = run_meta_filter(ms, filter, q->nq, scan && filter, false, &meta_bytes);
+    // the batched tensor-core kernel gates rows with a precomputed mask (K0b) instead of the fused predicate
+    const bool batched = scan && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
+    rc = run_meta_filter(ms, filter, q->nq, scan && filter, batched && filter, &meta_bytes);
     if (rc) return rc;
     unsigned long long hstats[4] = {0, 0, 0, 0};
     uint64_t n_out = 0;
@@ -1410,7 +1667,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     };
     if (scan) {
         QueryRun run;
-        const bool fuse = filter && !c->tuning.disable_fused_predicate && ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes;
+        const bool fuse = filter && !batched && !c->tuning.disable_fused_predicate && ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes;
         rc = run_queries(c, &ms->st, q, (filter && !fuse) ? ms->d_row_mask : nullptr,
                          (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, map, c->d_stats,
                          fuse ? &ms->cur_filter : nullptr, &run);

@@ -1,0 +1,703 @@
+// batched.cu — K2: query batches as a TMA-fed tcgen05 (UMMA) 3xTF32 tile contraction (sm_100a).
+//
+// Replaces, for nq > 1, the serial per-query inner loop of VecQueryPlan::collect (reference
+// src/vec.rs:243-266: every 8-row block is scored against every query) together with the scoring
+// kernels of src/vec_compute.rs:9-54.  A batch feeds ONE global collector (src/vec.rs:217-219), so the
+// kernel keeps one candidate list per CTA over all (row, query) pairs it scores.
+//
+// Structure:
+//   S[row, q] = sum_d V[row, d] * Q[q, d] is a dense contraction: 128 store rows (UMMA M, the TMEM
+//   lanes) x 256 queries (UMMA N, TMEM columns) per tile, K streamed in blocks of 32 fp32 columns
+//   (one 128-byte swizzle atom).  fp32 accuracy on tf32 tensor cores comes from the 3xTF32 split
+//   x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi):  S ~= Vlo*Qhi + Vhi*Qlo + Vhi*Qhi
+//   (three tcgen05.mma kind::tf32 per k-step, fp32 accumulators in TMEM).
+//   Warp roles: warp 0 TMA producer (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx),
+//   warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-7 split the landed V tile into
+//   hi/lo in shared memory, warps 8-11 epilogue (tcgen05.ld -> metric -> loosened vec_filter ->
+//   lock-free per-CTA top-k of APPROXIMATE scores).  The accumulator is double buffered in TMEM
+//   (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   Exactness: tensor-core scores differ from the reference's 8-lane fp32 order in the last bits, so
+//   K2 only SELECTS candidates; rescore_kernel then recomputes every surviving (row, query) pair in the
+//   reference's exact arithmetic order (same code shape as K1), applies the exact vec_filter, and the
+//   final order comes from the exact keys.  The host verifies that no excluded pair can reach the
+//   result (approximate cut + error bound < exact k-th score) and otherwise falls back to K1 per query.
+#include <cuda.h>  // CUtensorMap types only; the encoder is resolved through cudaGetDriverEntryPoint
+#include <float.h>
+
+#include "internal.h"
+
+namespace otters {
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint32_t BM = kBatchRows;     // 128 store rows per tile
+constexpr uint32_t BN = kBatchQueries;  // 256 queries per tile
+constexpr uint32_t BK = 32;             // fp32 columns per k-block (128 bytes)
+constexpr uint32_t UK = 8;              // K of one tcgen05.mma kind::tf32
+constexpr uint32_t STAGES = 2;
+constexpr uint32_t A_BYTES = BM * BK * 4;  // 16 KB
+constexpr uint32_t B_BYTES = BN * BK * 4;  // 32 KB
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // Vhi | Vlo | Qhi | Qlo = 96 KB
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t NUM_THREADS = 384;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, kind::tf32, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 consecutive TMEM columns of this thread's lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major tile whose rows are one 128-byte swizzle atom wide
+// (rows 128 bytes apart, 8-row groups 1024 bytes apart; tile base 1024-byte aligned):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 = 1024 >> 4 | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor, kind::tf32: [4,6) D format = 1 (f32) | [7,10) A format = 2 (tf32) | [10,13) B format = 2 |
+// [15] A major = 0 (K) | [16] B major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+struct CtaHdr {
+    unsigned long long tau;  // candidates must have key > tau
+    uint32_t count;          // slots reserved in the candidate buffer (may transiently exceed cap)
+    uint32_t written;        // slots whose entry has been stored
+    uint32_t excl;           // ord_f32 of the best signed score this CTA excluded from its list (0 = nothing excluded)
+};
+// The upper half of a key ("goodness": ord(score) for take Max, ~ord(score) for take Min) orders candidates by
+// score alone; excl tracks its maximum over everything a CTA left out of its list.
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+__device__ __forceinline__ bool before(uint64_t ka, uint32_t qa, uint64_t kb, uint32_t qb) {
+    return ka > kb || (ka == kb && qa < qb);
+}
+
+// one warp: sort (key, qid) pairs best-first; entries >= cnt are cleared first
+__device__ void warp_sort_pairs(uint64_t* keys, uint32_t* qids, uint32_t cnt, uint32_t cap, int lane) {
+    for (uint32_t i = cnt + lane; i < cap; i += 32) {
+        keys[i] = 0ull;
+        qids[i] = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    for (uint32_t size = 2; size <= cap; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < (cap >> 1); t += 32) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool fwd = (lo & size) == 0;
+                uint64_t ka = keys[lo], kb = keys[hi];
+                uint32_t qa = qids[lo], qb = qids[hi];
+                bool swap = fwd ? before(kb, qb, ka, qa) : before(ka, qa, kb, qb);
+                if (swap) {
+                    keys[lo] = kb;
+                    keys[hi] = ka;
+                    qids[lo] = qb;
+                    qids[hi] = qa;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Lock-free append (same protocol as K1's warp_push, scan.cu) with a query-id payload.  After a compaction
+// the CTA's new threshold is published to the grid-wide threshold (any key below some CTA's k-th best key
+// cannot be among the global best k), and the grid-wide value is adopted when it is higher.
+__device__ void warp_push_pairs(CtaHdr* hdr, uint64_t* keys, uint32_t* qids, uint32_t cap, uint32_t k, bool has, uint64_t key,
+                                uint32_t qid, unsigned long long* g_tau, int lane) {
+    for (;;) {
+        const uint64_t tau = ld_volatile_u64(&hdr->tau);
+        if (has && key <= tau) {  // rejected by the exact key test (rare): it counts as excluded
+            atomicMax(&hdr->excl, (uint32_t)(key >> 32));
+            has = false;
+        }
+        const unsigned m = __ballot_sync(FULL, has);
+        const uint32_t n = __popc(m);
+        if (!n) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&hdr->count, n);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + n <= cap) {
+            if (has) {
+                const uint32_t at = base + __popc(m & ((1u << lane) - 1u));
+                keys[at] = key;
+                qids[at] = qid;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&hdr->written, n);
+            }
+            return;
+        }
+        if (base <= cap) {
+            // compactor: valid entries are [0, base)
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (ld_volatile_u32(&hdr->written) != base) {
+                    if (clock64() - t0 > 4000000000ll) __trap();  // watchdog
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            warp_sort_pairs(keys, qids, base, cap, lane);
+            if (lane == 0) {
+                if (base > k) {  // entries [k, base) are dropped: remember the best of them
+                    atomicMax(&hdr->excl, (uint32_t)(keys[k] >> 32));
+                }
+                unsigned long long t = keys[k - 1];  // base > cap - 32 >= k
+                const unsigned long long g = atomicMax(g_tau, t);
+                if (g > t) t = g;
+                if (t > hdr->tau) *reinterpret_cast<volatile unsigned long long*>(&hdr->tau) = t;
+                *reinterpret_cast<volatile uint32_t*>(&hdr->written) = k;
+                __threadfence_block();
+                atomicExch(&hdr->count, k);
+            }
+            __syncwarp();
+        } else {
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (ld_volatile_u32(&hdr->count) > cap) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > 4000000000ll) __trap();  // watchdog
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// loosened vec_filter on an approximate score: never rejects a pair whose exact score passes (|a - e| <= delta)
+__device__ __forceinline__ bool score_passes_loose(float s, float thr, int cmp, float delta) {
+    switch (cmp) {
+    case 0: return s < thr + delta;
+    case 1: return s > thr - delta;
+    case 2: return s <= thr + delta;
+    case 3: return s >= thr - delta;
+    default: return fabsf(s - thr) <= delta;
+    }
+}
+
+// tile t -> (row tile, query tile): consecutive tiles share the row tile so that the CTAs working on it at the
+// same time find the V tile in L2 after the first HBM read
+__device__ __forceinline__ bool tile_live(const BatchParams& p, uint32_t rt) {
+    if (!p.row_mask) return true;
+    const uint32_t w0 = rt * (BM / 32);
+    uint32_t any = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < BM / 32; ++i) any |= (w0 + i) < p.row_mask_words ? __ldg(p.row_mask + w0 + i) : 0xFFFFFFFFu;
+    return any != 0;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qh,
+             const __grid_constant__ CUtensorMap tm_ql, const __grid_constant__ BatchParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    // the operand tiles need 1024-byte alignment (128B swizzle atoms)
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* aux = smem + STAGES * STAGE_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);       // [STAGES] TMA landed
+    uint64_t* bar_cast = bar_full + STAGES;                       // [STAGES] V split into hi/lo
+    uint64_t* bar_empty = bar_cast + STAGES;                      // [STAGES] MMAs reading the stage completed
+    uint64_t* bar_tfull = bar_empty + STAGES;                     // [2] accumulator complete
+    uint64_t* bar_tempty = bar_tfull + 2;                         // [2] accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    CtaHdr* hdr = reinterpret_cast<CtaHdr*>(aux + 128);
+    uint64_t* cand_keys = reinterpret_cast<uint64_t*>(aux + 256);
+    uint32_t* cand_qids = reinterpret_cast<uint32_t*>(aux + 256 + (size_t)p.cap * 8);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_v);
+        prefetch_tmap(&tm_qh);
+        prefetch_tmap(&tm_ql);
+    }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_cast[s], 128);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(&bar_tfull[b], 1);
+            mbar_init(&bar_tempty[b], 128);
+        }
+        fence_mbar_init();
+        hdr->tau = 0ull;
+        hdr->count = 0;
+        hdr->written = 0;
+        hdr->excl = 0;
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const uint32_t n_tiles = p.n_rowtiles * p.n_qtiles;
+    const uint32_t nkb = p.nkb;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const uint32_t rt = t / p.n_qtiles, qt = t % p.n_qtiles;
+                if (!tile_live(p, rt)) continue;
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&bar_empty[s], ph ^ 1u);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + 2 * B_BYTES);
+                    tma_load_2d(st, &tm_v, (int)(kb * BK), (int)(rt * BM), &bar_full[s]);
+                    tma_load_2d(st + 2 * A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN), &bar_full[s]);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN), &bar_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t it = 0, tn = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const uint32_t rt = t / p.n_qtiles;
+                if (!tile_live(p, rt)) continue;
+                const uint32_t buf = tn & 1u, bph = (tn >> 1) & 1u;
+                mbar_wait(&bar_tempty[buf], bph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&bar_full[s], ph);
+                    mbar_wait(&bar_cast[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t d_vh = umma_desc_sw128(sa), d_vl = umma_desc_sw128(sa + A_BYTES);
+                    const uint64_t d_qh = umma_desc_sw128(sa + 2 * A_BYTES), d_ql = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < BK / UK; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);  // K advance inside the swizzle atom
+                        umma_tf32(d_tmem, d_vl + adv, d_qh + adv, kInstrDesc, (kb | kk) != 0 ? 1u : 0u);
+                        umma_tf32(d_tmem, d_vh + adv, d_ql + adv, kInstrDesc, 1u);
+                        umma_tf32(d_tmem, d_vh + adv, d_qh + adv, kInstrDesc, 1u);
+                    }
+                    umma_commit(&bar_empty[s]);
+                }
+                umma_commit(&bar_tfull[buf]);
+                ++tn;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== split warps: V tile -> hi (in place) and lo =====
+        const int tt = tid - 128;
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t rt = t / p.n_qtiles;
+            if (!tile_live(p, rt)) continue;
+            for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(&bar_full[s], ph);
+                float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+                for (uint32_t i = 0; i < A_BYTES / 16 / 128; ++i) {
+                    const uint32_t idx = tt + i * 128;
+                    const float4 x = hi[idx];
+                    float4 h, l;
+                    h.x = rna_tf32(x.x);
+                    h.y = rna_tf32(x.y);
+                    h.z = rna_tf32(x.z);
+                    h.w = rna_tf32(x.w);
+                    l.x = rna_tf32(x.x - h.x);
+                    l.y = rna_tf32(x.y - h.y);
+                    l.z = rna_tf32(x.z - h.z);
+                    l.w = rna_tf32(x.w - h.w);
+                    hi[idx] = h;
+                    lo[idx] = l;
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&bar_cast[s]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue: TMEM -> metric -> loosened filter -> per-CTA top-k of approximate scores =====
+        const uint32_t quarter = (uint32_t)warp & 3u;  // TMEM lanes [32*quarter, 32*quarter+32)
+        const bool take_max = p.take_max != 0;
+        unsigned long long scored = 0;
+        uint32_t tn = 0;
+        bool nonfinite = false;
+        const float sgn = take_max ? 1.0f : -1.0f;
+        float xbest = -INFINITY;  // best signed score among the pairs this thread excluded by the top-k test
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t rt = t / p.n_qtiles, qt = t % p.n_qtiles;
+            if (!tile_live(p, rt)) continue;
+            const uint32_t buf = tn & 1u, bph = (tn >> 1) & 1u;
+            const uint32_t row = rt * BM + quarter * 32 + lane;
+            bool live = row < p.n_rows;
+            if (live && p.row_mask) {
+                const uint32_t w = (row >> 5) < p.row_mask_words ? __ldg(p.row_mask + (row >> 5)) : 0xFFFFFFFFu;
+                live = (w >> (row & 31)) & 1u;
+            }
+            float rs = 0.f;  // cosine: 1/|v|; euclidean: |v|^2
+            if (METRIC != OTTERS_METRIC_DOT && row < p.n_rows) {
+                const float inv = __ldg(p.inv_norms + row);
+                rs = METRIC == OTTERS_METRIC_COSINE ? inv : (inv > 0.f ? 1.0f / (inv * inv) : 0.f);
+            }
+            const uint32_t q_base = qt * BN;
+            const uint32_t nq_tile = p.nq - q_base < BN ? p.nq - q_base : BN;
+            if (live) scored += nq_tile;
+            mbar_wait(&bar_tfull[buf], bph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN;
+            for (uint32_t c = 0; c < BN / 32; ++c) {
+                if (c * 32 >= nq_tile) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                // threshold of this chunk as a float pre-test (the exact key test is inside the push)
+                const uint64_t tau = ld_volatile_u64(&hdr->tau);
+                const float tau_s = tau ? key_score(tau, take_max) : (take_max ? -INFINITY : INFINITY);
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    const uint32_t qi = q_base + c * 32 + j;
+                    const bool inq = c * 32 + j < nq_tile;
+                    const float a = __uint_as_float(v[j]);
+                    float s;
+                    if (METRIC == OTTERS_METRIC_COSINE) s = a * __ldg(p.q_scal + (inq ? qi : 0)) * rs;
+                    else if (METRIC == OTTERS_METRIC_EUCLIDEAN) s = (__ldg(p.q_scal + (inq ? qi : 0)) + rs) - 2.0f * a;
+                    else s = a;
+                    bool ok = live && inq;
+                    if (ok && !(fabsf(s) <= FLT_MAX)) nonfinite = true;  // inf / NaN: let the exact path decide
+                    if (p.has_filter) ok = ok && score_passes_loose(s, p.thr, p.cmp, p.delta);
+                    const bool top = take_max ? s >= tau_s : s <= tau_s;
+                    if (ok && !top) xbest = fmaxf(xbest, s * sgn);
+                    ok = ok && top;
+                    if (__ballot_sync(FULL, ok))
+                        warp_push_pairs(hdr, cand_keys, cand_qids, p.cap, p.k, ok, make_key(s, row, take_max), qi, p.g_tau, lane);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_tempty[buf]);
+            ++tn;
+            // adopt the grid-wide threshold once per tile
+            if (warp == 8 && lane == 0) {
+                const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
+                if (g > hdr->tau) atomicMax(&hdr->tau, g);
+            }
+        }
+        if (__any_sync(FULL, nonfinite) && lane == 0) atomicOr(p.g_flags, 1u);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) xbest = fmaxf(xbest, __shfl_xor_sync(FULL, xbest, d));
+        if (lane == 0 && xbest > -INFINITY) atomicMax(&hdr->excl, (uint32_t)(make_key(xbest * sgn, 0, take_max) >> 32));
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) scored += __shfl_xor_sync(FULL, scored, d);
+        if (lane == 0 && scored) atomicAdd(p.pairs_scored, scored);
+        named_bar_sync(1, 128);  // the four epilogue warps: every push has completed
+        if (warp == 8) {
+            const uint32_t cnt = hdr->count;
+            warp_sort_pairs(cand_keys, cand_qids, cnt, p.cap, lane);
+            const uint32_t n = cnt < p.k ? cnt : p.k;
+            for (uint32_t i = lane; i < n; i += 32) {
+                p.cta_keys[(size_t)blockIdx.x * p.k + i] = cand_keys[i];
+                p.cta_qids[(size_t)blockIdx.x * p.k + i] = cand_qids[i];
+            }
+            if (lane == 0) {
+                p.cta_counts[blockIdx.x] = n;
+                // best score this CTA left out: rejected by the top-k test, dropped by a compaction, or cut here
+                uint32_t x = hdr->excl;
+                if (cnt > p.k && (uint32_t)(cand_keys[p.k] >> 32) > x) x = (uint32_t)(cand_keys[p.k] >> 32);
+                if (x) atomicMax(p.g_excl, x);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- query split: hi = rna_tf32(q), lo = rna_tf32(q - hi); rows >= nq are zero -----------------------------
+__global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql) {
+    const size_t total = (size_t)nq_pad * dim_pad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / dim_pad);
+        float x = r < nq ? q[i] : 0.f;
+        float h = rna_tf32(x);
+        qh[i] = h;
+        ql[i] = rna_tf32(x - h);
+    }
+}
+
+// ---- exact re-scoring of the selected (row, query) pairs ---------------------------------------------------
+// Two threads per pair hold the eight f32x8 lane accumulators (4 each) exactly like K1 (scan.cu): multiply and
+// add are separate round-to-nearest operations, 8-column blocks in order, wide's non-AVX reduce_add order,
+// serial dim%8 tail added last, cosine as (dot * q_inv) * row_inv (reference src/vec_compute.rs:9-54).
+template <int METRIC>
+__global__ void __launch_bounds__(256) rescore_kernel(const __grid_constant__ RescoreParams p) {
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1);
+    const int h = threadIdx.x & 1;
+    const int lane = threadIdx.x & 31;
+    const uint32_t total = p.n_lists * p.k;
+    const uint32_t list = slot < total ? slot / p.k : 0, pos = slot < total ? slot % p.k : 0;
+    const bool valid = slot < total && pos < p.cta_counts[list];
+    uint64_t key_a = 0;
+    uint32_t qid = 0, row = 0;
+    if (valid) {
+        key_a = p.cta_keys[(size_t)list * p.k + pos];
+        qid = p.cta_qids[(size_t)list * p.k + pos];
+        row = key_row(key_a);
+    }
+    const bool take_max = p.take_max != 0;
+    const uint32_t dim8 = p.dim & ~7u, ntail = p.dim & 7u;
+    const float* vrow = p.vectors + (size_t)row * p.pitch_g;
+    const float* qrow = p.queries + (size_t)qid * p.dim_pad;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (valid) {
+        const float4* vp = reinterpret_cast<const float4*>(vrow) + h;
+        const float4* qp = reinterpret_cast<const float4*>(qrow) + h;
+        const uint32_t nblk = dim8 >> 3;
+#pragma unroll 4
+        for (uint32_t j = 0; j < nblk; ++j) {
+            const float4 v = __ldg(vp + 2 * j);
+            const float4 q = __ldg(qp + 2 * j);
+            if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
+                const float d0 = __fsub_rn(q.x, v.x), d1 = __fsub_rn(q.y, v.y), d2 = __fsub_rn(q.z, v.z), d3 = __fsub_rn(q.w, v.w);
+                a0 = __fadd_rn(a0, __fmul_rn(d0, d0));
+                a1 = __fadd_rn(a1, __fmul_rn(d1, d1));
+                a2 = __fadd_rn(a2, __fmul_rn(d2, d2));
+                a3 = __fadd_rn(a3, __fmul_rn(d3, d3));
+            } else {
+                a0 = __fadd_rn(a0, __fmul_rn(q.x, v.x));
+                a1 = __fadd_rn(a1, __fmul_rn(q.y, v.y));
+                a2 = __fadd_rn(a2, __fmul_rn(q.z, v.z));
+                a3 = __fadd_rn(a3, __fmul_rn(q.w, v.w));
+            }
+        }
+    }
+    const float sdot = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+    const float other = __shfl_xor_sync(FULL, sdot, 1);
+    const float tot = h == 0 ? __fadd_rn(sdot, other) : __fadd_rn(other, sdot);
+    float tail = -0.0f;
+    if (valid && ntail) {
+        for (uint32_t e = 0; e < ntail; ++e) {
+            if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
+                const float d = __fsub_rn(qrow[dim8 + e], vrow[dim8 + e]);
+                tail = __fadd_rn(tail, __fmul_rn(d, d));
+            } else {
+                tail = __fadd_rn(tail, __fmul_rn(qrow[dim8 + e], vrow[dim8 + e]));
+            }
+        }
+    }
+    float score = __fadd_rn(tot, tail);
+    if (METRIC == OTTERS_METRIC_COSINE && valid) score = __fmul_rn(__fmul_rn(score, p.q_inv[qid]), p.inv_norms[row]);
+    bool ok = valid && h == 0 && !(score != score);  // NaN never returned (src/vec_compute.rs:237-239)
+    if (p.has_filter) ok = ok && score_passes(score, p.thr, p.cmp);
+    if (h == 0 && slot < p.out_slots) {
+        Cand c;
+        c.key = ok ? make_key(score, row, take_max) : 0ull;
+        c.qid = ok ? qid : 0xFFFFFFFFu;
+        c.pad = 0;
+        p.out[slot] = c;
+    }
+    // telemetry: largest |approximate - exact| over the re-scored pairs (non-negative floats order like uints)
+    float err = 0.f;
+    if (valid && h == 0 && !(score != score)) {
+        const float e = fabsf(key_score(key_a, take_max) - score);
+        if (e <= FLT_MAX) err = e;
+    }
+    const unsigned m = __ballot_sync(FULL, ok);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) err = fmaxf(err, __shfl_xor_sync(FULL, err, d));
+    if (lane == 0) {
+        if (m) atomicAdd(p.out_count, (uint32_t)__popc(m));
+        if (err > 0.f) atomicMax(p.max_err_bits, __float_as_uint(err));
+    }
+}
+
+__global__ void pad_cands_kernel(Cand* buf, uint32_t from, uint32_t to) {
+    for (uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x; i < to; i += gridDim.x * blockDim.x) {
+        Cand c;
+        c.key = 0ull;
+        c.qid = 0xFFFFFFFFu;
+        c.pad = 0;
+        buf[i] = c;
+    }
+}
+
+// largest row norm of the store: 1 / min positive inverse norm (0 when every row is zero)
+__global__ void min_inv_norm_kernel(const float* inv, uint64_t n, uint32_t* out_bits) {
+    float m = INFINITY;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float v = inv[i];
+        if (v > 0.f && v < m) m = v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMin(out_bits, __float_as_uint(m));  // positive floats order like uints
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2D fp32 tensor [rows][cols] with a row pitch of pitch_floats, boxes of box_rows x 32 columns, 128B swizzle;
+// out-of-bounds elements are filled with zeros
+int make_tensor_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_floats, uint32_t box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return fail(OTTERS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_floats * sizeof(float)};
+    cuuint32_t box[2] = {BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OTTERS_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return OTTERS_OK;
+}
+
+template <int METRIC>
+int launch_batch_one(const CUtensorMap& tv, const CUtensorMap& tqh, const CUtensorMap& tql, const BatchParams& p, uint32_t grid,
+                     uint32_t smem, uint32_t* configured, cudaStream_t s) {
+    auto kern = batch_kernel<METRIC>;
+    if (smem > configured[METRIC]) {
+        OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[METRIC] = smem;
+    }
+    kern<<<grid, NUM_THREADS, smem, s>>>(tv, tqh, tql, p);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+}  // namespace
+
+uint32_t batch_smem_bytes(uint32_t cap) { return STAGES * STAGE_BYTES + 1024 + 256 + cap * 12; }
+
+int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, cudaStream_t s) {
+    const size_t total = (size_t)nq_pad * dim_pad;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 1184);
+    split_queries_kernel<<<blocks ? blocks : 1, 256, 0, s>>>(q, nq, nq_pad, dim_pad, qh, ql);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s) {
+    CUtensorMap tv, tqh, tql;
+    int rc = make_tensor_map(&tv, l.vectors, l.n_rows, l.dim, l.pitch_g, BM);
+    if (rc) return rc;
+    rc = make_tensor_map(&tqh, l.q_hi, l.nq_pad, l.dim, l.dim_pad, BN);
+    if (rc) return rc;
+    rc = make_tensor_map(&tql, l.q_lo, l.nq_pad, l.dim, l.dim_pad, BN);
+    if (rc) return rc;
+    p.n_rowtiles = (uint32_t)((l.n_rows + BM - 1) / BM);
+    p.n_qtiles = l.nq_pad / BN;
+    p.nkb = (l.dim + BK - 1) / BK;
+    const uint32_t smem = batch_smem_bytes(p.cap);
+    switch (metric) {
+    case OTTERS_METRIC_COSINE: return launch_batch_one<OTTERS_METRIC_COSINE>(tv, tqh, tql, p, l.grid, smem, smem_configured, s);
+    case OTTERS_METRIC_EUCLIDEAN: return launch_batch_one<OTTERS_METRIC_EUCLIDEAN>(tv, tqh, tql, p, l.grid, smem, smem_configured, s);
+    case OTTERS_METRIC_DOT: return launch_batch_one<OTTERS_METRIC_DOT>(tv, tqh, tql, p, l.grid, smem, smem_configured, s);
+    }
+    return fail(OTTERS_ERR_INVALID, "Search metric is not set");
+}
+
+int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s) {
+    const uint32_t total = p.n_lists * p.k;
+    const unsigned blocks = (total + 127) / 128;
+    if (blocks) {
+        switch (metric) {
+        case OTTERS_METRIC_COSINE: rescore_kernel<OTTERS_METRIC_COSINE><<<blocks, 256, 0, s>>>(p); break;
+        case OTTERS_METRIC_EUCLIDEAN: rescore_kernel<OTTERS_METRIC_EUCLIDEAN><<<blocks, 256, 0, s>>>(p); break;
+        default: rescore_kernel<OTTERS_METRIC_DOT><<<blocks, 256, 0, s>>>(p); break;
+        }
+    }
+    if (n_sort > total) pad_cands_kernel<<<64, 256, 0, s>>>(p.out, total, n_sort);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_min_inv_norm(const float* inv, uint64_t n, uint32_t* out_bits, cudaStream_t s) {
+    OTTERS_CUDA(cudaMemsetAsync(out_bits, 0x7F, 4, s));  // 0x7F7F7F7F: a huge positive float
+    min_inv_norm_kernel<<<296, 256, 0, s>>>(inv, n, out_bits);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+}  // namespace otters

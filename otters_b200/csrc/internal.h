@@ -38,6 +38,8 @@ constexpr uint32_t kTileRows = 16;     // rows per staged tile (2 threads per ro
 constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work unit
 constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
 constexpr uint32_t kSelectSmemElems = 8192;
+constexpr uint32_t kBatchRows = 128;    // store rows per tile of the batched kernel (UMMA M)
+constexpr uint32_t kBatchQueries = 256; // queries per tile of the batched kernel (UMMA N)
 
 struct DevLeaf;
 
@@ -105,7 +107,7 @@ struct ResultHeader {
     uint32_t pad;
     unsigned long long rows_scored;
     unsigned long long stats[4];  // [0] evaluated chunks, [1] vectors_compared
-    unsigned long long pad2[2];
+    unsigned long long extra[2];  // batched path: [0] flags | max |approx - exact| bits << 32, [1] goodness of the best excluded pair
 };
 static_assert(sizeof(ResultHeader) == 64, "ResultHeader must be 64 bytes");
 
@@ -146,9 +148,65 @@ int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, 
                        cudaStream_t s);
 int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
                        uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr, const unsigned long long* rows_scored_src,
-                       const unsigned long long* stats_src, cudaStream_t s);
+                       const unsigned long long* stats_src, cudaStream_t s, const unsigned long long* extra_src = nullptr);
 int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k, ShardMap map, int take_max,
                             otters_topk_record* recs, cudaStream_t s);
+
+// ---- batched (tensor-core) path: batched.cu -------------------------------------------------------------
+struct BatchParams {
+    uint32_t n_rows, nq;
+    uint32_t n_rowtiles, n_qtiles, nkb;  // filled by launch_batch
+    const float* inv_norms;
+    const float* q_scal;         // per query: 1/|q| (cosine) or |q|^2 (euclidean); unused for dot
+    int32_t take_max;
+    int32_t has_filter;
+    float thr;
+    int32_t cmp;
+    float delta;                 // bound on |approximate - exact| score (loosens the vec_filter)
+    const uint32_t* row_mask;    // Lsb0 words, bit = 1 keep; null = all rows
+    uint32_t row_mask_words;
+    uint32_t k, cap;
+    unsigned long long* g_tau;   // grid-wide threshold key shared by the CTAs (selection speed only)
+    uint32_t* g_flags;           // bit 0: a non-finite approximate score was seen
+    uint32_t* g_excl;            // max over CTAs of the goodness (key >> 32) of the best excluded pair; 0 = none
+    unsigned long long* pairs_scored;
+    uint64_t* cta_keys;          // [grid][k] approximate keys, best first
+    uint32_t* cta_qids;          // [grid][k]
+    uint32_t* cta_counts;        // [grid]
+};
+struct BatchLaunch {
+    const float* vectors;
+    uint64_t n_rows, pitch_g;
+    uint32_t dim, dim_pad;
+    const float* q_hi;
+    const float* q_lo;
+    uint32_t nq_pad;             // multiple of kBatchQueries
+    uint32_t grid;
+};
+struct RescoreParams {
+    const float* vectors;
+    const float* inv_norms;
+    const float* queries;        // [nq][dim_pad] raw fp32
+    const float* q_inv;          // per query 1/|q| (cosine)
+    uint64_t pitch_g;
+    uint32_t dim, dim_pad;
+    const uint64_t* cta_keys;
+    const uint32_t* cta_qids;
+    const uint32_t* cta_counts;
+    uint32_t n_lists, k;
+    int32_t take_max, has_filter;
+    float thr;
+    int32_t cmp;
+    Cand* out;                   // [out_slots] exact candidates (key 0 = dropped)
+    uint32_t out_slots;
+    uint32_t* out_count;         // number of surviving candidates
+    uint32_t* max_err_bits;
+};
+uint32_t batch_smem_bytes(uint32_t cap);
+int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, cudaStream_t s);
+int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s);
+int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s);
+int launch_min_inv_norm(const float* inv, uint64_t n, uint32_t* out_bits, cudaStream_t s);
 
 // ---- store kernels ----------------------------------------------------------------------------
 int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t first, uint64_t n, float* out,

@@ -313,7 +313,8 @@ __global__ void append_prev_kernel(Cand* buf, const uint32_t* emit_count, const 
 
 __global__ void take_sorted_kernel(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k,
                                    Cand* out, uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr,
-                                   const unsigned long long* rows_scored_src, const unsigned long long* stats_src) {
+                                   const unsigned long long* rows_scored_src, const unsigned long long* stats_src,
+                                   const unsigned long long* extra_src) {
     const uint64_t total = (uint64_t)*emit_count + (prev_count ? *prev_count : 0);
     const uint64_t kk = total < k ? total : k;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,6 +328,8 @@ __global__ void take_sorted_kernel(const Cand* buf, const uint32_t* emit_count, 
             hdr->rows_scored = rows_scored_src ? *rows_scored_src : 0ull;
             hdr->stats[0] = stats_src ? stats_src[0] : 0ull;
             hdr->stats[1] = stats_src ? stats_src[1] : 0ull;
+            hdr->extra[0] = extra_src ? extra_src[0] : 0ull;
+            hdr->extra[1] = extra_src ? extra_src[1] : 0ull;
         }
     }
 }
@@ -411,8 +414,9 @@ int launch_append_prev(Cand* buf, const uint32_t* emit_count, const Cand* prev, 
 
 int launch_take_sorted(const Cand* buf, const uint32_t* emit_count, const uint32_t* prev_count, uint64_t k, Cand* out,
                        uint32_t* out_count, uint64_t* tau_out, ResultHeader* hdr, const unsigned long long* rows_scored_src,
-                       const unsigned long long* stats_src, cudaStream_t s) {
-    take_sorted_kernel<<<256, 256, 0, s>>>(buf, emit_count, prev_count, k, out, out_count, tau_out, hdr, rows_scored_src, stats_src);
+                       const unsigned long long* stats_src, cudaStream_t s, const unsigned long long* extra_src) {
+    take_sorted_kernel<<<256, 256, 0, s>>>(buf, emit_count, prev_count, k, out, out_count, tau_out, hdr, rows_scored_src, stats_src,
+                                           extra_src);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
