@@ -38,6 +38,8 @@ WORKLOADS = {
     "target": dict(rows=10_000_000, dim=768, chunk=1024, metric="Cosine", k=100, meta=True,
                    desc="MetaStore 10Mx768 fp32 Cosine top-100, chunk 1024, meta_filter price.gt & item.eq & ts.gte"),
     "c1": dict(rows=100_000, dim=128, chunk=0, metric="Cosine", k=10, meta=False, desc="VecStore 100kx128 fp32 Cosine top-10"),
+    "c2": dict(rows=1_000_000, dim=768, chunk=0, metric="DotProduct", k=100, meta=False, nq=1024,
+               desc="VecStore 1Mx768 fp32 Dot, batch of 1024 queries, top-100 (one merged list; tcgen05 3xTF32 kernel + exact re-scoring)"),
     "c3": dict(rows=10_000_000, dim=128, chunk=1024, metric="Cosine", k=100, meta=True,
                desc="MetaStore 10Mx128 Cosine top-100, chunk 1024, meta_filter price.gt & item.eq & ts.gte"),
     "c4": dict(rows=10_000_000, dim=768, chunk=0, metric="Euclidean", k=100, meta=False, desc="VecStore 10Mx768 fp32 L2 top-100"),
@@ -154,6 +156,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_peak_tflops():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, dense bf16 burst)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s dense bf16)"
+
+
 def measured_traffic(workload):
     """dram bytes per scan launch from the committed ncu capture of this workload, if one exists."""
     try:
@@ -174,13 +184,16 @@ def cpu_arm(wl, name, budget_s, steps=None, warmup=1):
     metric = getattr(ob.Metric, wl["metric"])
     tt = ob.TakeType.Min if metric == ob.Metric.Euclidean else ob.TakeType.Max
     # sample: a contiguous, chunk-aligned row range spread like the full table (same generators, same filter)
+    nq = wl.get("nq", 1)
     sample_rows = min(rows, 409_600 if dim >= 768 else 1_024_000)
     if dim >= 1536:
         sample_rows = min(rows, 204_800)
+    if nq > 1:
+        sample_rows = min(rows, max(1024, 4_194_304 // nq))  # the batch re-scores every sampled row nq times
     r0 = (rows // 2 // max(chunk, 1)) * max(chunk, 1) if wl["meta"] else 0
     r0 = min(r0, rows - sample_rows)
     vectors = ora.synth_fill(r0, sample_rows, dim, DATA_SEED)
-    queries = ora.synth_fill(0, 8, dim, QUERY_SEED)
+    queries = ora.synth_fill(0, max(8, nq), dim, QUERY_SEED)
     threads = ora.num_threads()
     if wl["meta"]:
         cols = meta_columns(ob, np.arange(r0, r0 + sample_rows), chunk)
@@ -197,7 +210,8 @@ def cpu_arm(wl, name, budget_s, steps=None, warmup=1):
         inv = ora.inv_norms(vectors)
 
         def one(i):
-            return ora.vecstore_query(vectors, queries[i % 8][None, :], metric, tt, k, None, None, ora.FAITHFUL, inv)
+            qs = queries[:nq] if nq > 1 else queries[i % 8][None, :]
+            return ora.vecstore_query(vectors, qs, metric, tt, k, None, None, ora.FAITHFUL, inv)
         cores = 1  # VecQueryPlan::collect is single-threaded (src/vec.rs:222-267)
     for i in range(warmup):
         one(i)
@@ -213,10 +227,10 @@ def cpu_arm(wl, name, budget_s, steps=None, warmup=1):
             break
         if steps is None and (time.perf_counter() - t_start > budget_s or i >= 200):
             break
-    per_query_sample = float(np.mean(times))
+    per_query_sample = float(np.mean(times)) / nq
     qps_full = 1.0 / (per_query_sample * rows / sample_rows)
     return dict(value=qps_full, unit="queries/s", cores=cores, kind="port",
-                sample=f"{len(times)} queries over rows [{r0},{r0 + sample_rows}) of {rows} ({sample_rows} rows, same generators/filter), "
+                sample=f"{len(times)} {'batches of %d queries' % nq if nq > 1 else 'queries'} over rows [{r0},{r0 + sample_rows}) of {rows} ({sample_rows} rows, same generators/filter), "
                        f"time scaled x{rows / sample_rows:.2f}; oracle = C port of the reference CPU path (no Rust toolchain here), "
                        f"gcc -O3 -mavx2 -ffp-contract=off, {cores} thread(s) of {threads}",
                 ms_per_query_sample=per_query_sample * 1e3, n=len(times))
@@ -228,7 +242,7 @@ def run_reference(args, wl):
         return
     t0 = time.perf_counter()
     res = cpu_arm(wl, args.workload, budget_s=60.0, steps=args.steps, warmup=max(args.warmup, 1))
-    ms = 1e3 / res["value"]
+    ms = 1e3 / res["value"] * wl.get("nq", 1)
     line = {
         "impl": "reference", "metric": "queries_per_sec", "value": res["value"], "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -292,14 +306,15 @@ def run_ours(args, wl):
         store.add_synthetic_sharded(world, rank, block, n_local, DATA_SEED)
     build_s = time.perf_counter() - t_build
 
-    nqv = 16
+    nq = wl.get("nq", 1)
+    nqv = 16 if nq == 1 else 2 * nq
     queries = synth_fill_np(0, nqv, dim, QUERY_SEED)
 
     def make_vq(i):
         vq = _ffi.VecQuery()
-        q = queries[i % nqv]
+        q = queries[i % nqv] if nq == 1 else queries[(i % 2) * nq:(i % 2 + 1) * nq]
         vq.queries = q.ctypes.data_as(_ffi.c_f32p)
-        vq.nq, vq.dim, vq.metric, vq.take_type, vq.k = 1, dim, int(metric), int(tt), k
+        vq.nq, vq.dim, vq.metric, vq.take_type, vq.k = nq, dim, int(metric), int(tt), k
         if vf:
             vq.has_filter, vq.thr, vq.cmp = 1, vf[0], int(vf[1])
         return vq
@@ -357,6 +372,7 @@ def run_ours(args, wl):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, scan_bytes, meta_bytes, rows_scored, launches = [], [], [], [], 0
+    batch_info = []
     t0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
@@ -368,6 +384,8 @@ def run_ours(args, wl):
         meta_bytes.append(w["meta_bytes"])
         rows_scored.append(w["rows_scored"])
         launches += int(w["kernel_launches"])
+        if nq > 1:
+            batch_info.append((w["batch_used"], w["batch_fallback"], w["batch_max_err"], w["batch_delta"], w["select_ms"]))
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
@@ -411,27 +429,44 @@ def run_ours(args, wl):
         if world == 1 and not args.no_cpu:
             c = cpu_arm(wl, args.workload, budget_s=args.cpu_budget)
             cpu = {kk: c[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-        h2d = dim * 4  # the query vector
+        h2d = nq * dim * 4  # the query vector(s)
         if fp is not None:
             h2d += 3 * 64 + 16  # three lowered leaves + clause offsets
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                "traffic": measured_traffic(args.workload), "peak_source": peak_src, "kernel": "scan_kernel (K1)",
+                "scan_ms": float(np.mean(scan_ms)) if scan_ms else None,
+                "algorithmic_bytes_per_launch": float(np.mean(scan_bytes)) if scan_bytes else None}
+        if nq > 1:
+            # tensor-bound: algorithmic flops = 2 * pairs * dim, counted ONCE (the 3xTF32 split issues 3x that on the pipe)
+            tpeak, tsrc = measured_peak_tflops()
+            flops = 2.0 * float(np.mean(rows_scored)) * dim
+            tach = flops / (float(np.mean(scan_ms)) * 1e-3) / 1e12 if scan_ms else 0.0
+            bi = np.array(batch_info, dtype=np.float64)
+            roof = {"bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak if tpeak else None,
+                    "traffic": measured_traffic(args.workload), "peak_source": tsrc, "kernel": "batch_kernel (K2, tcgen05 kind::tf32 x3)",
+                    "scan_ms": float(np.mean(scan_ms)) if scan_ms else None, "algorithmic_flops_per_launch": flops,
+                    "note": "peak is the measured dense bf16 rate; kind::tf32 runs at half of it and the fp32-faithful 3xTF32 split "
+                            "issues 3 MMAs per product, so 1/6 of the peak is the ceiling of this formulation",
+                    "tensor_path_used": float(bi[:, 0].mean()), "fallbacks": float(bi[:, 1].sum()),
+                    "max_abs_err_vs_exact": float(bi[:, 2].max()), "assumed_err_bound": float(bi[:, 3].max()),
+                    "rescore_sort_ms": float(bi[:, 4].mean())}
         line = {
-            "metric": "queries_per_sec", "value": 1e3 / dev_ms, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "metric": "queries_per_sec", "value": nq * 1e3 / dev_ms, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload}: {wl['desc']}", "rows": rows, "dim": dim, "k": k, "chunk_size": chunk,
                 "filter": expr_desc, "rows_scored_per_query": rows_scored_total,
                 "parallelism": f"rows block-cyclic ({block}-row blocks) over {world} GPU(s)" + (" + NCCL all-gather of k records + device merge" if world > 1 else ""),
-                "l2": "no flush needed: every query streams >= GBs of distinct rows, far larger than the 126 MB L2",
+                "l2": ("no flush needed: every step streams %.2f GB of distinct rows, far larger than the 126 MB L2" % (rows_scored_total / max(nq, 1) * dim * 4 / 1e9)
+                       if rows_scored_total / max(nq, 1) * dim * 4 > 4 * 126e6 else
+                       "NOT flushed: the %.0f MB store is L2-resident between steps (latency-bound case; the HBM roofline does not apply)" % (rows * dim * 4 / 1e6)),
                 "store_build_s": build_s,
             },
-            "e2e": {"value": 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * 16 + 48),
+            "e2e": {"value": nq * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * 16 + 48),
                     "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
-                         "traffic": measured_traffic(args.workload), "peak_source": peak_src, "kernel": "scan_kernel (K1)",
-                         "scan_ms": float(np.mean(scan_ms)) if scan_ms else None,
-                         "algorithmic_bytes_per_launch": float(np.mean(scan_bytes)) if scan_bytes else None},
+            "roofline": roof,
             "rows_scored_per_sec": rows_scored_total * 1e3 / dev_ms,
             "vectors_compared_per_sec": (float(tot[1].item()) * 1e3 / dev_ms) if wl["meta"] else rows_scored_total * 1e3 / dev_ms,
             "cpu_baseline": cpu,

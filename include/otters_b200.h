@@ -94,6 +94,7 @@ typedef struct {
     uint32_t unit_rows;    /* 32, 64 or 128 rows per dynamically scheduled work unit */
     uint32_t disable_fused_predicate; /* 1: evaluate the row predicate in its own kernel instead of inside the scan */
     uint32_t batch_mode;   /* query batches: 0 = automatic, 1 = always the tensor-core kernel (when k <= 1024), 2 = never */
+    uint32_t batch_cta_group; /* tensor-core kernel: 0 = automatic (CTA pairs, tcgen05 cta_group::2), 1 = single CTAs, 2 = pairs */
 } otters_scan_tuning;
 OTTERS_API int otters_ctx_set_tuning(otters_ctx *ctx, const otters_scan_tuning *t);
 

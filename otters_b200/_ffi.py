@@ -35,6 +35,7 @@ class ScanTuning(C.Structure):
         ("unit_rows", C.c_uint32),
         ("disable_fused_predicate", C.c_uint32),
         ("batch_mode", C.c_uint32),
+        ("batch_cta_group", C.c_uint32),
     ]
 
 

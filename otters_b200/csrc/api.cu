@@ -3,6 +3,7 @@
 // / meta.cu / store.cu; there is no CPU fallback.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -85,7 +86,7 @@ struct otters_ctx {
     size_t d_qscal_floats = 0;
     uint32_t* d_cta_qids = nullptr;     // [grid_max][kMaxFusedK]
     unsigned long long* d_batch_info = nullptr;  // d_ctrl + 64: [0] shared threshold key, [1] flags | max error bits << 32, [2] best excluded
-    uint32_t batch_smem_configured[3] = {0, 0, 0};
+    uint32_t batch_smem_configured[6] = {0, 0, 0, 0, 0, 0};
 
     // pinned staging: queries / masks, lowered filters, results
     uint8_t* h_stage = nullptr;
@@ -212,7 +213,8 @@ struct VecStorage {
     uint64_t n = 0, cap = 0;
     float* d_rows = nullptr;
     float* d_inv = nullptr;
-    float max_norm = -1.f;  // largest row norm (lazily computed for the batched path's error bound); < 0 = unknown
+    uint32_t* d_minv_bits = nullptr;  // smallest positive inverse row norm (float bits), for the batched path's error bound
+    bool minv_valid = false;
 
     int reserve(uint64_t want) {
         if (want <= cap) return OTTERS_OK;
@@ -253,7 +255,7 @@ struct VecStorage {
         if (rc) return rc;
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be reused after return
         n += cnt;
-        max_norm = -1.f;
+        minv_valid = false;
         return OTTERS_OK;
     }
     int add_synth(ShardMap gen_map, uint64_t cnt, uint64_t seed) {
@@ -267,13 +269,16 @@ struct VecStorage {
         if (rc) return rc;
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
         n += cnt;
-        max_norm = -1.f;
+        minv_valid = false;
         return OTTERS_OK;
     }
     void release() {
         cudaFree(d_rows);
         cudaFree(d_inv);
+        cudaFree(d_minv_bits);
         d_rows = d_inv = nullptr;
+        d_minv_bits = nullptr;
+        minv_valid = false;
         n = cap = 0;
     }
 };
@@ -379,11 +384,11 @@ struct QueryRun {
 };
 
 static float host_inv_norm(const float* v, uint32_t dim) {
-    // src/vec.rs:390-397: serial f32 sum of squares, sqrt, reciprocal (0 for a zero vector).
-    // volatile keeps the compiler from contracting or reassociating.
-    volatile float s = -0.0f;
+    // src/vec.rs:390-397: serial f32 sum of squares, sqrt, reciprocal (0 for a zero vector).  The host code is
+    // built with -ffp-contract=off and without fast-math, so the loop is neither contracted nor reassociated.
+    float s = -0.0f;
     for (uint32_t i = 0; i < dim; ++i) {
-        volatile float p = v[i] * v[i];
+        const float p = v[i] * v[i];
         s = s + p;
     }
     float norm = sqrtf(s);
@@ -396,25 +401,13 @@ static float host_inv_norm(const float* v, uint32_t dim) {
 // reference's exact arithmetic and the result is accepted only if no excluded pair can reach it:
 //   (approximate cut score) +- delta must lie strictly outside the exact k-th score,
 // with delta a bound on |tensor-core score - exact score|.  Otherwise the caller falls back to K1 per query.
-static double host_norm(const float* v, uint32_t dim) {
-    double s = 0.0;
-    for (uint32_t i = 0; i < dim; ++i) s += (double)v[i] * (double)v[i];
-    return sqrt(s);
-}
-
-static int store_max_norm(otters_ctx* c, VecStorage* st, float* out) {
-    if (st->max_norm < 0.f) {
-        uint32_t* d_bits = reinterpret_cast<uint32_t*>(c->d_ctrl + 192);
-        int rc = launch_min_inv_norm(st->d_inv, st->n, d_bits, c->stream);
-        if (rc) return rc;
-        uint32_t bits = 0;
-        OTTERS_CUDA(cudaMemcpyAsync(&bits, d_bits, 4, cudaMemcpyDeviceToHost, c->stream));
-        OTTERS_CUDA(cudaStreamSynchronize(c->stream));
-        float mn;
-        memcpy(&mn, &bits, 4);
-        st->max_norm = (mn > 0.f && mn < 1e30f) ? 1.0f / mn : 0.f;
-    }
-    *out = st->max_norm;
+static int store_min_inv_norm(otters_ctx* c, VecStorage* st) {
+    if (st->minv_valid) return OTTERS_OK;
+    if (!st->d_minv_bits && cudaMalloc((void**)&st->d_minv_bits, 16) != cudaSuccess)
+        return fail(OTTERS_ERR_NOMEM, "device allocation failed");
+    int rc = launch_min_inv_norm(st->d_inv, st->n, st->d_minv_bits, c->stream);
+    if (rc) return rc;
+    st->minv_valid = true;
     return OTTERS_OK;
 }
 
@@ -428,7 +421,7 @@ static bool batch_eligible(const otters_ctx* c, const otters_vec_query* q, uint6
     return q->nq >= 8 && n_rows >= 4096;
 }
 
-static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q, const std::vector<float>& q_inv,
+static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
                        const uint32_t* d_row_mask, uint32_t row_mask_words, otters_topk_record* d_records_out, ShardMap map,
                        const unsigned long long* stats_src, QueryRun* run, bool* accepted) {
     *accepted = false;
@@ -440,44 +433,35 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     const uint32_t nq_pad = (uint32_t)round_up(q->nq, kBatchQueries);
     const bool take_max = q->take_type == OTTERS_TAKE_MAX;
 
-    // error bound of the tensor-core scores
-    double qmax = 0.0;
-    for (uint32_t i = 0; i < q->nq; ++i) qmax = std::max(qmax, host_norm(q->queries + (size_t)i * q->dim, q->dim));
-    const double kappa = ldexp(1.0, -15) * std::max(1.0, (double)st->dim / 1024.0);
-    float delta;
-    if (q->metric == OTTERS_METRIC_COSINE) {
-        delta = (float)(kappa * 1.01);
-    } else {
-        float vmax = 0.f;
-        int rc0 = store_max_norm(c, st, &vmax);
-        if (rc0) return rc0;
-        delta = (float)(q->metric == OTTERS_METRIC_DOT ? kappa * 1.01 * qmax * vmax : kappa * 1.01 * (qmax + vmax) * (qmax + vmax));
-    }
-    if (!(delta <= FLT_MAX)) return OTTERS_OK;  // non-finite inputs: exact path
-
-    // per-query scalars: 1/|q| (cosine, the reference's value) or |q|^2 (euclidean)
-    int rc = ensure_dev(&c->d_qscal, &c->d_qscal_floats, (size_t)q->nq, s);
+    // per-query scalars on the device: 1/|q| exactly as the reference computes it (cosine; also used by the exact
+    // re-scoring) and |q|^2 (euclidean); the batch's error bound follows from the largest norms
+    int rc = ensure_dev(&c->d_qscal, &c->d_qscal_floats, (size_t)q->nq * 2, s);
     if (rc) return rc;
     rc = ensure_dev(&c->d_qh, &c->d_qh_floats, (size_t)nq_pad * dim_pad, s);
     if (rc) return rc;
     rc = ensure_dev(&c->d_ql, &c->d_ql_floats, (size_t)nq_pad * dim_pad, s);
     if (rc) return rc;
-    float* hs = reinterpret_cast<float*>(c->h_stage) + (size_t)q->nq * dim_pad;  // after the staged queries
-    for (uint32_t i = 0; i < q->nq; ++i) {
-        if (q->metric == OTTERS_METRIC_EUCLIDEAN) {
-            const double n = host_norm(q->queries + (size_t)i * q->dim, q->dim);
-            hs[i] = (float)(n * n);
-        } else {
-            hs[i] = q_inv[i];
-        }
+    float* d_qinv = c->d_qscal;
+    float* d_qn2 = c->d_qscal + q->nq;
+    uint32_t* d_excl = reinterpret_cast<uint32_t*>(c->d_ctrl + 80);
+    float* d_delta = reinterpret_cast<float*>(c->d_ctrl + 84);
+    uint32_t* d_qmax2 = reinterpret_cast<uint32_t*>(c->d_ctrl + 88);
+    if (q->metric == OTTERS_METRIC_COSINE) {
+        rc = launch_inv_norms(c->d_query, dim_pad, st->dim, 0, q->nq, d_qinv, s);
+        if (rc) return rc;
+    } else {
+        rc = store_min_inv_norm(c, st);
+        if (rc) return rc;
     }
-    OTTERS_CUDA(cudaMemcpyAsync(c->d_qscal, hs, (size_t)q->nq * 4, cudaMemcpyHostToDevice, s));
-    OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
-    c->stage_pending = true;
-    rc = launch_split_queries(c->d_query, q->nq, nq_pad, dim_pad, c->d_qh, c->d_ql, s);
+    rc = launch_split_queries(c->d_query, q->nq, nq_pad, dim_pad, c->d_qh, c->d_ql, d_qn2, d_qmax2, s);
+    if (rc) return rc;
+    rc = launch_batch_delta(q->metric, st->dim, d_qmax2, st->d_minv_bits, d_delta, s);
     if (rc) return rc;
 
-    const uint32_t n_rowtiles = (uint32_t)((st->n + kBatchRows - 1) / kBatchRows);
+    // CTA pairs (cta_group::2) unless the tuning asks for single CTAs or there is too little work to pair up
+    const uint32_t cg = (c->tuning.batch_cta_group == 1 || c->sm_count < 2) ? 1 : 2;
+    const uint32_t tile_rows = kBatchRows * cg;
+    const uint32_t n_rowtiles = (uint32_t)((st->n + tile_rows - 1) / tile_rows);
     const uint64_t n_tiles = (uint64_t)n_rowtiles * (nq_pad / kBatchQueries);
     BatchLaunch bl{};
     bl.vectors = st->d_rows;
@@ -488,28 +472,30 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bl.q_hi = c->d_qh;
     bl.q_lo = c->d_ql;
     bl.nq_pad = nq_pad;
-    bl.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count, n_tiles);
+    bl.cta_group = cg;
+    bl.grid = (uint32_t)std::min<uint64_t>((uint64_t)(c->sm_count / cg), n_tiles) * cg;
     BatchParams bp{};
     bp.n_rows = (uint32_t)st->n;
     bp.nq = q->nq;
     bp.inv_norms = st->d_inv;
-    bp.q_scal = c->d_qscal;
+    bp.q_scal = q->metric == OTTERS_METRIC_COSINE ? d_qinv : d_qn2;
     bp.take_max = take_max;
     bp.has_filter = q->has_filter;
     bp.thr = q->thr;
     bp.cmp = q->cmp;
-    bp.delta = delta;
+    bp.delta = d_delta;
     bp.row_mask = d_row_mask;
     bp.row_mask_words = row_mask_words;
     bp.k = k;
     bp.cap = cap;
     bp.g_tau = c->d_batch_info;
     bp.g_flags = reinterpret_cast<uint32_t*>(c->d_batch_info + 1);
-    bp.g_excl = reinterpret_cast<uint32_t*>(c->d_batch_info + 2);
+    bp.g_excl = d_excl;
     bp.pairs_scored = c->d_rows_scored;
     bp.cta_keys = c->d_cta_keys;
     bp.cta_qids = c->d_cta_qids;
     bp.cta_counts = c->d_cta_counts;
+    if (const char* e = getenv("OTTERS_BATCH_DBG")) bp.dbg = (uint32_t)atoi(e);  // timing experiments; results are garbage
     cudaEventRecord(c->ev[2], s);
     cudaEventRecord(c->ev[3], s);
     rc = launch_batch(bl, bp, q->metric, c->batch_smem_configured, s);
@@ -535,7 +521,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     rp.vectors = st->d_rows;
     rp.inv_norms = st->d_inv;
     rp.queries = c->d_query;
-    rp.q_inv = c->d_qscal;
+    rp.q_inv = d_qinv;
     rp.pitch_g = st->pitch;
     rp.dim = st->dim;
     rp.dim_pad = dim_pad;
@@ -564,7 +550,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         if (rc) return rc;
     }
     cudaEventRecord(c->ev[5], s);
-    c->last.kernel_launches += 6 + (d_records_out ? 1 : 0);
+    c->last.kernel_launches += 8 + (d_records_out ? 1 : 0);
 
     // fetch header + candidates and verify the selection
     const size_t bytes = sizeof(ResultHeader) + (size_t)k_eff * sizeof(Cand);
@@ -578,9 +564,11 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     const uint32_t flags = (uint32_t)hdr->extra[0];
     const uint32_t err_bits = (uint32_t)(hdr->extra[0] >> 32);
     const uint32_t excl = (uint32_t)hdr->extra[1];
-    float max_err;
+    const uint32_t delta_bits = (uint32_t)(hdr->extra[1] >> 32);
+    float max_err, delta;
     memcpy(&max_err, &err_bits, 4);
-    bool ok = (flags & 1u) == 0 && max_err <= delta;
+    memcpy(&delta, &delta_bits, 4);
+    bool ok = (flags & 1u) == 0 && delta <= FLT_MAX && max_err <= delta;
     if (ok && excl != 0) {
         // some pair was left out of the candidate lists: its exact score is within delta of its tensor-core
         // score, so it cannot belong to the result iff even that bound stays strictly outside the k-th score
@@ -625,13 +613,14 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (rc) return rc;
     rc = ensure_dev(&c->d_query, &c->d_query_floats, qfloats, s);
     if (rc) return rc;
-    std::vector<float> q_inv(q->nq);
     float* hq = reinterpret_cast<float*>(c->h_stage);
-    for (uint32_t i = 0; i < q->nq; ++i) {
-        const float* src = q->queries + (size_t)i * q->dim;
-        memcpy(hq + (size_t)i * dim_pad, src, (size_t)q->dim * 4);
-        for (uint32_t j = q->dim; j < dim_pad; ++j) hq[(size_t)i * dim_pad + j] = 0.f;
-        q_inv[i] = host_inv_norm(src, q->dim);
+    if (dim_pad == q->dim) {
+        memcpy(hq, q->queries, qfloats * 4);
+    } else {
+        for (uint32_t i = 0; i < q->nq; ++i) {
+            memcpy(hq + (size_t)i * dim_pad, q->queries + (size_t)i * q->dim, (size_t)q->dim * 4);
+            for (uint32_t j = q->dim; j < dim_pad; ++j) hq[(size_t)i * dim_pad + j] = 0.f;
+        }
     }
     OTTERS_CUDA(cudaMemcpyAsync(c->d_query, hq, qfloats * 4, cudaMemcpyHostToDevice, s));
     OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
@@ -639,12 +628,16 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
 
     if (batch_eligible(c, q, n_rows, k_eff)) {
         bool accepted = false;
-        rc = run_batched(c, st, q, q_inv, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, &accepted);
+        rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, &accepted);
         if (rc) return rc;
         if (accepted) return OTTERS_OK;
         rc = reset_scan_state(c);  // selection could not be verified: exact path, query by query
         if (rc) return rc;
     }
+
+    // per-query inverse norms for the streaming kernel (a by-value kernel parameter)
+    std::vector<float> q_inv(q->nq);
+    for (uint32_t i = 0; i < q->nq; ++i) q_inv[i] = host_inv_norm(q->queries + (size_t)i * q->dim, q->dim);
 
     const bool fused = k_eff <= kMaxFusedK;
     ScanPlan pl;

@@ -34,10 +34,7 @@ constexpr uint32_t BM = kBatchRows;     // 128 store rows per tile
 constexpr uint32_t BN = kBatchQueries;  // 256 queries per tile
 constexpr uint32_t BK = 32;             // fp32 columns per k-block (128 bytes)
 constexpr uint32_t UK = 8;              // K of one tcgen05.mma kind::tf32
-constexpr uint32_t STAGES = 2;
-constexpr uint32_t A_BYTES = BM * BK * 4;  // 16 KB
-constexpr uint32_t B_BYTES = BN * BK * 4;  // 32 KB
-constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // Vhi | Vlo | Qhi | Qlo = 96 KB
+constexpr uint32_t A_BYTES = BM * BK * 4;  // 16 KB: the V tile of one CTA and one k-block
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t NUM_THREADS = 384;
 
@@ -106,9 +103,8 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor, kind::tf32: [4,6) D format = 1 (f32) | [7,10) A format = 2 (tf32) | [10,13) B format = 2 |
-// [15] A major = 0 (K) | [16] B major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+// Instruction descriptor, kind::tf32 (Geo<CG>::IDESC): [4,6) D format = 1 (f32) | [7,10) A format = 2 (tf32) |
+// [10,13) B format = 2 | [15] A major = 0 (K) | [16] B major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
 
 struct CtaHdr {
     unsigned long long tau;  // candidates must have key > tau
@@ -159,7 +155,7 @@ __device__ void warp_sort_pairs(uint64_t* keys, uint32_t* qids, uint32_t cnt, ui
 // Lock-free append (same protocol as K1's warp_push, scan.cu) with a query-id payload.  After a compaction
 // the CTA's new threshold is published to the grid-wide threshold (any key below some CTA's k-th best key
 // cannot be among the global best k), and the grid-wide value is adopted when it is higher.
-__device__ void warp_push_pairs(CtaHdr* hdr, uint64_t* keys, uint32_t* qids, uint32_t cap, uint32_t k, bool has, uint64_t key,
+__device__ __noinline__ void warp_push_pairs(CtaHdr* hdr, uint64_t* keys, uint32_t* qids, uint32_t cap, uint32_t k, bool has, uint64_t key,
                                 uint32_t qid, unsigned long long* g_tau, int lane) {
     for (;;) {
         const uint64_t tau = ld_volatile_u64(&hdr->tau);
@@ -234,35 +230,146 @@ __device__ __forceinline__ bool score_passes_loose(float s, float thr, int cmp, 
     }
 }
 
+// metric epilogue on a tensor-core dot product a = <v, q>
+template <int METRIC>
+__device__ __forceinline__ float batch_score(float a, const float* q_scal, uint32_t qi, float rs) {
+    if (METRIC == OTTERS_METRIC_COSINE) return a * __ldg(q_scal + qi) * rs;          // rs = 1/|v|, q_scal = 1/|q|
+    if (METRIC == OTTERS_METRIC_EUCLIDEAN) return (__ldg(q_scal + qi) + rs) - 2.0f * a;  // rs = |v|^2, q_scal = |q|^2
+    return a;
+}
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return r;
+}
+
+// Per-configuration geometry.  CG = 1: one CTA per tile of 128 rows x 256 queries.  CG = 2: a CTA pair
+// (cluster of two, tcgen05 cta_group::2) per tile of 256 rows x 256 queries; each CTA stages its own 128 rows
+// and HALF of the query tile, so its stage shrinks to 64 KB (3 stages instead of 2) and the shared-memory
+// operand traffic per MMA halves.
+template <int CG>
+struct Geo {
+    static constexpr uint32_t BN_LOAD = BN / CG;              // query rows staged per CTA
+    static constexpr uint32_t B_BYTES = BN_LOAD * BK * 4;     // 32 KB / 16 KB
+    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // Vhi | Vlo | Qhi | Qlo
+    static constexpr uint32_t STAGES = CG == 2 ? 3 : 2;
+    static constexpr uint32_t TILE_ROWS = BM * CG;
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same barrier of CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if ((++spins & 0x3FFFu) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// CG = 2: the arrival is multicast to the same barrier of both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+    if constexpr (CG == 1) {
+        umma_commit(bar);
+    } else {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"(mask)
+                     : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst_smem, uint32_t ncols) {
+    if constexpr (CG == 1) {
+        tmem_alloc(dst_smem, ncols);
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+    if constexpr (CG == 1) tmem_dealloc(taddr, ncols);
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // tile t -> (row tile, query tile): consecutive tiles share the row tile so that the CTAs working on it at the
-// same time find the V tile in L2 after the first HBM read
+// same time find the V tile in L2 after the first HBM read.  A row tile whose rows are all masked is skipped
+// by every warp role (the test reads the same mask words everywhere).
+template <int CG>
 __device__ __forceinline__ bool tile_live(const BatchParams& p, uint32_t rt) {
     if (!p.row_mask) return true;
-    const uint32_t w0 = rt * (BM / 32);
+    const uint32_t w0 = rt * (Geo<CG>::TILE_ROWS / 32);
     uint32_t any = 0;
 #pragma unroll
-    for (uint32_t i = 0; i < BM / 32; ++i) any |= (w0 + i) < p.row_mask_words ? __ldg(p.row_mask + w0 + i) : 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < Geo<CG>::TILE_ROWS / 32; ++i) any |= (w0 + i) < p.row_mask_words ? __ldg(p.row_mask + w0 + i) : 0xFFFFFFFFu;
     return any != 0;
 }
 
-template <int METRIC>
+template <int METRIC, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qh,
              const __grid_constant__ CUtensorMap tm_ql, const __grid_constant__ BatchParams p) {
+    using G = Geo<CG>;
+    constexpr uint32_t STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES, B_BYTES = G::B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // position in the CTA pair; rank 0 issues the MMAs
+    const uint32_t unit = blockIdx.x / CG, n_units = gridDim.x / CG;
 
-    // the operand tiles need 1024-byte alignment (128B swizzle atoms)
+    // the operand tiles need 1024-byte alignment (128B swizzle atoms); both CTAs of a pair compute the same offsets
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* aux = smem + STAGES * STAGE_BYTES;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);       // [STAGES] TMA landed
-    uint64_t* bar_cast = bar_full + STAGES;                       // [STAGES] V split into hi/lo
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);       // [STAGES] this CTA's TMA loads landed
+    uint64_t* bar_cast = bar_full + STAGES;                       // [STAGES] (rank 0) V split into hi/lo in every CTA of the pair
     uint64_t* bar_empty = bar_cast + STAGES;                      // [STAGES] MMAs reading the stage completed
     uint64_t* bar_tfull = bar_empty + STAGES;                     // [2] accumulator complete
-    uint64_t* bar_tempty = bar_tfull + 2;                         // [2] accumulator drained by the epilogue
+    uint64_t* bar_tempty = bar_tfull + 2;                         // [2] (rank 0) accumulator drained by every epilogue thread
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
     CtaHdr* hdr = reinterpret_cast<CtaHdr*>(aux + 128);
     uint64_t* cand_keys = reinterpret_cast<uint64_t*>(aux + 256);
@@ -276,12 +383,12 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     if (warp == 1 && lane == 0) {
         for (uint32_t s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_cast[s], 128);
+            mbar_init(&bar_cast[s], 128 * CG);
             mbar_init(&bar_empty[s], 1);
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(&bar_tfull[b], 1);
-            mbar_init(&bar_tempty[b], 128);
+            mbar_init(&bar_tempty[b], 128 * CG);
         }
         fence_mbar_init();
         hdr->tau = 0ull;
@@ -289,62 +396,74 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         hdr->written = 0;
         hdr->excl = 0;
     }
-    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    if constexpr (CG == 2) {
+        __syncthreads();
+        cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+    }
+    if (warp == 2) tmem_alloc_cg<CG>(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // both halves of the pair's tensor memory are allocated
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const uint32_t n_tiles = p.n_rowtiles * p.n_qtiles;
+    const uint32_t n_rowtiles = (p.n_rows + G::TILE_ROWS - 1) / G::TILE_ROWS;
+    const uint32_t n_tiles = n_rowtiles * p.n_qtiles;
     const uint32_t nkb = p.nkb;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA stages its own rows and its share of the query tile) =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (uint32_t t = unit; t < n_tiles; t += n_units) {
                 const uint32_t rt = t / p.n_qtiles, qt = t % p.n_qtiles;
-                if (!tile_live(p, rt)) continue;
+                if (!tile_live<CG>(p, rt)) continue;
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u);
                     uint8_t* st = smem + s * STAGE_BYTES;
+                    if (p.dbg & 1u) {  // timing experiment: no loads
+                        mbar_arrive_expect_tx(&bar_full[s], 0);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&bar_full[s], A_BYTES + 2 * B_BYTES);
-                    tma_load_2d(st, &tm_v, (int)(kb * BK), (int)(rt * BM), &bar_full[s]);
-                    tma_load_2d(st + 2 * A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN), &bar_full[s]);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN), &bar_full[s]);
+                    tma_load_2d(st, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full[s]);
+                    tma_load_2d(st + 2 * A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer (one thread of rank 0) =====
+        if (lane == 0 && rank == 0) {
             uint32_t it = 0, tn = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (uint32_t t = unit; t < n_tiles; t += n_units) {
                 const uint32_t rt = t / p.n_qtiles;
-                if (!tile_live(p, rt)) continue;
+                if (!tile_live<CG>(p, rt)) continue;
                 const uint32_t buf = tn & 1u, bph = (tn >> 1) & 1u;
-                mbar_wait(&bar_tempty[buf], bph ^ 1u);
+                if constexpr (CG == 2) mbar_wait_cluster(&bar_tempty[buf], bph ^ 1u);
+                else mbar_wait(&bar_tempty[buf], bph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&bar_full[s], ph);
-                    mbar_wait(&bar_cast[s], ph);
+                    if constexpr (CG == 2) mbar_wait_cluster(&bar_cast[s], ph);
+                    else mbar_wait(&bar_cast[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t d_vh = umma_desc_sw128(sa), d_vl = umma_desc_sw128(sa + A_BYTES);
                     const uint64_t d_qh = umma_desc_sw128(sa + 2 * A_BYTES), d_ql = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                    for (uint32_t kk = 0; kk < BK / UK; ++kk) {
+                    for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
                         const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);  // K advance inside the swizzle atom
-                        umma_tf32(d_tmem, d_vl + adv, d_qh + adv, kInstrDesc, (kb | kk) != 0 ? 1u : 0u);
-                        umma_tf32(d_tmem, d_vh + adv, d_ql + adv, kInstrDesc, 1u);
-                        umma_tf32(d_tmem, d_vh + adv, d_qh + adv, kInstrDesc, 1u);
+                        umma_tf32_cg<CG>(d_tmem, d_vl + adv, d_qh + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
+                        umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_ql + adv, G::IDESC, 1u);
+                        umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, 1u);
                     }
-                    umma_commit(&bar_empty[s]);
+                    umma_commit_cg<CG>(&bar_empty[s]);
                 }
-                umma_commit(&bar_tfull[buf]);
+                umma_commit_cg<CG>(&bar_tfull[buf]);
                 ++tn;
             }
         }
@@ -352,16 +471,16 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         // ===== split warps: V tile -> hi (in place) and lo =====
         const int tt = tid - 128;
         uint32_t it = 0;
-        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (uint32_t t = unit; t < n_tiles; t += n_units) {
             const uint32_t rt = t / p.n_qtiles;
-            if (!tile_live(p, rt)) continue;
+            if (!tile_live<CG>(p, rt)) continue;
             for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                 mbar_wait(&bar_full[s], ph);
                 float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
                 float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
 #pragma unroll
-                for (uint32_t i = 0; i < A_BYTES / 16 / 128; ++i) {
+                for (uint32_t i = 0; i < ((p.dbg & 2u) ? 0u : A_BYTES / 16 / 128); ++i) {
                     const uint32_t idx = tt + i * 128;
                     const float4 x = hi[idx];
                     float4 h, l;
@@ -377,7 +496,8 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                     lo[idx] = l;
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                mbar_arrive(&bar_cast[s]);
+                if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_cast[s], 0);
+                else mbar_arrive(&bar_cast[s]);
             }
         }
     } else if (warp >= 8) {
@@ -388,12 +508,13 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         uint32_t tn = 0;
         bool nonfinite = false;
         const float sgn = take_max ? 1.0f : -1.0f;
+        const float delta = p.has_filter ? __ldg(p.delta) : 0.f;
         float xbest = -INFINITY;  // best signed score among the pairs this thread excluded by the top-k test
-        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (uint32_t t = unit; t < n_tiles; t += n_units) {
             const uint32_t rt = t / p.n_qtiles, qt = t % p.n_qtiles;
-            if (!tile_live(p, rt)) continue;
+            if (!tile_live<CG>(p, rt)) continue;
             const uint32_t buf = tn & 1u, bph = (tn >> 1) & 1u;
-            const uint32_t row = rt * BM + quarter * 32 + lane;
+            const uint32_t row = rt * G::TILE_ROWS + rank * BM + quarter * 32 + lane;
             bool live = row < p.n_rows;
             if (live && p.row_mask) {
                 const uint32_t w = (row >> 5) < p.row_mask_words ? __ldg(p.row_mask + (row >> 5)) : 0xFFFFFFFFu;
@@ -411,34 +532,39 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN;
             for (uint32_t c = 0; c < BN / 32; ++c) {
-                if (c * 32 >= nq_tile) break;  // warp-uniform
+                if (c * 32 >= nq_tile || (p.dbg & 4u)) break;  // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
                 tmem_ld_wait();
                 // threshold of this chunk as a float pre-test (the exact key test is inside the push)
                 const uint64_t tau = ld_volatile_u64(&hdr->tau);
                 const float tau_s = tau ? key_score(tau, take_max) : (take_max ? -INFINITY : INFINITY);
+                // fast path: straight-line scoring of the 32 columns, one bit per passing column
+                uint32_t pass = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) {
-                    const uint32_t qi = q_base + c * 32 + j;
-                    const bool inq = c * 32 + j < nq_tile;
-                    const float a = __uint_as_float(v[j]);
-                    float s;
-                    if (METRIC == OTTERS_METRIC_COSINE) s = a * __ldg(p.q_scal + (inq ? qi : 0)) * rs;
-                    else if (METRIC == OTTERS_METRIC_EUCLIDEAN) s = (__ldg(p.q_scal + (inq ? qi : 0)) + rs) - 2.0f * a;
-                    else s = a;
-                    bool ok = live && inq;
+                    const float s = batch_score<METRIC>(__uint_as_float(v[j]), p.q_scal, q_base + c * 32 + j, rs);
+                    bool ok = live && (c * 32 + j < nq_tile);
                     if (ok && !(fabsf(s) <= FLT_MAX)) nonfinite = true;  // inf / NaN: let the exact path decide
-                    if (p.has_filter) ok = ok && score_passes_loose(s, p.thr, p.cmp, p.delta);
+                    if (p.has_filter) ok = ok && score_passes_loose(s, p.thr, p.cmp, delta);
                     const bool top = take_max ? s >= tau_s : s <= tau_s;
                     if (ok && !top) xbest = fmaxf(xbest, s * sgn);
-                    ok = ok && top;
-                    if (__ballot_sync(FULL, ok))
-                        warp_push_pairs(hdr, cand_keys, cand_qids, p.cap, p.k, ok, make_key(s, row, take_max), qi, p.g_tau, lane);
+                    pass |= (ok && top) ? (1u << j) : 0u;
+                }
+                // rare path: columns where some lane passed are re-read one at a time and pushed (kept out of the
+                // unrolled loop so that the hot code stays small)
+                uint32_t cols = __reduce_or_sync(FULL, pass);
+                while (cols) {
+                    const uint32_t j = __ffs(cols) - 1;
+                    cols &= cols - 1;
+                    const uint32_t qi = q_base + c * 32 + j;
+                    const float s = batch_score<METRIC>(__uint_as_float(tmem_ld_32x32b_x1(taddr + c * 32 + j)), p.q_scal, qi, rs);
+                    warp_push_pairs(hdr, cand_keys, cand_qids, p.cap, p.k, (pass >> j) & 1u, make_key(s, row, take_max), qi, p.g_tau, lane);
                 }
             }
             tc_fence_before();
-            mbar_arrive(&bar_tempty[buf]);
+            if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_tempty[buf], 0);
+            else mbar_arrive(&bar_tempty[buf]);
             ++tn;
             // adopt the grid-wide threshold once per tile
             if (warp == 8 && lane == 0) {
@@ -472,24 +598,57 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         }
     }
 
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // no arrival on the peer's barriers is still in flight; both CTAs are done with TMEM
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc_cg<CG>(tmem_base, TMEM_COLS);
     }
 }
 
 // ---- query split: hi = rna_tf32(q), lo = rna_tf32(q - hi); rows >= nq are zero -----------------------------
-__global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql) {
-    const size_t total = (size_t)nq_pad * dim_pad;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(i / dim_pad);
-        float x = r < nq ? q[i] : 0.f;
-        float h = rna_tf32(x);
-        qh[i] = h;
-        ql[i] = rna_tf32(x - h);
+// One warp per (padded) query row.  Also leaves |q|^2 per query (the euclidean epilogue's scalar) and the
+// largest |q|^2 of the batch (for the error bound).
+__global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql,
+                                     float* qn2, uint32_t* qmax2_bits) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < nq_pad; r += gridDim.x * wpb) {
+        float acc = 0.f;
+        for (uint32_t c = lane; c < dim_pad; c += 32) {
+            const size_t i = (size_t)r * dim_pad + c;
+            const float x = r < nq ? q[i] : 0.f;
+            const float h = rna_tf32(x);
+            qh[i] = h;
+            ql[i] = rna_tf32(x - h);
+            acc = fmaf(x, x, acc);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+        if (lane == 0 && r < nq) {
+            qn2[r] = acc;
+            if (acc > 0.f && acc <= FLT_MAX) atomicMax(qmax2_bits, __float_as_uint(acc));  // positive floats order like uints
+            else if (!(acc <= FLT_MAX)) atomicMax(qmax2_bits, 0x7F800000u);                   // inf / NaN query
+        }
     }
+}
+
+// Bound on |tensor-core score - exact score| for this batch: kappa * |q|max * |v|max for dot
+// products, kappa for cosine, kappa * (|q|max + |v|max)^2 for squared distances, kappa = 2^-15 * max(1, dim / 1024).
+__global__ void batch_delta_kernel(int metric, uint32_t dim, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta) {
+    const double kappa = ldexp(1.0, -15) * fmax(1.0, (double)dim / 1024.0) * 1.01;
+    double d;
+    if (metric == OTTERS_METRIC_COSINE) {
+        d = kappa;
+    } else {
+        const double qmax = sqrt((double)__uint_as_float(*qmax2_bits));
+        const float vinv = __uint_as_float(*vmin_inv_bits);  // smallest positive inverse row norm (huge when all rows are zero)
+        const double vmax = (vinv > 0.f && vinv < 1e30f) ? 1.0 / (double)vinv : 0.0;
+        d = metric == OTTERS_METRIC_DOT ? kappa * qmax * vmax : kappa * (qmax + vmax) * (qmax + vmax);
+    }
+    *delta = (float)d;  // inf / NaN propagate: the host then takes the exact path
 }
 
 // ---- exact re-scoring of the selected (row, query) pairs ---------------------------------------------------
@@ -633,49 +792,77 @@ int make_tensor_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t
     return OTTERS_OK;
 }
 
-template <int METRIC>
+template <int METRIC, int CG>
 int launch_batch_one(const CUtensorMap& tv, const CUtensorMap& tqh, const CUtensorMap& tql, const BatchParams& p, uint32_t grid,
                      uint32_t smem, uint32_t* configured, cudaStream_t s) {
-    auto kern = batch_kernel<METRIC>;
-    if (smem > configured[METRIC]) {
+    auto kern = batch_kernel<METRIC, CG>;
+    uint32_t& have = configured[METRIC * 2 + (CG - 1)];
+    if (smem > have) {
         OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[METRIC] = smem;
+        have = smem;
     }
-    kern<<<grid, NUM_THREADS, smem, s>>>(tv, tqh, tql, p);
-    OTTERS_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OTTERS_CUDA(cudaLaunchKernelEx(&cfg, kern, tv, tqh, tql, p));
     return OTTERS_OK;
+}
+
+template <int CG>
+int launch_batch_cg(const CUtensorMap& tv, const CUtensorMap& tqh, const CUtensorMap& tql, const BatchParams& p, uint32_t grid,
+                    uint32_t smem, int metric, uint32_t* configured, cudaStream_t s) {
+    switch (metric) {
+    case OTTERS_METRIC_COSINE: return launch_batch_one<OTTERS_METRIC_COSINE, CG>(tv, tqh, tql, p, grid, smem, configured, s);
+    case OTTERS_METRIC_EUCLIDEAN: return launch_batch_one<OTTERS_METRIC_EUCLIDEAN, CG>(tv, tqh, tql, p, grid, smem, configured, s);
+    case OTTERS_METRIC_DOT: return launch_batch_one<OTTERS_METRIC_DOT, CG>(tv, tqh, tql, p, grid, smem, configured, s);
+    }
+    return fail(OTTERS_ERR_INVALID, "Search metric is not set");
 }
 
 }  // namespace
 
-uint32_t batch_smem_bytes(uint32_t cap) { return STAGES * STAGE_BYTES + 1024 + 256 + cap * 12; }
+uint32_t batch_smem_bytes(uint32_t cap) {
+    static_assert(Geo<1>::STAGES * Geo<1>::STAGE_BYTES == Geo<2>::STAGES * Geo<2>::STAGE_BYTES, "both geometries stage 192 KB");
+    return Geo<1>::STAGES * Geo<1>::STAGE_BYTES + 1024 + 256 + cap * 12;
+}
 
-int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, cudaStream_t s) {
-    const size_t total = (size_t)nq_pad * dim_pad;
-    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 1184);
-    split_queries_kernel<<<blocks ? blocks : 1, 256, 0, s>>>(q, nq, nq_pad, dim_pad, qh, ql);
+int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, float* qn2,
+                         uint32_t* qmax2_bits, cudaStream_t s) {
+    const unsigned blocks = (unsigned)std::min<uint32_t>((nq_pad + 7) / 8, 1184);
+    split_queries_kernel<<<blocks ? blocks : 1, 256, 0, s>>>(q, nq, nq_pad, dim_pad, qh, ql, qn2, qmax2_bits);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_batch_delta(int metric, uint32_t dim, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta, cudaStream_t s) {
+    batch_delta_kernel<<<1, 1, 0, s>>>(metric, dim, qmax2_bits, vmin_inv_bits, delta);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
 
 int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s) {
+    const uint32_t cg = l.cta_group == 2 ? 2 : 1;
     CUtensorMap tv, tqh, tql;
     int rc = make_tensor_map(&tv, l.vectors, l.n_rows, l.dim, l.pitch_g, BM);
     if (rc) return rc;
-    rc = make_tensor_map(&tqh, l.q_hi, l.nq_pad, l.dim, l.dim_pad, BN);
+    rc = make_tensor_map(&tqh, l.q_hi, l.nq_pad, l.dim, l.dim_pad, BN / cg);
     if (rc) return rc;
-    rc = make_tensor_map(&tql, l.q_lo, l.nq_pad, l.dim, l.dim_pad, BN);
+    rc = make_tensor_map(&tql, l.q_lo, l.nq_pad, l.dim, l.dim_pad, BN / cg);
     if (rc) return rc;
-    p.n_rowtiles = (uint32_t)((l.n_rows + BM - 1) / BM);
     p.n_qtiles = l.nq_pad / BN;
     p.nkb = (l.dim + BK - 1) / BK;
     const uint32_t smem = batch_smem_bytes(p.cap);
-    switch (metric) {
-    case OTTERS_METRIC_COSINE: return launch_batch_one<OTTERS_METRIC_COSINE>(tv, tqh, tql, p, l.grid, smem, smem_configured, s);
-    case OTTERS_METRIC_EUCLIDEAN: return launch_batch_one<OTTERS_METRIC_EUCLIDEAN>(tv, tqh, tql, p, l.grid, smem, smem_configured, s);
-    case OTTERS_METRIC_DOT: return launch_batch_one<OTTERS_METRIC_DOT>(tv, tqh, tql, p, l.grid, smem, smem_configured, s);
-    }
-    return fail(OTTERS_ERR_INVALID, "Search metric is not set");
+    if (cg == 2) return launch_batch_cg<2>(tv, tqh, tql, p, l.grid, smem, metric, smem_configured, s);
+    return launch_batch_cg<1>(tv, tqh, tql, p, l.grid, smem, metric, smem_configured, s);
 }
 
 int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s) {

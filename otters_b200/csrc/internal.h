@@ -155,14 +155,14 @@ int launch_cands_to_records(const Cand* cands, const uint32_t* count, uint32_t k
 // ---- batched (tensor-core) path: batched.cu -------------------------------------------------------------
 struct BatchParams {
     uint32_t n_rows, nq;
-    uint32_t n_rowtiles, n_qtiles, nkb;  // filled by launch_batch
+    uint32_t n_qtiles, nkb;      // filled by launch_batch
     const float* inv_norms;
     const float* q_scal;         // per query: 1/|q| (cosine) or |q|^2 (euclidean); unused for dot
     int32_t take_max;
     int32_t has_filter;
     float thr;
     int32_t cmp;
-    float delta;                 // bound on |approximate - exact| score (loosens the vec_filter)
+    const float* delta;          // device: bound on |approximate - exact| score (loosens the vec_filter)
     const uint32_t* row_mask;    // Lsb0 words, bit = 1 keep; null = all rows
     uint32_t row_mask_words;
     uint32_t k, cap;
@@ -173,6 +173,7 @@ struct BatchParams {
     uint64_t* cta_keys;          // [grid][k] approximate keys, best first
     uint32_t* cta_qids;          // [grid][k]
     uint32_t* cta_counts;        // [grid]
+    uint32_t dbg;                // timing experiments only (OTTERS_BATCH_DBG): 1 no loads, 2 no split, 4 no epilogue, 8 no MMAs
 };
 struct BatchLaunch {
     const float* vectors;
@@ -181,7 +182,8 @@ struct BatchLaunch {
     const float* q_hi;
     const float* q_lo;
     uint32_t nq_pad;             // multiple of kBatchQueries
-    uint32_t grid;
+    uint32_t grid;               // CTAs (a multiple of cta_group)
+    uint32_t cta_group;          // 1: one CTA per 128-row tile; 2: CTA pairs (tcgen05 cta_group::2) on 256-row tiles
 };
 struct RescoreParams {
     const float* vectors;
@@ -203,7 +205,9 @@ struct RescoreParams {
     uint32_t* max_err_bits;
 };
 uint32_t batch_smem_bytes(uint32_t cap);
-int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, cudaStream_t s);
+int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, float* qn2,
+                         uint32_t* qmax2_bits, cudaStream_t s);
+int launch_batch_delta(int metric, uint32_t dim, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta, cudaStream_t s);
 int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s);
 int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s);
 int launch_min_inv_norm(const float* inv, uint64_t n, uint32_t* out_bits, cudaStream_t s);

@@ -6,7 +6,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from helpers import ob, ora
 
 ctx = ob.default_context(0)
-ctx.set_tuning(batch_mode=1)
+import sys as _s
+cg = int(_s.argv[1]) if len(_s.argv) > 1 else 0
+ctx.set_tuning(batch_mode=1, batch_cta_group=cg)
+print("cta_group", cg)
 for (n, dim, nq, k, metric) in [(300, 24, 2, 30, ob.Metric.DotProduct), (300, 32, 2, 30, ob.Metric.DotProduct), (2000, 64, 8, 30, ob.Metric.DotProduct),
                                 (2000, 64, 8, 30, ob.Metric.Cosine), (2000, 64, 8, 30, ob.Metric.Euclidean), (5000, 768, 64, 100, ob.Metric.DotProduct)]:
     v = ora.synth_fill(0, n, dim, 0x7735 + n)

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 METRICS = [ob.Metric.Cosine, ob.Metric.Euclidean, ob.Metric.DotProduct]
 
 
-@pytest.fixture()
-def bctx(ctx):
-    ctx.set_tuning(batch_mode=1)
+@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+def bctx(ctx, request):
+    """Forces the tensor-core kernel, once as CTA pairs (tcgen05 cta_group::2, the default) and once as single CTAs."""
+    ctx.set_tuning(batch_mode=1, batch_cta_group=request.param)
     yield ctx
     ctx.set_tuning()
 
