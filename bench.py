@@ -259,6 +259,10 @@ def run_reference(args, wl):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
 def run_ours(args, wl):
+    # libraries (NCCL's version banner, ...) may write to fd 1: park the real stdout and send everything else to stderr,
+    # so that the ONE JSON line is all this process prints on stdout
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -277,9 +281,11 @@ def run_ours(args, wl):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = ob.Context(local_rank, stream.cuda_stream)
+    tune = {}
     if args.tuning:
         w, s, kc, cps, ur = (int(x) for x in args.tuning.split(","))
-        ctx.set_tuning(w, s, kc, cps, ur)
+        tune = dict(warps_per_cta=w, slots_per_warp=s, kc_floats=kc, ctas_per_sm=cps, unit_rows=ur)
+    ctx.set_tuning(**tune)
 
     rows, dim, chunk, k = wl["rows"], wl["dim"], wl["chunk"], wl["k"]
     metric = getattr(ob.Metric, wl["metric"])
@@ -321,6 +327,9 @@ def run_ours(args, wl):
 
     shard = CudaShard(store, 0, k, block_rows=block)
     take_max = tt == ob.TakeType.Max
+    # N > 1: the exchange is fused into the selection kernel (peer stores over NVLink + flags + merge, no NCCL call on the
+    # query path) when the box can map peer memory; otherwise NCCL all-gather + merge kernel
+    fused = world > 1 and nq == 1 and args.exchange != "nccl" and shard.enable_peer_exchange()
 
     def barrier():
         if world > 1:
@@ -332,6 +341,9 @@ def run_ours(args, wl):
 
     def e2e_step(i):
         vq = make_vq(i)
+        if fused:
+            out, _ = shard.search_fused(vq, fp, k)
+            return out
         if args.phase_timing:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             evs[0].record()
@@ -364,6 +376,9 @@ def run_ours(args, wl):
     qstats = _ffi.QueryStats()
     step_e2e = e2e_step_single if world == 1 else e2e_step
 
+    if world > 1 and wl["meta"]:  # vectors_compared of this shard (summed over the ranks below)
+        _, st0 = shard.enqueue(make_vq(0), fp, k, want_stats=True)
+        qstats.vectors_compared = st0.vectors_compared
     for i in range(args.warmup):
         step_e2e(i)
     barrier()
@@ -372,20 +387,12 @@ def run_ours(args, wl):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms, scan_bytes, meta_bytes, rows_scored, launches = [], [], [], [], 0
-    batch_info = []
+    batch_info, phase_ms = [], []
     t0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
         step_e2e(args.warmup + i)
-        w = ctx.last_work()
-        if w["scan_ms"] > 0:
-            scan_ms.append(w["scan_ms"])
-            scan_bytes.append(w["scan_bytes"])
-        meta_bytes.append(w["meta_bytes"])
-        rows_scored.append(w["rows_scored"])
-        launches += int(w["kernel_launches"])
-        if nq > 1:
-            batch_info.append((w["batch_used"], w["batch_fallback"], w["batch_max_err"], w["batch_delta"], w["select_ms"]))
+        launches += int(ctx.last_work()["kernel_launches"])
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
@@ -393,11 +400,31 @@ def run_ours(args, wl):
     if args.phase_timing and phase_ev:
         pe = np.array(phase_ev[args.warmup:])
         print(f"[rank {rank}] phases ms: local+gather(dev)={pe[:,0].mean():.3f} merge+fetch(dev)={pe[:,1].mean():.3f} "
-              f"host enqueue={pe[:,2].mean():.3f} host merge={pe[:,3].mean():.3f} scan={np.mean(scan_ms) if scan_ms else 0:.3f}", file=sys.stderr)
+              f"host enqueue={pe[:,2].mean():.3f} host merge={pe[:,3].mean():.3f}", file=sys.stderr)
+
+    # ---- roofline numerator: the same steps with the library's per-phase CUDA events switched on (they bracket the
+    # kernels on the launching stream; kept out of the throughput loops because every event costs a few microseconds)
+    ctx.set_tuning(**tune, timing=1)
+    for i in range(min(args.steps, 30)):
+        step_e2e(args.warmup + i)
+        w = ctx.last_work()
+        if w["scan_ms"] > 0:
+            scan_ms.append(w["scan_ms"])
+            scan_bytes.append(w["scan_bytes"])
+        meta_bytes.append(w["meta_bytes"])
+        phase_ms.append((w["prune_ms"], w["rowmask_ms"], w["scan_ms"], w["select_ms"]))
+        rows_scored.append(w["rows_scored"])
+        if nq > 1:
+            batch_info.append((w["batch_used"], w["batch_fallback"], w["batch_max_err"], w["batch_delta"], w["select_ms"]))
+    ctx.set_tuning(**tune)
+    barrier()
 
     # ---- value: device pipeline only (no per-step host sync, results stay in HBM) -------------------------
     def dev_step(i):
         vq = make_vq(i)
+        if fused:
+            shard.search_fused(vq, fp, k, fetch=False)
+            return
         gathered, _ = shard.enqueue(vq, fp, k)
         if world > 1:
             shard.merge(gathered, k, take_max, fetch=False)
@@ -415,12 +442,12 @@ def run_ours(args, wl):
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(np.sum(rows_scored)), float(qstats.vectors_compared)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(np.mean(rows_scored)) if rows_scored else 0.0, float(qstats.vectors_compared)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms, e2e_wall_ms = (float(x) for x in t.tolist())
-    rows_scored_total = float(tot[0].item()) / args.steps
+    rows_scored_total = float(tot[0].item())
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -457,7 +484,9 @@ def run_ours(args, wl):
             "config": {
                 "workload": f"{args.workload}: {wl['desc']}", "rows": rows, "dim": dim, "k": k, "chunk_size": chunk,
                 "filter": expr_desc, "rows_scored_per_query": rows_scored_total,
-                "parallelism": f"rows block-cyclic ({block}-row blocks) over {world} GPU(s)" + (" + NCCL all-gather of k records + device merge" if world > 1 else ""),
+                "parallelism": f"rows block-cyclic ({block}-row blocks) over {world} GPU(s)" + (
+                    "" if world == 1 else (" + exchange fused into the selection kernel (peer stores over NVLink, flags, merge)" if fused
+                                           else " + NCCL all-gather of k records + device merge")),
                 "l2": ("no flush needed: every step streams %.2f GB of distinct rows, far larger than the 126 MB L2" % (rows_scored_total / max(nq, 1) * dim * 4 / 1e9)
                        if rows_scored_total / max(nq, 1) * dim * 4 > 4 * 126e6 else
                        "NOT flushed: the %.0f MB store is L2-resident between steps (latency-bound case; the HBM roofline does not apply)" % (rows * dim * 4 / 1e6)),
@@ -466,13 +495,15 @@ def run_ours(args, wl):
             "e2e": {"value": nq * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * 16 + 48),
                     "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms},
             "gpu_launches": launches,
+            "phases_ms": dict(zip(("prune", "rowmask", "scan", "select"), (float(x) for x in np.mean(np.array(phase_ms), axis=0)))) if phase_ms else None,
             "roofline": roof,
             "rows_scored_per_sec": rows_scored_total * 1e3 / dev_ms,
             "vectors_compared_per_sec": (float(tot[1].item()) * 1e3 / dev_ms) if wl["meta"] else rows_scored_total * 1e3 / dev_ms,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -489,6 +520,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--phase-timing", action="store_true", help="print per-phase device/host times of the sharded step (debug)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"], help="N > 1: fused peer-memory exchange when available, or force NCCL")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.rows:

@@ -95,6 +95,8 @@ typedef struct {
     uint32_t disable_fused_predicate; /* 1: evaluate the row predicate in its own kernel instead of inside the scan */
     uint32_t batch_mode;   /* query batches: 0 = automatic, 1 = always the tensor-core kernel (when k <= 1024), 2 = never */
     uint32_t batch_cta_group; /* tensor-core kernel: 0 = automatic (CTA pairs, tcgen05 cta_group::2), 1 = single CTAs, 2 = pairs */
+    uint32_t timing;       /* per-phase CUDA events (otters_last_work *_ms, otters_query_stats durations): 0 = automatic (only
+                              for blocking MetaStore queries that ask for stats), 1 = always, 2 = never */
 } otters_scan_tuning;
 OTTERS_API int otters_ctx_set_tuning(otters_ctx *ctx, const otters_scan_tuning *t);
 
@@ -289,6 +291,31 @@ typedef struct {
 OTTERS_API int otters_query_local_device(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q,
                               const otters_filter *filter, const otters_shard_map *map, void *d_records,
                               otters_query_stats *stats /* nullable */);
+/* Fused exchange over peer memory (NVLink / NVSwitch).  Every rank owns a record area of 2 * world * k_max
+ * otters_topk_record and a flag area of 2 * world uint32 (zero-initialised), both mapped into every peer process
+ * (CUDA IPC / symmetric memory; otters_b200/sharded.py uses torch.distributed._symmetric_memory for the mapping).
+ * peer_records[p] / peer_flags[p] are rank p's areas as mapped into THIS process (p == rank: the local areas). */
+typedef struct {
+    uint32_t world;              /* 2..8 */
+    uint32_t rank;
+    uint64_t k_max;              /* records per (query parity, rank) slot; take counts must not exceed it */
+    void *const *peer_records;   /* [world] */
+    uint32_t *const *peer_flags; /* [world] */
+} otters_peer_exchange;
+
+/* Row-sharded query with the exchange fused into the selection kernel: local prune/scan, then ONE kernel selects
+ * the local top-k, stores its k records straight into every peer's record area, publishes them with a release
+ * flag, waits for the other ranks' flags and merges world * k records — no NCCL call and no extra launch on the
+ * query path.  `seq` numbers the queries of this exchange (1, 2, 3, ... identical on every rank; areas are double
+ * buffered on its parity).  Every rank must call it for every query.  With out_idx = out_score = out_qid = NULL and
+ * cap = 0 the call only enqueues (no copy, no sync).  Returns OTTERS_ERR_UNSUPPORTED for plans the fused selection
+ * does not serve (take counts above 1024 or above k_max, batches routed to the tensor-core kernel); callers then
+ * use otters_query_local_device + an all-gather + otters_topk_merge_device.  Stats are local to the shard. */
+OTTERS_API int otters_query_exchange(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q,
+                          const otters_filter *filter, const otters_shard_map *map, const otters_peer_exchange *ex,
+                          uint64_t seq, uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap,
+                          uint64_t *out_len, otters_query_stats *stats /* nullable */);
+
 /* Appends n_local rows of the synthetic generator whose global row ids follow `map` (bench/test utility). */
 OTTERS_API int otters_vecstore_add_synthetic_sharded(otters_vecstore *vs, const otters_shard_map *map, uint64_t n_local, uint64_t seed);
 /* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k.

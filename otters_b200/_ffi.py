@@ -36,6 +36,7 @@ class ScanTuning(C.Structure):
         ("disable_fused_predicate", C.c_uint32),
         ("batch_mode", C.c_uint32),
         ("batch_cta_group", C.c_uint32),
+        ("timing", C.c_uint32),
     ]
 
 
@@ -154,6 +155,16 @@ class TopkRecord(C.Structure):
     _fields_ = [("row", C.c_uint64), ("score", C.c_float), ("qid", C.c_uint32)]
 
 
+class PeerExchange(C.Structure):
+    _fields_ = [
+        ("world", C.c_uint32),
+        ("rank", C.c_uint32),
+        ("k_max", C.c_uint64),
+        ("peer_records", C.POINTER(C.c_void_p)),
+        ("peer_flags", C.POINTER(C.c_void_p)),
+    ]
+
+
 VECTORS_HOST, VECTORS_DEVICE, VECTORS_SYNTHETIC = 0, 1, 2
 
 _p = C.c_void_p
@@ -224,6 +235,11 @@ otters_vecstore_add_synthetic_sharded = _sig(
 )
 otters_topk_merge_device = _sig(
     "otters_topk_merge_device", C.c_int, _p, _p, C.c_uint64, C.c_uint64, C.c_int32, c_u64p, c_f32p, c_u32p, C.c_uint64, c_u64p
+)
+
+otters_query_exchange = _sig(
+    "otters_query_exchange", C.c_int, _p, _p, C.POINTER(VecQuery), C.POINTER(Filter), C.POINTER(ShardMap), C.POINTER(PeerExchange),
+    C.c_uint64, c_u64p, c_f32p, c_u32p, C.c_uint64, c_u64p, C.POINTER(QueryStats)
 )
 
 BOUND_SYMBOLS = sorted(n for n in dir() if n.startswith("otters_"))

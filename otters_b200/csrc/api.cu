@@ -52,8 +52,8 @@ struct otters_ctx {
     otters_last_work last{};
 
     // device scratch
-    float* d_query = nullptr;
-    size_t d_query_floats = 0;
+    float* d_query = nullptr;           // the staged queries inside d_io
+    size_t d_query_off = 0;
     // one 64-byte control block, zeroed by a single memset at the start of every query:
     //   +0 unit counter, +4 emit count, +8 list counts[2], +16 tau, +24 rows scored, +32 stats[4]
     uint8_t* d_ctrl = nullptr;
@@ -87,17 +87,32 @@ struct otters_ctx {
     uint32_t* d_cta_qids = nullptr;     // [grid_max][kMaxFusedK]
     unsigned long long* d_batch_info = nullptr;  // d_ctrl + 64: [0] shared threshold key, [1] flags | max error bits << 32, [2] best excluded
     uint32_t batch_smem_configured[6] = {0, 0, 0, 0, 0, 0};
+    // fused peer exchange requested by otters_query_exchange for the query being enqueued
+    bool ex_active = false;
+    uint32_t ex_world = 0, ex_rank = 0, ex_kmax = 0, ex_k = 0, ex_seq = 0;
+    otters_topk_record* ex_records[kMaxPeers] = {};
+    uint32_t* ex_flags[kMaxPeers] = {};
 
-    // pinned staging: queries / masks, lowered filters, results
+    // Per-query input image: [control block 256 B | lowered filter | queries], assembled in pinned memory and sent with
+    // ONE host-to-device copy per query (it also resets the control block, so there is no memset on the query path).
+    // Two pinned slots alternate so the host can assemble query i+1 while the copy of query i is still in flight.
+    uint8_t* d_io = nullptr;
+    size_t d_io_bytes = 0;
+    uint8_t* h_io[2] = {nullptr, nullptr};
+    size_t h_io_bytes[2] = {0, 0};
+    cudaEvent_t ev_io[2]{};
+    bool io_pending[2] = {false, false};
+    int io_slot = 0;
+    size_t io_used = 0;
+    bool io_open = false;
+    // pinned staging: row masks, results
     uint8_t* h_stage = nullptr;
     size_t h_stage_bytes = 0;
-    uint8_t* h_filter = nullptr;
-    size_t h_filter_bytes = 0;
     uint8_t* h_result = nullptr;
     size_t h_result_bytes = 0;
 
     cudaEvent_t ev[8]{};
-    bool stage_pending = false;   // an async H2D copy out of h_stage is in flight (ev[7] marks its end)
+    bool timing = false;          // record the phase events for the query being enqueued
     bool timed_single = false;    // ev[3]/ev[4] bracket the single scan kernel of the last query
     bool timed_meta = false;      // ev[0]/ev[1] bracket the prune kernel of the last query
     bool timed_rowmask = false;   // ev[1]/ev[6] bracket the stand-alone row-mask kernel of the last query
@@ -108,10 +123,6 @@ struct otters_ctx {
 namespace otters {
 
 static int ensure_stage(otters_ctx* c, size_t bytes) {
-    if (c->stage_pending) {  // the staging buffer is about to be rewritten
-        OTTERS_CUDA(cudaEventSynchronize(c->ev[7]));
-        c->stage_pending = false;
-    }
     if (bytes <= c->h_stage_bytes) return OTTERS_OK;
     if (c->h_stage) cudaFreeHost(c->h_stage);
     c->h_stage = nullptr;
@@ -148,12 +159,91 @@ static int reset_scan_state(otters_ctx* c) {
     return OTTERS_OK;
 }
 
-// one memset resets every per-query counter (unit counter, list counts, tau, rows scored, stats)
+static void bind_io(otters_ctx* c) {
+    c->d_ctrl = c->d_io;
+    c->d_counter = reinterpret_cast<uint32_t*>(c->d_ctrl);
+    c->d_list_count = reinterpret_cast<uint32_t*>(c->d_ctrl + 8);
+    c->d_tau = reinterpret_cast<uint64_t*>(c->d_ctrl + 16);
+    c->d_rows_scored = reinterpret_cast<unsigned long long*>(c->d_ctrl + 24);
+    c->d_stats = reinterpret_cast<unsigned long long*>(c->d_ctrl + 32);
+    c->d_batch_info = reinterpret_cast<unsigned long long*>(c->d_ctrl + 64);
+}
+
+static int io_reserve(otters_ctx* c, size_t total) {
+    const int sl = c->io_slot;
+    if (total > c->h_io_bytes[sl]) {
+        const size_t nb = std::max<size_t>(round_up(total + total / 2, 4096), 1 << 16);
+        uint8_t* nh = nullptr;
+        OTTERS_CUDA(cudaMallocHost((void**)&nh, nb));
+        if (c->h_io[sl]) {
+            memcpy(nh, c->h_io[sl], c->io_used);
+            cudaFreeHost(c->h_io[sl]);
+        }
+        c->h_io[sl] = nh;
+        c->h_io_bytes[sl] = nb;
+    }
+    if (total > c->d_io_bytes) {
+        OTTERS_CUDA(cudaStreamSynchronize(c->stream));  // earlier queries still use the old buffer
+        const size_t nb = std::max<size_t>(round_up(total + total / 2, 4096), 1 << 16);
+        uint8_t* nd = nullptr;
+        if (cudaMalloc((void**)&nd, nb) != cudaSuccess) return fail(OTTERS_ERR_NOMEM, "device allocation for query inputs failed");
+        if (c->d_io) {
+            OTTERS_CUDA(cudaMemcpy(nd, c->d_io, 256, cudaMemcpyDeviceToDevice));
+            cudaFree(c->d_io);
+        }
+        c->d_io = nd;
+        c->d_io_bytes = nb;
+        bind_io(c);
+    }
+    return OTTERS_OK;
+}
+
+// Opens the input image of a new query: takes the next pinned slot (waiting for the copy that last used it) and
+// zeroes the control block image (unit counter, list counts, tau, rows scored, stats, batch info).
 static int begin_query(otters_ctx* c) {
-    OTTERS_CUDA(cudaMemsetAsync(c->d_ctrl, 0, 128, c->stream));
+    const int sl = c->io_slot;
+    if (c->io_pending[sl]) {
+        OTTERS_CUDA(cudaEventSynchronize(c->ev_io[sl]));
+        c->io_pending[sl] = false;
+    }
+    c->io_used = 0;
+    int rc = io_reserve(c, 256);
+    if (rc) return rc;
+    memset(c->h_io[sl], 0, 256);
+    c->io_used = 256;
+    c->io_open = true;
     c->last = otters_last_work{};
     c->timed_single = c->timed_meta = c->timed_rowmask = false;
+    c->timing = c->tuning.timing == 1;
     return OTTERS_OK;
+}
+
+// appends `bytes` (256-byte aligned) to the input image; returns the host pointer to fill and the device address
+static int io_push(otters_ctx* c, size_t bytes, uint8_t** host, size_t* dev_off) {
+    const size_t off = round_up(c->io_used, 256);
+    int rc = io_reserve(c, off + bytes + 256);
+    if (rc) return rc;
+    *host = c->h_io[c->io_slot] + off;
+    *dev_off = off;
+    c->io_used = off + bytes;
+    return OTTERS_OK;
+}
+
+// sends the input image with one copy; kernels enqueued afterwards see the control block reset and all inputs
+static int io_flush(otters_ctx* c) {
+    if (!c->io_open) return OTTERS_OK;
+    const int sl = c->io_slot;
+    OTTERS_CUDA(cudaMemcpyAsync(c->d_io, c->h_io[sl], c->io_used, cudaMemcpyHostToDevice, c->stream));
+    OTTERS_CUDA(cudaEventRecord(c->ev_io[sl], c->stream));
+    c->io_pending[sl] = true;
+    c->io_slot ^= 1;
+    c->io_open = false;
+    c->d_query = reinterpret_cast<float*>(c->d_io + c->d_query_off);  // d_io may have moved while the image grew
+    return OTTERS_OK;
+}
+
+static inline void rec_event(otters_ctx* c, int i) {
+    if (c->timing) cudaEventRecord(c->ev[i], c->stream);
 }
 
 static int alloc_list(otters_ctx* c, int i, size_t entries) {
@@ -375,6 +465,20 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     return OTTERS_OK;
 }
 
+static void fill_exchange(const otters_ctx* c, SelectParams* se) {
+    if (!c->ex_active) return;
+    se->ex_world = c->ex_world;
+    se->ex_rank = c->ex_rank;
+    se->ex_kmax = c->ex_kmax;
+    se->ex_seq = c->ex_seq;
+    se->ex_k = c->ex_k;
+    for (uint32_t i = 0; i < c->ex_world; ++i) {
+        se->ex_records[i] = c->ex_records[i];
+        se->ex_flags[i] = c->ex_flags[i];
+    }
+    se->records = nullptr;
+}
+
 // ---- the query core: scan + select for every query of the batch --------------------------------------
 struct QueryRun {
     uint32_t result_list = 0;  // index into ctx->d_list holding the final ordered candidates
@@ -395,6 +499,27 @@ static float host_inv_norm(const float* v, uint32_t dim) {
     return norm != 0.0f ? 1.0f / norm : 0.0f;
 }
 
+
+// appends the queries, zero padded to the stored row pitch, to the input image of the current query
+static int stage_queries(otters_ctx* c, const otters_vec_query* q, uint32_t dim_pad) {
+    const size_t qfloats = (size_t)q->nq * dim_pad;
+    uint8_t* h = nullptr;
+    size_t off = 0;
+    int rc = io_push(c, std::max<size_t>(qfloats * 4, 16), &h, &off);
+    if (rc) return rc;
+    float* hq = reinterpret_cast<float*>(h);
+    if (dim_pad == q->dim) {
+        memcpy(hq, q->queries, qfloats * 4);
+    } else {
+        for (uint32_t i = 0; i < q->nq; ++i) {
+            memcpy(hq + (size_t)i * dim_pad, q->queries + (size_t)i * q->dim, (size_t)q->dim * 4);
+            for (uint32_t j = q->dim; j < dim_pad; ++j) hq[(size_t)i * dim_pad + j] = 0.f;
+        }
+    }
+    c->d_query = reinterpret_cast<float*>(c->d_io + off);  // io_push may have moved d_io: take the address afterwards
+    c->d_query_off = off;
+    return OTTERS_OK;
+}
 
 // ---- query batches on the tensor cores (K2, batched.cu) ---------------------------------------------------
 // Selection runs on 3xTF32 tensor-core scores; every selected (row, query) pair is re-scored in the
@@ -496,11 +621,11 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bp.cta_qids = c->d_cta_qids;
     bp.cta_counts = c->d_cta_counts;
     if (const char* e = getenv("OTTERS_BATCH_DBG")) bp.dbg = (uint32_t)atoi(e);  // timing experiments; results are garbage
-    cudaEventRecord(c->ev[2], s);
-    cudaEventRecord(c->ev[3], s);
+    rec_event(c, 2);
+    rec_event(c, 3);
     rc = launch_batch(bl, bp, q->metric, c->batch_smem_configured, s);
     if (rc) return rc;
-    cudaEventRecord(c->ev[4], s);
+    rec_event(c, 4);
     c->timed_single = true;
 
     // exact re-scoring of every selected pair, then a full sort of the exact candidates
@@ -549,7 +674,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         rc = launch_cands_to_records(c->d_list[0], c->d_list_count, k, map, take_max, d_records_out, s);
         if (rc) return rc;
     }
-    cudaEventRecord(c->ev[5], s);
+    rec_event(c, 5);
     c->last.kernel_launches += 8 + (d_records_out ? 1 : 0);
 
     // fetch header + candidates and verify the selection
@@ -558,7 +683,6 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (rc) return rc;
     OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[0], bytes, cudaMemcpyDeviceToHost, s));
     OTTERS_CUDA(cudaStreamSynchronize(s));
-    c->stage_pending = false;
     const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
     const Cand* list = reinterpret_cast<const Cand*>(c->h_result + sizeof(ResultHeader));
     const uint32_t flags = (uint32_t)hdr->extra[0];
@@ -607,26 +731,11 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     c->last_metric = q->metric;
     cudaStream_t s = c->stream;
 
-    // stage queries (zero padded to the stored pitch) and their inverse norms
-    const size_t qfloats = (size_t)q->nq * dim_pad;
-    int rc = ensure_stage(c, qfloats * 4 + (size_t)q->nq * 4 + 64);
+    // the queries were staged (zero padded to the stored pitch) by stage_queries(); send the input image now
+    int rc = io_flush(c);
     if (rc) return rc;
-    rc = ensure_dev(&c->d_query, &c->d_query_floats, qfloats, s);
-    if (rc) return rc;
-    float* hq = reinterpret_cast<float*>(c->h_stage);
-    if (dim_pad == q->dim) {
-        memcpy(hq, q->queries, qfloats * 4);
-    } else {
-        for (uint32_t i = 0; i < q->nq; ++i) {
-            memcpy(hq + (size_t)i * dim_pad, q->queries + (size_t)i * q->dim, (size_t)q->dim * 4);
-            for (uint32_t j = q->dim; j < dim_pad; ++j) hq[(size_t)i * dim_pad + j] = 0.f;
-        }
-    }
-    OTTERS_CUDA(cudaMemcpyAsync(c->d_query, hq, qfloats * 4, cudaMemcpyHostToDevice, s));
-    OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
-    c->stage_pending = true;
 
-    if (batch_eligible(c, q, n_rows, k_eff)) {
+    if (!c->ex_active && batch_eligible(c, q, n_rows, k_eff)) {
         bool accepted = false;
         rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, &accepted);
         if (rc) return rc;
@@ -691,18 +800,18 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (fused) {
         rc = ensure_list0(c, kMaxFusedK);
         if (rc) return rc;
-        cudaEventRecord(c->ev[2], s);
+        rec_event(c, 2);
         for (uint32_t qi = 0; qi < q->nq; ++qi) {
             if (qi) OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(uint32_t), s));  // qi == 0: begin_query()
             sp.query = c->d_query + (size_t)qi * dim_pad;
             sp.q_inv = q_inv[qi];
             sp.qid = qi;
             sp.tau_in = qi ? c->d_tau : nullptr;
-            if (qi == 0 && q->nq == 1) cudaEventRecord(c->ev[3], s);
+            if (qi == 0 && q->nq == 1) rec_event(c, 3);
             rc = launch_scan(sp, pl.launch, q->metric, false, c->scan_smem_configured, s);
             if (rc) return rc;
             if (qi == 0 && q->nq == 1) {
-                cudaEventRecord(c->ev[4], s);
+                rec_event(c, 4);
                 c->timed_single = true;
             }
             SelectParams se{};
@@ -726,14 +835,16 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             se.hdr = list_hdr(c, cur ^ 1);
             se.rows_scored_src = c->d_rows_scored;
             se.stats_src = stats_src;
+            if (qi + 1 == q->nq) fill_exchange(c, &se);
             rc = launch_select(se, s);
             if (rc) return rc;
             cur ^= 1;
             c->last.kernel_launches += 2;
         }
-        cudaEventRecord(c->ev[5], s);
+        rec_event(c, 5);
         run->result_list = cur;
         run->big = false;
+        if (c->ex_active) run->k_eff = c->ex_k;  // the merged list may be longer than this shard's own
     } else {
         // large k: emit every passing candidate, sort everything, keep the best k (per query, with the
         // running list appended before the sort)
@@ -753,7 +864,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         sp.emit = c->d_emit;
         sp.emit_count = c->d_counter + 1;
         sp.emit_cap = (uint32_t)std::min<uint64_t>(n_sort, 0xFFFFFFFFull);
-        cudaEventRecord(c->ev[2], s);
+        rec_event(c, 2);
         for (uint32_t qi = 0; qi < q->nq; ++qi) {
             if (qi) OTTERS_CUDA(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(uint32_t), s));
             sp.query = c->d_query + (size_t)qi * dim_pad;
@@ -777,7 +888,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, sp.take_max, d_records_out, s);
             if (rc) return rc;
         }
-        cudaEventRecord(c->ev[5], s);
+        rec_event(c, 5);
         run->result_list = 0;
         run->big = true;
     }
@@ -794,8 +905,7 @@ static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint
         if (rc) return rc;
         OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[run.result_list], bytes, cudaMemcpyDeviceToHost, s));
         OTTERS_CUDA(cudaStreamSynchronize(s));
-        c->stage_pending = false;
-    }
+        }
     const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
     const uint32_t n = hdr->count;
     c->last.rows_scored = hdr->rows_scored;
@@ -817,9 +927,11 @@ static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint
 static void finish_work_stats(otters_ctx* c) {
     // only called after the stream was synchronised, so all events have completed
     float ms = 0.f;
-    if (c->timed_single && elapsed_ms(c->ev[3], c->ev[4], &ms)) c->last.scan_ms = ms;
-    else if (elapsed_ms(c->ev[2], c->ev[5], &ms)) c->last.scan_ms = ms;
-    if (c->timed_single && elapsed_ms(c->ev[4], c->ev[5], &ms)) c->last.select_ms = ms;
+    if (c->timing) {
+        if (c->timed_single && elapsed_ms(c->ev[3], c->ev[4], &ms)) c->last.scan_ms = ms;
+        else if (elapsed_ms(c->ev[2], c->ev[5], &ms)) c->last.scan_ms = ms;
+        if (c->timed_single && elapsed_ms(c->ev[4], c->ev[5], &ms)) c->last.select_ms = ms;
+    }
     const uint64_t per_row = (uint64_t)c->last_dim * 4 + (c->last_metric == OTTERS_METRIC_COSINE ? 4 : 0);
     c->last.scan_bytes = c->last.rows_scored * per_row;
 }
@@ -869,17 +981,14 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
         c->own_stream = true;
     }
     c->grid_max = (uint32_t)c->sm_count * 2;
-    OTTERS_CUDA(cudaMalloc((void**)&c->d_ctrl, 256));
-    OTTERS_CUDA(cudaMemset(c->d_ctrl, 0, 256));
-    c->d_counter = reinterpret_cast<uint32_t*>(c->d_ctrl);
-    c->d_list_count = reinterpret_cast<uint32_t*>(c->d_ctrl + 8);
-    c->d_tau = reinterpret_cast<uint64_t*>(c->d_ctrl + 16);
-    c->d_rows_scored = reinterpret_cast<unsigned long long*>(c->d_ctrl + 24);
-    c->d_stats = reinterpret_cast<unsigned long long*>(c->d_ctrl + 32);
+    c->d_io_bytes = 1 << 16;
+    OTTERS_CUDA(cudaMalloc((void**)&c->d_io, c->d_io_bytes));
+    OTTERS_CUDA(cudaMemset(c->d_io, 0, 256));
+    bind_io(c.get());
+    for (auto& e : c->ev_io) OTTERS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_keys, (size_t)c->grid_max * kMaxFusedK * sizeof(uint64_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_counts, (size_t)c->grid_max * sizeof(uint32_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_qids, (size_t)c->grid_max * kMaxFusedK * sizeof(uint32_t)));
-    c->d_batch_info = reinterpret_cast<unsigned long long*>(c->d_ctrl + 64);
     {
         int rc0 = alloc_list(c.get(), 0, kMaxFusedK);
         if (rc0) return rc0;
@@ -891,8 +1000,6 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
     OTTERS_CUDA(cudaMalloc((void**)&c->d_scratch_keys, (size_t)c->scratch_elems * sizeof(uint64_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_scratch_src, (size_t)c->scratch_elems * sizeof(uint32_t)));
     for (auto& e : c->ev) OTTERS_CUDA(cudaEventCreate(&e));
-    int rc = ensure_stage(c.get(), 1 << 16);
-    if (rc) return rc;
     *out = c.release();
     return OTTERS_OK;
 }
@@ -901,8 +1008,11 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     if (!c) return OTTERS_OK;
     DeviceGuard g(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_query);
-    cudaFree(c->d_ctrl);
+    cudaFree(c->d_io);
+    for (auto& e : c->ev_io)
+        if (e) cudaEventDestroy(e);
+    for (auto& h : c->h_io)
+        if (h) cudaFreeHost(h);
     cudaFree(c->d_cta_keys);
     cudaFree(c->d_cta_counts);
     cudaFree(c->d_list_raw[0]);
@@ -917,7 +1027,6 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     cudaFree(c->d_qscal);
     cudaFree(c->d_cta_qids);
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->h_filter) cudaFreeHost(c->h_filter);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -1073,6 +1182,8 @@ extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query
     uint32_t mask_words = 0;
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
+    rc = stage_queries(c, q, vs->st.pitch);
+    if (rc) return rc;
     QueryRun run;
     rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, ShardMap{}, nullptr, nullptr, &run);
     if (rc) return rc;
@@ -1154,8 +1265,6 @@ struct otters_metastore {
     DevColumn* d_cols = nullptr;
     uint32_t* d_chunk_keep = nullptr;
     uint32_t* d_row_mask = nullptr;
-    uint8_t* d_filter = nullptr;
-    size_t d_filter_bytes = 0;
     FusedFilter cur_filter;       // where the last lowered filter lives on the device
     bool has_stats = false;
     otters_query_stats last{};
@@ -1178,7 +1287,6 @@ extern "C" int otters_metastore_destroy(otters_metastore* ms) {
     cudaFree(ms->d_cols);
     cudaFree(ms->d_chunk_keep);
     cudaFree(ms->d_row_mask);
-    cudaFree(ms->d_filter);
     ms->st.release();
     delete ms;
     return OTTERS_OK;
@@ -1574,6 +1682,9 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     mp.stats = c->d_stats;
     *meta_bytes = 0;
     if (!f) {
+        int rc0 = io_flush(c);
+        if (rc0) return rc0;
+        mp.stats = c->d_stats;
         c->last.kernel_launches += 1;
         return launch_count_all_chunks(mp, s);
     }
@@ -1583,21 +1694,17 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     if (rc) return rc;
     const size_t off_bytes = round_up(offs.size() * 4, 16);
     const size_t total = off_bytes + leaves.size() * sizeof(DevLeaf);
-    if (c->stage_pending) {  // an earlier asynchronous call may still be reading the pinned staging buffers
-        OTTERS_CUDA(cudaEventSynchronize(c->ev[7]));
-        c->stage_pending = false;
-    }
-    rc = ensure_pinned(&c->h_filter, &c->h_filter_bytes, total + 64);
+    uint8_t* hf = nullptr;
+    size_t f_off = 0;
+    rc = io_push(c, total + 16, &hf, &f_off);
     if (rc) return rc;
-    rc = ensure_dev(&ms->d_filter, &ms->d_filter_bytes, total + 16, s);
+    memcpy(hf, offs.data(), offs.size() * 4);
+    if (!leaves.empty()) memcpy(hf + off_bytes, leaves.data(), leaves.size() * sizeof(DevLeaf));
+    rc = io_flush(c);  // control block reset + lowered filter + staged queries: one copy
     if (rc) return rc;
-    memcpy(c->h_filter, offs.data(), offs.size() * 4);
-    if (!leaves.empty()) memcpy(c->h_filter + off_bytes, leaves.data(), leaves.size() * sizeof(DevLeaf));
-    OTTERS_CUDA(cudaMemcpyAsync(ms->d_filter, c->h_filter, total, cudaMemcpyHostToDevice, s));
-    OTTERS_CUDA(cudaEventRecord(c->ev[7], s));
-    c->stage_pending = true;
-    mp.clause_off = reinterpret_cast<const uint32_t*>(ms->d_filter);
-    mp.leaves = reinterpret_cast<const DevLeaf*>(ms->d_filter + off_bytes);
+    mp.stats = c->d_stats;
+    mp.clause_off = reinterpret_cast<const uint32_t*>(c->d_io + f_off);
+    mp.leaves = reinterpret_cast<const DevLeaf*>(c->d_io + f_off + off_bytes);
     mp.n_clauses = f->n_clauses;
     ms->cur_filter.leaves = mp.leaves;
     ms->cur_filter.clause_off = mp.clause_off;
@@ -1608,23 +1715,25 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     if (want_row_mask && !force_row_mask && !c->tuning.disable_fused_predicate &&
         ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes)
         want_row_mask = false;  // the scan kernel evaluates the predicate itself (fused K0b)
-    cudaEventRecord(c->ev[0], s);
-    rc = launch_prune(mp, s);
+    rec_event(c, 0);
+    rc = launch_prune(mp, (uint32_t)leaves.size(), s);
     if (rc) return rc;
-    cudaEventRecord(c->ev[1], s);
+    rec_event(c, 1);
     c->timed_meta = true;
     c->last.kernel_launches += 1;
     if (want_row_mask) {
         rc = launch_rowmask(mp, (uint32_t)leaves.size(), s);
         if (rc) return rc;
         c->last.kernel_launches += 1;
-        cudaEventRecord(c->ev[6], s);
+        rec_event(c, 6);
         c->timed_rowmask = true;
     }
     // algorithmic metadata bytes: zonemap entries per leaf + column values/null bits of evaluated rows are
     // accounted by the caller once the evaluated-chunk count is known
     return OTTERS_OK;
 }
+
+static int exchange_only(otters_ctx* c, int take_max, const unsigned long long* stats_src, QueryRun* run);
 
 static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
                            otters_topk_record* d_records, ShardMap map, uint64_t* out_idx, float* out_score,
@@ -1638,13 +1747,19 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     cudaStream_t s = c->stream;
     rc = begin_query(c);
     if (rc) return rc;
+    // durations of otters_query_stats come from per-phase events: recorded only when the caller waits for stats
+    if (c->tuning.timing == 0 && stats && !d_records && !(c->ex_active && !out_len)) c->timing = true;
     // per-chunk collect() errors are swallowed by the reference (src/meta_compute.rs:182): an empty
     // batch or a wrong-dimension query returns no rows but still reports stats
     const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
     const bool scan = !chunk_err && q->k > 0 && ms->st.n > 0;
     uint64_t meta_bytes = 0;
+    if (scan) {
+        rc = stage_queries(c, q, ms->st.pitch);
+        if (rc) return rc;
+    }
     // the batched tensor-core kernel gates rows with a precomputed mask (K0b) instead of the fused predicate
-    const bool batched = scan && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
+    const bool batched = scan && !c->ex_active && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
     rc = run_meta_filter(ms, filter, q->nq, scan && filter, batched && filter, &meta_bytes);
     if (rc) return rc;
     unsigned long long hstats[4] = {0, 0, 0, 0};
@@ -1654,10 +1769,10 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
         if (r2) return r2;
         OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         OTTERS_CUDA(cudaStreamSynchronize(s));
-        c->stage_pending = false;
-        memcpy(hstats, c->h_result, 2 * sizeof(unsigned long long));
+            memcpy(hstats, c->h_result, 2 * sizeof(unsigned long long));
         return OTTERS_OK;
     };
+    const bool on_device = d_records || (c->ex_active && !out_len);  // result stays in HBM: no copy, no sync unless stats are wanted
     if (scan) {
         QueryRun run;
         const bool fuse = filter && !batched && !c->tuning.disable_fused_predicate && ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes;
@@ -1665,7 +1780,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
                          (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, map, c->d_stats,
                          fuse ? &ms->cur_filter : nullptr, &run);
         if (rc) return rc;
-        if (d_records) {
+        if (on_device) {
             if (stats) {  // device-resident result: only the stats come back (this synchronises)
                 rc = fetch_stats_only();
                 if (rc) return rc;
@@ -1674,6 +1789,20 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
             rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, &n_out, hstats);
             if (rc) return rc;
             finish_work_stats(c);
+        }
+    } else if (c->ex_active) {
+        // nothing to scan on this rank, but it still takes part in the exchange
+        QueryRun run;
+        rc = exchange_only(c, q->take_type == OTTERS_TAKE_MAX, c->d_stats, &run);
+        if (rc) return rc;
+        if (on_device) {
+            if (stats) {
+                rc = fetch_stats_only();
+                if (rc) return rc;
+            }
+        } else {
+            rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, &n_out, hstats);
+            if (rc) return rc;
         }
     } else {
         if (d_records) {
@@ -1695,7 +1824,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     st.pruned_chunks = st.total_chunks - st.evaluated_chunks;
     st.vectors_compared = hstats[1];
     // every path above synchronised the stream unless the result stays on the device without stats
-    const bool synced = !(d_records && !stats && scan);
+    const bool synced = c->timing && !(on_device && !stats && (scan || c->ex_active));
     float ms_f = 0.f;
     if (synced && c->timed_meta && elapsed_ms(c->ev[0], c->ev[1], &ms_f)) {
         st.prune_s = ms_f * 1e-3;
@@ -1842,8 +1971,111 @@ extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* 
     uint32_t mask_words = 0;
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
     if (rc) return rc;
+    rc = stage_queries(c, q, vs->st.pitch);
+    if (rc) return rc;
     QueryRun run;
     return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, map, nullptr, nullptr, &run);
+}
+
+
+namespace otters {
+// no local scan on this rank (empty shard, take(0) locally impossible, swallowed per-chunk error): the rank still
+// contributes k empty records and merges everybody else's
+static int exchange_only(otters_ctx* c, int take_max, const unsigned long long* stats_src, QueryRun* run) {
+    int rc0 = io_flush(c);
+    if (rc0) return rc0;
+    SelectParams se{};
+    se.cta_keys = c->d_cta_keys;
+    se.cta_counts = c->d_cta_counts;
+    se.n_lists = 0;
+    se.list_stride = 1;
+    se.out = c->d_list[1];
+    se.out_count = c->d_list_count + 1;
+    se.tau_out = c->d_tau;
+    se.k = 0;
+    se.scratch_keys = c->d_scratch_keys;
+    se.scratch_src = c->d_scratch_src;
+    se.scratch_elems = c->scratch_elems;
+    se.take_max = take_max;
+    se.hdr = list_hdr(c, 1);
+    se.rows_scored_src = c->d_rows_scored;
+    se.stats_src = stats_src;
+    fill_exchange(c, &se);
+    int rc = launch_select(se, c->stream);
+    if (rc) return rc;
+    c->last.kernel_launches += 1;
+    run->result_list = 1;
+    run->k_eff = c->ex_k;
+    run->big = false;
+    return OTTERS_OK;
+}
+}  // namespace otters
+
+extern "C" int otters_query_exchange(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                                     const otters_shard_map* map_in, const otters_peer_exchange* ex, uint64_t seq, uint64_t* out_idx,
+                                     float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
+    if ((!vs && !ms) || (vs && ms) || !q || !ex) return fail(OTTERS_ERR_INVALID, "pass exactly one store, a query and an exchange");
+    if (ex->world < 2 || ex->world > kMaxPeers || ex->rank >= ex->world || !ex->peer_records || !ex->peer_flags)
+        return fail(OTTERS_ERR_INVALID, "peer exchange: world must be 2..8 with mapped record and flag areas");
+    if (seq == 0) return fail(OTTERS_ERR_INVALID, "peer exchange: sequence numbers start at 1");
+    if (q->k == 0 || q->k > kMaxFusedK || q->k > ex->k_max)
+        return fail(OTTERS_ERR_UNSUPPORTED, "peer exchange serves take counts 1..min(1024, k_max)");
+    if (vs && filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
+    otters_ctx* c = vs ? vs->st.ctx : ms->ctx;
+    DeviceGuard g(c->device);
+    const bool want_fetch = out_idx || out_score || out_qid || cap;
+    if (want_fetch && !out_len) return fail(OTTERS_ERR_INVALID, "null out_len");
+    c->ex_active = true;
+    c->ex_world = ex->world;
+    c->ex_rank = ex->rank;
+    c->ex_kmax = (uint32_t)ex->k_max;
+    c->ex_k = (uint32_t)q->k;
+    c->ex_seq = (uint32_t)seq;
+    for (uint32_t i = 0; i < ex->world; ++i) {
+        c->ex_records[i] = (otters_topk_record*)ex->peer_records[i];
+        c->ex_flags[i] = ex->peer_flags[i];
+    }
+    struct Reset {
+        otters_ctx* c;
+        ~Reset() { c->ex_active = false; }
+    } reset{c};
+    const ShardMap map = to_map(map_in);
+    const bool take_max = q->take_type == OTTERS_TAKE_MAX;
+    int rc;
+    if (ms) {
+        // meta_query_impl drives prune + scan + fused select/exchange; with want_fetch it also copies the result
+        uint64_t n = 0;
+        rc = meta_query_impl(ms, q, filter, nullptr, map, out_idx, out_score, out_qid, want_fetch ? cap : 0, want_fetch ? &n : nullptr,
+                             stats);
+        if (rc) return rc;
+        if (out_len) *out_len = n;
+        return OTTERS_OK;
+    }
+    rc = validate_query(q, vs->st.dim, false);
+    if (rc) return rc;
+    rc = begin_query(c);
+    if (rc) return rc;
+    QueryRun run;
+    if (vs->st.n == 0) {
+        rc = exchange_only(c, take_max, nullptr, &run);
+    } else {
+        const uint32_t* d_mask = nullptr;
+        uint32_t mask_words = 0;
+        rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
+        if (rc) return rc;
+        rc = stage_queries(c, q, vs->st.pitch);
+        if (rc) return rc;
+        rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, map, nullptr, nullptr, &run);
+    }
+    if (rc) return rc;
+    if (!want_fetch) {
+        if (out_len) *out_len = 0;
+        return OTTERS_OK;
+    }
+    rc = fetch_results(c, run, take_max, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
+    if (rc) return rc;
+    finish_work_stats(c);
+    return OTTERS_OK;
 }
 
 extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, uint64_t n_records, uint64_t k, int32_t take_type,

@@ -543,8 +543,9 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 uint32_t pass = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) {
-                    const float s = batch_score<METRIC>(__uint_as_float(v[j]), p.q_scal, q_base + c * 32 + j, rs);
-                    bool ok = live && (c * 32 + j < nq_tile);
+                    const bool inq = c * 32 + j < nq_tile;  // columns past the batch hold zero queries: never read their scalars
+                    const float s = batch_score<METRIC>(__uint_as_float(v[j]), p.q_scal, inq ? q_base + c * 32 + j : 0u, rs);
+                    bool ok = live && inq;
                     if (ok && !(fabsf(s) <= FLT_MAX)) nonfinite = true;  // inf / NaN: let the exact path decide
                     if (p.has_filter) ok = ok && score_passes_loose(s, p.thr, p.cmp, delta);
                     const bool top = take_max ? s >= tau_s : s <= tau_s;

@@ -38,6 +38,7 @@ constexpr uint32_t kTileRows = 16;     // rows per staged tile (2 threads per ro
 constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work unit
 constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
 constexpr uint32_t kSelectSmemElems = 8192;
+constexpr uint32_t kMaxPeers = 8;       // GPUs of one NVSwitch domain taking part in a row-sharded search
 constexpr uint32_t kBatchRows = 128;    // store rows per tile of the batched kernel (UMMA M)
 constexpr uint32_t kBatchQueries = 256; // queries per tile of the batched kernel (UMMA N)
 
@@ -135,6 +136,13 @@ struct SelectParams {
     ResultHeader* hdr;
     const unsigned long long* rows_scored_src;
     const unsigned long long* stats_src;
+    // fused peer exchange of the row-sharded search (ex_world > 1): this rank's k records are stored straight into
+    // every peer's record area over NVLink, a per-(query parity, rank) flag publishes them, and the same kernel
+    // waits for the other ranks' records and merges all of them into `out`
+    uint32_t ex_world, ex_rank, ex_kmax, ex_seq;
+    uint32_t ex_k;                              // records every rank contributes (the caller's take count)
+    otters_topk_record* ex_records[kMaxPeers];  // peer p's record area as mapped here: [2][world][k_max]
+    uint32_t* ex_flags[kMaxPeers];              // peer p's flag area: [2][world]
 };
 int launch_select(const SelectParams& p, cudaStream_t s);
 
@@ -276,7 +284,7 @@ struct MetaKernelParams {
     uint32_t* row_mask;          // words
     unsigned long long* stats;   // [0] evaluated chunks, [1] vectors_compared
 };
-int launch_prune(const MetaKernelParams& p, cudaStream_t s);
+int launch_prune(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s);
 int launch_rowmask(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s);
 int launch_count_all_chunks(const MetaKernelParams& p, cudaStream_t s);
 

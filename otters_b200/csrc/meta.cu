@@ -15,6 +15,8 @@
 namespace otters {
 namespace {
 
+__device__ __forceinline__ bool chunk_leaf_rule(const DevLeaf& lf, uint32_t ch);
+
 template <typename T>
 __device__ __forceinline__ bool range_sat(int op, T mn, T mx, T t) {
     switch (op) {
@@ -28,7 +30,11 @@ __device__ __forceinline__ bool range_sat(int op, T mn, T mx, T t) {
 }
 
 __device__ __forceinline__ bool chunk_leaf_sat(const DevLeaf& lf, uint32_t ch) {
-    if (lf.non_null[ch] == 0) return false;  // every rule is ANDed with non_null > 0
+    const bool has_rows = __ldg(lf.non_null + ch) != 0;  // every rule is ANDed with non_null > 0
+    return chunk_leaf_rule(lf, ch) && has_rows;
+}
+
+__device__ __forceinline__ bool chunk_leaf_rule(const DevLeaf& lf, uint32_t ch) {
     switch (lf.exec) {
     case LEAF_I32: return range_sat<int32_t>(lf.op, ((const int32_t*)lf.zmin)[ch], ((const int32_t*)lf.zmax)[ch], lf.i32);
     case LEAF_I64: return range_sat<int64_t>(lf.op, ((const int64_t*)lf.zmin)[ch], ((const int64_t*)lf.zmax)[ch], lf.i64);
@@ -40,28 +46,44 @@ __device__ __forceinline__ bool chunk_leaf_sat(const DevLeaf& lf, uint32_t ch) {
         const uint64_t* w = lf.bloom + (size_t)ch * lf.bloom_stride;
         const uint64_t m = lf.bloom_mbits[ch];
         const uint32_t kh = lf.bloom_k[ch];
+        bool all = true;  // every probe is issued (no early exit) so that the word loads overlap
         for (uint32_t i = 0; i < kh; ++i) {
             uint64_t bit = (lf.h1 + (uint64_t)i * lf.h2) % m;
-            if (!((w[bit >> 6] >> (bit & 63)) & 1ull)) return false;
+            all &= ((__ldg(w + (bit >> 6)) >> (bit & 63)) & 1ull) != 0;
         }
-        return true;
+        return all;
     }
     }
 }
 
-// K0: one thread per chunk
-__global__ void prune_kernel(const __grid_constant__ MetaKernelParams p) {
+// K0: one thread per chunk.  The lowered filter is staged in shared memory first and every leaf is evaluated
+// unconditionally, so the zonemap / Bloom loads of all leaves are in flight together (three dependent memory
+// round trips in total instead of one chain per leaf).
+constexpr uint32_t kPruneSmemLeaves = 64;
+
+__global__ void __launch_bounds__(64) prune_kernel(const __grid_constant__ MetaKernelParams p, uint32_t n_leaves) {
+    __shared__ __align__(16) DevLeaf s_leaves[kPruneSmemLeaves];
+    __shared__ uint32_t s_off[kPruneSmemLeaves + 1];
+    const DevLeaf* leaves = p.leaves;
+    const uint32_t* clause_off = p.clause_off;
+    if (n_leaves <= kPruneSmemLeaves && p.n_clauses <= kPruneSmemLeaves) {
+        const uint32_t words = n_leaves * (uint32_t)(sizeof(DevLeaf) / 4);
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(s_leaves)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.leaves) + i);
+        for (uint32_t i = threadIdx.x; i <= p.n_clauses; i += blockDim.x) s_off[i] = __ldg(p.clause_off + i);
+        __syncthreads();
+        leaves = s_leaves;
+        clause_off = s_off;
+    }
     const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     uint32_t len = 0;
     if (ch < p.n_chunks) {
         keep = true;
-        for (uint32_t ci = 0; ci < p.n_clauses && keep; ++ci) {
+        for (uint32_t ci = 0; ci < p.n_clauses; ++ci) {
             bool any = false;
-            for (uint32_t li = p.clause_off[ci]; li < p.clause_off[ci + 1] && !any; ++li) {
-                any = chunk_leaf_sat(p.leaves[li], ch);
-            }
-            keep = any;
+            for (uint32_t li = clause_off[ci]; li < clause_off[ci + 1]; ++li) any |= chunk_leaf_sat(leaves[li], ch);
+            keep &= any;
         }
         const uint64_t base = (uint64_t)ch * p.chunk_size;
         len = (uint32_t)(base + p.chunk_size <= p.n_rows ? p.chunk_size : p.n_rows - base);
@@ -124,9 +146,9 @@ __global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ Me
 
 }  // namespace
 
-int launch_prune(const MetaKernelParams& p, cudaStream_t s) {
+int launch_prune(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s) {
     if (p.n_chunks == 0) return OTTERS_OK;
-    prune_kernel<<<(p.n_chunks + 255) / 256, 256, 0, s>>>(p);
+    prune_kernel<<<(p.n_chunks + 63) / 64, 64, 0, s>>>(p, n_leaves);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

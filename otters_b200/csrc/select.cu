@@ -60,6 +60,25 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
 // so position order == qid order among equal keys); lists 1.. are this query's per-CTA lists.
 // tag = list << 11 | position  (position < 2048 because k <= 1024 in the fused path)
 constexpr uint32_t kPosBits = 11;
+constexpr uint32_t kRankSelectElems = 2048;  // largest working set served by the rank-counting fast paths
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ otters_topk_record ld_record_volatile(const otters_topk_record* p) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    otters_topk_record r;
+    r.row = (uint64_t)a | ((uint64_t)b << 32);
+    r.score = __uint_as_float(c);
+    r.qid = d;
+    return r;
+}
 
 // WITH_PREV = false is the single-query hot path: no running list, all keys distinct, keys sorted alone.
 template <bool WITH_PREV>
@@ -104,7 +123,54 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
     uint64_t* keys = s_keys;
     uint32_t* src = s_src;
     uint32_t P = 0;
-    for (;;) {
+    bool done = false;
+    if (!WITH_PREV && L > 0 && p.n_lists * L <= kRankSelectElems) {
+        // Fast path of the single-query case (all keys distinct): every thread loads one element of the union of
+        // prefixes and finds its final position by counting the better elements — no sorting network, two barriers.
+        const uint32_t nel_max = p.n_lists * L;
+        uint64_t* ranked = s_keys + kSelectSmemElems / 2;
+        if (threadIdx.x == 0) {
+            s_nel = 0;
+            s_retry = 0;
+        }
+        __syncthreads();
+        uint32_t loc = 0;
+        for (uint32_t e = threadIdx.x; e < nel_max; e += blockDim.x) {
+            const uint32_t l = e / L, i = e - l * L;
+            const uint64_t key = i < p.cta_counts[l] ? p.cta_keys[(size_t)l * p.list_stride + i] : 0ull;
+            s_keys[e] = key;
+            loc += key != 0ull;
+        }
+        if (loc) atomicAdd(&s_nel, loc);
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < nel_max; e += blockDim.x) {
+            const uint64_t key = s_keys[e];
+            if (key == 0ull) continue;
+            uint32_t rank = 0;
+#pragma unroll 8
+            for (uint32_t j = 0; j < nel_max; ++j) rank += s_keys[j] > key;
+            if (rank < kk) ranked[rank] = key;
+        }
+        __syncthreads();
+        if (L < maxcount) {  // was any list cut short in a way that matters?
+            if (s_nel < kk) {
+                if (threadIdx.x == 0) s_retry = 1;
+            } else if (kk > 0) {
+                const uint64_t tk = ranked[kk - 1];
+                for (uint32_t l = threadIdx.x; l < p.n_lists; l += blockDim.x)
+                    if (p.cta_counts[l] > L && p.cta_keys[(size_t)l * p.list_stride + L] > tk) s_retry = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_retry) {
+            keys = ranked;
+            done = true;
+        } else {
+            L = L * 4 < maxcount ? L * 4 : maxcount;
+        }
+        __syncthreads();
+    }
+    while (!done) {
         if (threadIdx.x == 0) {
             s_nel = 0;
             s_retry = 0;
@@ -160,39 +226,108 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
     }
 
     // emit the best kk, ordered
-    for (uint32_t i = threadIdx.x; i < kk; i += blockDim.x) {
+    const bool exchange = p.ex_world > 1;
+    const uint32_t par = p.ex_seq & 1u;
+    for (uint32_t i = threadIdx.x; i < (exchange ? p.ex_k : (p.records ? p.k : kk)); i += blockDim.x) {
         Cand c;
-        c.key = keys[i];
+        c.key = 0ull;
         c.qid = p.qid;
-        if (WITH_PREV) {
-            uint32_t s = src[i];
-            uint32_t l = s >> kPosBits, pos = s & ((1u << kPosBits) - 1u);
-            if (l == 0) c.qid = p.prev[pos].qid;
-        }
         c.pad = 0;
-        p.out[i] = c;
-        if (p.records) {
-            otters_topk_record r;
-            r.row = p.map.global_row(key_row(c.key));
-            r.score = key_score(c.key, p.take_max != 0);
-            r.qid = c.qid;
-            p.records[i] = r;
+        if (i < kk) {
+            c.key = keys[i];
+            if (WITH_PREV) {
+                uint32_t s = src[i];
+                uint32_t l = s >> kPosBits, pos = s & ((1u << kPosBits) - 1u);
+                if (l == 0) c.qid = p.prev[pos].qid;
+            }
+            if (!exchange) p.out[i] = c;
         }
-    }
-    if (p.records) {
-        for (uint32_t i = kk + threadIdx.x; i < p.k; i += blockDim.x) {
+        if (exchange || p.records) {
             otters_topk_record r;
             r.row = 0xFFFFFFFFFFFFFFFFull;
             r.score = 0.f;
             r.qid = 0;
-            p.records[i] = r;
+            if (i < kk) {
+                r.row = p.map.global_row(key_row(c.key));
+                r.score = key_score(c.key, p.take_max != 0);
+                r.qid = c.qid;
+            }
+            if (p.records) p.records[i] = r;
+            if (exchange)  // peer stores over NVLink (the own area included)
+                for (uint32_t pr = 0; pr < p.ex_world; ++pr) p.ex_records[pr][((size_t)par * p.ex_world + p.ex_rank) * p.ex_kmax + i] = r;
+        }
+    }
+    uint32_t n_out = kk;
+    if (exchange) {
+        // publish: every record store above is ordered before the flag by the system-scope fence + release
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < p.ex_world) st_release_sys_u32(p.ex_flags[threadIdx.x] + par * p.ex_world + p.ex_rank, p.ex_seq);
+        // wait for the records of every rank for this query
+        if (threadIdx.x < p.ex_world) {
+            const uint32_t* f = p.ex_flags[p.ex_rank] + par * p.ex_world + threadIdx.x;
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u32(f) != p.ex_seq) {
+                if (clock64() - t0 > 20000000000ll) __trap();  // a rank never arrived (~10 s): fail instead of hanging
+            }
+        }
+        __syncthreads();
+        // merge world * k records (same order everywhere: better score, lower global row, lower query index)
+        const otters_topk_record* mine = p.ex_records[p.ex_rank] + (size_t)par * p.ex_world * p.ex_kmax;
+        const uint32_t n_in = p.ex_world * p.ex_k;
+        if (threadIdx.x == 0) s_nel = 0;
+        __syncthreads();
+        uint32_t loc = 0;
+        uint32_t P2 = n_in <= kRankSelectElems ? n_in : next_pow2(n_in);
+        for (uint32_t e = threadIdx.x; e < P2; e += blockDim.x) {
+            uint64_t key = 0ull;
+            uint32_t tag = 0xFFFFFFFFu;
+            if (e < n_in) {
+                const otters_topk_record r = ld_record_volatile(mine + (size_t)(e / p.ex_k) * p.ex_kmax + e % p.ex_k);
+                if (r.row != 0xFFFFFFFFFFFFFFFFull) {
+                    key = make_key(r.score, (uint32_t)r.row, p.take_max != 0);
+                    tag = r.qid;
+                    ++loc;
+                }
+            }
+            s_keys[e] = key;
+            s_src[e] = tag;
+        }
+        if (loc) atomicAdd(&s_nel, loc);
+        __syncthreads();
+        n_out = s_nel < p.ex_k ? s_nel : p.ex_k;
+        if (n_in <= kRankSelectElems) {
+            for (uint32_t e = threadIdx.x; e < n_in; e += blockDim.x) {
+                const uint64_t key = s_keys[e];
+                if (key == 0ull) continue;
+                const uint32_t tag = s_src[e];
+                uint32_t rank = 0;
+#pragma unroll 4
+                for (uint32_t j = 0; j < n_in; ++j) rank += before(s_keys[j], s_src[j], key, tag);
+                if (rank < n_out) {
+                    Cand c;
+                    c.key = key;
+                    c.qid = tag;
+                    c.pad = 0;
+                    p.out[rank] = c;
+                }
+            }
+        } else {
+            block_bitonic<true>(s_keys, s_src, P2);
+            for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+                Cand c;
+                c.key = s_keys[i];
+                c.qid = s_src[i];
+                c.pad = 0;
+                p.out[i] = c;
+            }
         }
     }
     if (threadIdx.x == 0) {
-        *p.out_count = kk;
-        if (p.tau_out) *p.tau_out = (kk == p.k && kk > 0) ? keys[kk - 1] : 0ull;
+        *p.out_count = n_out;
+        if (p.tau_out) *p.tau_out = (!exchange && kk == p.k && kk > 0) ? keys[kk - 1] : 0ull;
         if (p.hdr) {
-            p.hdr->count = kk;
+            p.hdr->count = n_out;
             p.hdr->rows_scored = p.rows_scored_src ? *p.rows_scored_src : 0ull;
             p.hdr->stats[0] = p.stats_src ? p.stats_src[0] : 0ull;
             p.hdr->stats[1] = p.stats_src ? p.stats_src[1] : 0ull;
@@ -230,6 +365,34 @@ merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int
     }
     if (loc) atomicAdd(&s_valid, loc);
     __syncthreads();
+    if (n <= kRankSelectElems) {
+        // few records (world * k): every thread counts the records ordered before its own — no sorting network
+        const uint32_t kr = s_valid < k ? s_valid : k;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const uint64_t key = keys[e];
+            if (key == 0ull) continue;
+            const uint32_t tag = src[e];
+            uint32_t rank = 0;
+#pragma unroll 4
+            for (uint32_t j = 0; j < n; ++j) rank += before(keys[j], src[j], key, tag);
+            if (rank < kr) {
+                Cand c;
+                c.key = key;
+                c.qid = tag;
+                c.pad = 0;
+                out[rank] = c;
+            }
+        }
+        if (threadIdx.x == 0) {
+            *out_count = kr;
+            if (hdr) {
+                hdr->count = kr;
+                hdr->rows_scored = rows_scored_src ? *rows_scored_src : 0ull;
+                hdr->stats[0] = hdr->stats[1] = 0ull;
+            }
+        }
+        return;
+    }
     if (P > kSelectSmemElems) block_bitonic<true>(scratch_keys, scratch_src, P);
     else block_bitonic<true>(reinterpret_cast<uint64_t*>(sm), reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8), P);
     uint32_t kk = s_valid < k ? s_valid : k;
@@ -371,6 +534,7 @@ int launch_select(const SelectParams& p, cudaStream_t s) {
     uint32_t P = 2;
     while (P < n_lists * L) P <<= 1;
     uint32_t block = P / 2 < 128 ? 128 : (P / 2 > 1024 ? 1024 : P / 2);
+    if (!p.prev || p.ex_world > 1) block = 1024;  // rank-counting paths: one element per thread
     if (p.prev) select_kernel<true><<<1, block, kSelectSmemBytes, s>>>(p);
     else select_kernel<false><<<1, block, kSelectSmemBytes, s>>>(p);
     OTTERS_CUDA(cudaGetLastError());

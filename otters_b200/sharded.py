@@ -95,6 +95,79 @@ class CudaShard:
         self.local = torch.empty((k_max, 16), dtype=torch.uint8, device=dev)
         self.gathered = torch.empty((self.world * k_max, 16), dtype=torch.uint8, device=dev)
         self.k_max = k_max
+        self.peer = None      # _ffi.PeerExchange once enable_peer_exchange() succeeded
+        self.peer_error = None
+        self._seq = 0
+
+    # ---- fused exchange over peer memory -------------------------------------------------------------------
+    def enable_peer_exchange(self) -> bool:
+        """Maps every rank's record/flag areas into every process (torch symmetric memory: CUDA VMM handles
+        exchanged over the process group) so that ``otters_query_exchange`` can store records straight into the
+        peers' HBM over NVLink.  Returns False (and keeps the NCCL all-gather path) when the mapping is unavailable."""
+        if self.world < 2 or self.world > 8:
+            return False
+        torch, dist, ffi = self._torch, self._dist, self._ffi
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            flag_bytes = 256  # 2 * world uint32, padded
+            rec_bytes = 2 * self.world * self.k_max * 16
+            dev = torch.device("cuda", self.ctx.device)
+            buf = symm.empty(flag_bytes + rec_bytes, dtype=torch.uint8, device=dev)
+            group = self.group if self.group is not None else dist.group.WORLD
+            try:
+                hdl = symm.rendezvous(buf, group=group)
+            except TypeError:
+                hdl = symm.rendezvous(buf, group.group_name)
+            buf.zero_()
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+                raise RuntimeError("symmetric memory returned no peer pointers")
+            self._symm = (buf, hdl)  # keep the mapping alive
+            self._peer_rec = (C.c_void_p * self.world)(*[p + flag_bytes for p in ptrs])
+            self._peer_flg = (C.c_void_p * self.world)(*ptrs)
+            self.peer = ffi.PeerExchange(self.world, self.rank, self.k_max, C.cast(self._peer_rec, C.POINTER(C.c_void_p)),
+                                         C.cast(self._peer_flg, C.POINTER(C.c_void_p)))
+        except Exception as e:  # no symmetric memory on this box / build: NCCL path stays
+            self.peer = None
+            self.peer_error = f"{type(e).__name__}: {e}"
+        # every rank must take the same path
+        ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            self.peer = None
+        return self.peer is not None
+
+    def search_fused(self, vq, fp, k: int, fetch: bool = True, want_stats: bool = False):
+        """Local search with the exchange and the merge fused into the selection kernel (no NCCL call)."""
+        ffi = self._ffi
+        assert self.peer is not None
+        self._seq += 1
+        st = ffi.QueryStats()
+        out_len = C.c_uint64(0)
+        if self.is_meta:
+            args = (None, self.store.handle, C.byref(vq), fp.byref() if fp else None)
+        else:
+            self.store._flush()
+            args = (self.store._handle(), None, C.byref(vq), None)
+        if fetch:
+            idx, score, qid = np.zeros(k, np.uint64), np.zeros(k, np.float32), np.zeros(k, np.uint32)
+            rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, idx.ctypes.data_as(ffi.c_u64p),
+                                           score.ctypes.data_as(ffi.c_f32p), qid.ctypes.data_as(ffi.c_u32p), k, C.byref(out_len),
+                                           C.byref(st) if (want_stats or self.is_meta) else None)
+        else:
+            rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, None, None, None, 0, None,
+                                           C.byref(st) if want_stats else None)
+        if rc != 0:
+            from .types import OttersError
+
+            raise OttersError(ffi.last_error())
+        if not fetch:
+            return None, st
+        m = min(out_len.value, k)
+        return (idx[:m], score[:m], qid[:m]), st
 
     def enqueue(self, vq, fp, k: int, want_stats: bool = False):
         """Enqueues local search + all-gather on the context's stream; returns the gathered record tensor."""

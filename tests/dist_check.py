@@ -72,9 +72,32 @@ for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob
         assert tot.tolist() == [ostats["evaluated_chunks"], ostats["vectors_compared"], ostats["total_chunks"]], (tot.tolist(), ostats)
         vsc = ob.VecStore(dim, ctx)
         vsc.add_vectors(vectors[g])
-        got = CudaShard(vsc, 0, k, block_rows=cs).search(vq, None, k, tt == ob.TakeType.Max)
+        shv = CudaShard(vsc, 0, k, block_rows=cs)
+        got = shv.search(vq, None, k, tt == ob.TakeType.Max)
         assert_same_results(got, want, f"cyclic vec {metric.name} nq={nq} rank {rank}")
+        # fused exchange over peer memory (select + NVLink stores + flags + merge in one kernel), when the box maps it
+        if shv.enable_peer_exchange():
+            fused_ok = True
+            for rep in range(3):  # both parities of the double-buffered areas
+                got, _ = shv.search_fused(vq, None, k)
+                assert_same_results(got, want, f"fused vec {metric.name} nq={nq} rank {rank} rep {rep}")
+            assert shardc.enable_peer_exchange()
+            got, st = shardc.search_fused(vq, fp, k, want_stats=True)
+            assert_same_results(got, (oi, os_, oq), f"fused meta {metric.name} nq={nq} rank {rank}")
+            tot = torch.tensor([st.evaluated_chunks, st.vectors_compared, st.total_chunks], dtype=torch.int64, device="cuda")
+            dist.all_reduce(tot)
+            assert tot.tolist() == [ostats["evaluated_chunks"], ostats["vectors_compared"], ostats["total_chunks"]], (tot.tolist(), ostats)
+            # a rank whose shard is empty still takes part
+            vse = ob.VecStore(dim, ctx)
+            if rank == 0:
+                vse.add_vectors(vectors[:500])
+            she = CudaShard(vse, 0, k)
+            assert she.enable_peer_exchange()
+            got, _ = she.search_fused(vq, None, k)
+            assert_same_results(got, ora.vecstore_query(vectors[:500], q, metric, tt, k), f"fused empty shard {metric.name} nq={nq}")
+        elif rank == 0:
+            print("peer exchange unavailable:", shv.peer_error)
 dist.barrier()
 if rank == 0:
-    print("DIST_CHECK_OK")
+    print("DIST_CHECK_OK", "fused_exchange=%s" % ("fused_ok" in globals()))
 dist.destroy_process_group()
