@@ -35,7 +35,7 @@ class Context:
     def set_tuning(self, warps_per_cta=0, slots_per_warp=0, kc_floats=0, ctas_per_sm=0, unit_rows=0, disable_fused_predicate=0,
                    batch_mode=0, batch_cta_group=0, timing=0) -> None:
         """batch_mode: 0 = automatic, 1 = always serve query batches with the tcgen05 kernel, 2 = never.
-        batch_cta_group: 0 = automatic (CTA pairs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2).
+        batch_cta_group: 0 = automatic (single CTAs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2).
         timing: per-phase CUDA events; 0 = only for blocking MetaStore queries with stats, 1 = always, 2 = never."""
         t = _ffi.ScanTuning(warps_per_cta, slots_per_warp, kc_floats, ctas_per_sm, unit_rows, disable_fused_predicate, batch_mode,
                             batch_cta_group, timing)

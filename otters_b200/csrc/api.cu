@@ -3,6 +3,7 @@
 // / meta.cu / store.cu; there is no CPU fallback.
 #include <float.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -450,8 +451,11 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     uint32_t grid = (uint32_t)c->sm_count * ctas_per_sm;
     uint32_t unit_rows = t.unit_rows ? t.unit_rows : kMaxUnitRows;
     if (unit_rows != 32 && unit_rows != 64 && unit_rows != 128) unit_rows = kMaxUnitRows;
+    // small stores (e.g. one shard of a row-sharded search) need finer units, or the last units of the dynamic schedule
+    // leave most warps idle: measured on a 1.25M x 768 shard, 32-row units scan in 0.293 ms against 0.330 ms for 128-row
+    // units (profiles/r1_unit_rows_shard.log); large stores keep 128-row units (fewer unit boundaries)
     if (!t.unit_rows)
-        while (unit_rows > 32 && n_rows / unit_rows < (uint64_t)grid * W * 2) unit_rows >>= 1;
+        while (unit_rows > 32 && n_rows / unit_rows < (uint64_t)grid * W * 16) unit_rows >>= 1;
     pl.unit_rows = unit_rows;
     pl.n_units = (uint32_t)((n_rows + unit_rows - 1) / unit_rows);
     uint32_t need_ctas = (pl.n_units + W - 1) / W;
@@ -553,7 +557,9 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     cudaStream_t s = c->stream;
     const uint32_t dim_pad = st->pitch;
     const uint64_t k_eff = run->k_eff;
-    const uint32_t k = (uint32_t)k_eff;
+    // every CTA keeps a few more candidates than asked for: the best EXCLUDED pair then lies well below the k-th score,
+    // so the certificate below rarely fails on a near-tie between the k-th and (k+1)-th pair
+    const uint32_t k = (uint32_t)std::min<uint64_t>(kMaxFusedK, k_eff + std::max<uint64_t>(k_eff / 8, 16));
     const uint32_t cap = (uint32_t)pow2_at_least(std::max<uint32_t>(2 * k, 64));
     const uint32_t nq_pad = (uint32_t)round_up(q->nq, kBatchQueries);
     const bool take_max = q->take_type == OTTERS_TAKE_MAX;
@@ -583,8 +589,9 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     rc = launch_batch_delta(q->metric, st->dim, d_qmax2, st->d_minv_bits, d_delta, s);
     if (rc) return rc;
 
-    // CTA pairs (cta_group::2) unless the tuning asks for single CTAs or there is too little work to pair up
-    const uint32_t cg = (c->tuning.batch_cta_group == 1 || c->sm_count < 2) ? 1 : 2;
+    // single CTAs by default: with the raw-hi operand split they measured faster than CTA pairs (6.04 vs 6.33 ms on
+    // 1M x 768 x 1024 queries, profiles/r1_batch_experiments.log); tcgen05 cta_group::2 pairs stay selectable
+    const uint32_t cg = (c->tuning.batch_cta_group == 2 && c->sm_count >= 2) ? 2 : 1;
     const uint32_t tile_rows = kBatchRows * cg;
     const uint32_t n_rowtiles = (uint32_t)((st->n + tile_rows - 1) / tile_rows);
     const uint64_t n_tiles = (uint64_t)n_rowtiles * (nq_pad / kBatchQueries);
@@ -671,7 +678,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
                             c->d_rows_scored, stats_src, s, c->d_batch_info + 1);
     if (rc) return rc;
     if (d_records_out) {
-        rc = launch_cands_to_records(c->d_list[0], c->d_list_count, k, map, take_max, d_records_out, s);
+        rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, take_max, d_records_out, s);
         if (rc) return rc;
     }
     rec_event(c, 5);
@@ -703,6 +710,10 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             ok = take_max ? (x + delta < e_k) : (x - delta > e_k);
         }
     }
+    if (getenv("OTTERS_BATCH_TRACE"))
+        fprintf(stderr, "[otters batch] k=%llu count=%u flags=%u max_err=%g delta=%g excl=%g e_k=%g verified=%d\n",
+                (unsigned long long)k_eff, hdr->count, flags, max_err, delta, excl ? key_score((uint64_t)excl << 32, take_max) : NAN,
+                hdr->count ? key_score(list[hdr->count - 1].key, take_max) : NAN, (int)ok);
     c->last.batch_max_err = max_err;
     c->last.batch_delta = delta;
     c->last.batch_candidates = 0;

@@ -370,7 +370,8 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     uint64_t* bar_empty = bar_cast + STAGES;                      // [STAGES] MMAs reading the stage completed
     uint64_t* bar_tfull = bar_empty + STAGES;                     // [2] accumulator complete
     uint64_t* bar_tempty = bar_tfull + 2;                         // [2] (rank 0) accumulator drained by every epilogue thread
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    uint64_t* bar_full2 = bar_tempty + 2;                         // [STAGES] (rank 0, CG = 2) the loads of BOTH CTAs landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full2 + STAGES);
     CtaHdr* hdr = reinterpret_cast<CtaHdr*>(aux + 128);
     uint64_t* cand_keys = reinterpret_cast<uint64_t*>(aux + 256);
     uint32_t* cand_qids = reinterpret_cast<uint32_t*>(aux + 256 + (size_t)p.cap * 8);
@@ -383,12 +384,13 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     if (warp == 1 && lane == 0) {
         for (uint32_t s = 0; s < STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_cast[s], 128 * CG);
+            mbar_init(&bar_cast[s], CG);  // one elected arrival per CTA of the pair
             mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_full2[s], CG);
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(&bar_tfull[b], 1);
-            mbar_init(&bar_tempty[b], 128 * CG);
+            mbar_init(&bar_tempty[b], CG);
         }
         fence_mbar_init();
         hdr->tau = 0ull;
@@ -407,6 +409,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
+    const bool raw_hi = (p.dbg & 16u) == 0;  // default; bit 16 of the debug word restores the in-place rounded-hi split for A/B runs
     const uint32_t n_rowtiles = (p.n_rows + G::TILE_ROWS - 1) / G::TILE_ROWS;
     const uint32_t n_tiles = n_rowtiles * p.n_qtiles;
     const uint32_t nkb = p.nkb;
@@ -447,24 +450,61 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 const uint32_t d_tmem = tmem_base + buf * BN;
                 for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-                    mbar_wait(&bar_full[s], ph);
-                    if constexpr (CG == 2) mbar_wait_cluster(&bar_cast[s], ph);
-                    else mbar_wait(&bar_cast[s], ph);
-                    tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t d_vh = umma_desc_sw128(sa), d_vl = umma_desc_sw128(sa + A_BYTES);
                     const uint64_t d_qh = umma_desc_sw128(sa + 2 * A_BYTES), d_ql = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+                    if (raw_hi) {
+                        // the landed fp32 tile itself is the hi operand (the tensor core reads its upper 19 bits), so two
+                        // thirds of the stage's MMAs start as soon as the loads land and hide the split of the lo tile
+                        if constexpr (CG == 2) mbar_wait_cluster(&bar_full2[s], ph);
+                        else mbar_wait(&bar_full[s], ph);
+                        tc_fence_after();
 #pragma unroll
-                    for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);  // K advance inside the swizzle atom
-                        umma_tf32_cg<CG>(d_tmem, d_vl + adv, d_qh + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
-                        umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_ql + adv, G::IDESC, 1u);
-                        umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, 1u);
+                        for (uint32_t kk = 0; kk < BK / UK; ++kk) {
+                            const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);  // K advance inside the swizzle atom
+                            umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_ql + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
+                            umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, 1u);
+                        }
+                        if constexpr (CG == 2) mbar_wait_cluster(&bar_cast[s], ph);
+                        else mbar_wait(&bar_cast[s], ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t kk = 0; kk < BK / UK; ++kk) {
+                            const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);
+                            umma_tf32_cg<CG>(d_tmem, d_vl + adv, d_qh + adv, G::IDESC, 1u);
+                        }
+                    } else {
+                        mbar_wait(&bar_full[s], ph);
+                        if constexpr (CG == 2) mbar_wait_cluster(&bar_cast[s], ph);
+                        else mbar_wait(&bar_cast[s], ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
+                            const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);  // K advance inside the swizzle atom
+                            umma_tf32_cg<CG>(d_tmem, d_vl + adv, d_qh + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
+                            umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_ql + adv, G::IDESC, 1u);
+                            umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, 1u);
+                        }
                     }
                     umma_commit_cg<CG>(&bar_empty[s]);
                 }
                 umma_commit_cg<CG>(&bar_tfull[buf]);
                 ++tn;
+            }
+        }
+    } else if (warp == 3) {
+        // ===== relay (CTA pairs with raw hi operands): tells rank 0 that this CTA's loads of a stage have landed =====
+        if (CG == 2 && raw_hi && lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t t = unit; t < n_tiles; t += n_units) {
+                const uint32_t rt = t / p.n_qtiles;
+                if (!tile_live<CG>(p, rt)) continue;
+                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&bar_full[s], ph);
+                    if (rank != 0) mbar_arrive_remote(&bar_full2[s], 0);
+                    else mbar_arrive(&bar_full2[s]);
+                }
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -479,6 +519,20 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 mbar_wait(&bar_full[s], ph);
                 float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
                 float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+                if (raw_hi) {
+                    // lo = x - (what the tensor core will read of x: its upper 19 bits), rounded to tf32; x stays as it is
+#pragma unroll
+                    for (uint32_t i = 0; i < A_BYTES / 16 / 128; ++i) {
+                        const uint32_t idx = tt + i * 128;
+                        const float4 x = hi[idx];
+                        float4 l;
+                        l.x = rna_tf32(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+                        l.y = rna_tf32(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+                        l.z = rna_tf32(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+                        l.w = rna_tf32(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                        lo[idx] = l;
+                    }
+                } else
 #pragma unroll
                 for (uint32_t i = 0; i < ((p.dbg & 2u) ? 0u : A_BYTES / 16 / 128); ++i) {
                     const uint32_t idx = tt + i * 128;
@@ -496,8 +550,12 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                     lo[idx] = l;
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_cast[s], 0);
-                else mbar_arrive(&bar_cast[s]);
+                named_bar_sync(2, 128);  // the four split warps; then ONE thread signals (a cluster-scope release per
+                                         // thread costs a gpu-wide fence each: profiles/r1_batch_c2_hot_sass.txt)
+                if (tt == 0) {
+                    if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_cast[s], 0);
+                    else mbar_arrive(&bar_cast[s]);
+                }
             }
         }
     } else if (warp >= 8) {
@@ -564,8 +622,11 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 }
             }
             tc_fence_before();
-            if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_tempty[buf], 0);
-            else mbar_arrive(&bar_tempty[buf]);
+            named_bar_sync(3, 128);  // every epilogue thread has drained its TMEM lanes; one thread signals
+            if (warp == 8 && lane == 0) {
+                if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_tempty[buf], 0);
+                else mbar_arrive(&bar_tempty[buf]);
+            }
             ++tn;
             // adopt the grid-wide threshold once per tile
             if (warp == 8 && lane == 0) {

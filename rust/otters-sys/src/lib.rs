@@ -97,7 +97,65 @@ pub struct otters_filter {
     pub leaves: *const otters_leaf,
 }
 
+/// otters_shard_map: how local rows of a shard map to global row ids (contiguous or block-cyclic).
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct otters_shard_map {
+    pub row_base: u64,
+    pub world: u32,
+    pub rank: u32,
+    pub block_rows: u64,
+}
+
+/// otters_topk_record: one entry of a shard's local top-k as it travels between GPUs.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct otters_topk_record {
+    pub row: u64,   // global row id; u64::MAX = empty slot
+    pub score: f32,
+    pub qid: u32,
+}
+
+/// otters_peer_exchange: record / flag areas of every rank as mapped into this process (CUDA IPC / VMM).
+#[repr(C)]
+pub struct otters_peer_exchange {
+    pub world: u32,
+    pub rank: u32,
+    pub k_max: u64,
+    pub peer_records: *const *mut c_void,
+    pub peer_flags: *const *mut u32,
+}
+
+/// otters_scan_tuning: profiling knobs (0 = automatic everywhere); results never depend on them.
+#[repr(C)]
+#[derive(Default, Clone, Copy)]
+pub struct otters_scan_tuning {
+    pub warps_per_cta: u32,
+    pub slots_per_warp: u32,
+    pub kc_floats: u32,
+    pub ctas_per_sm: u32,
+    pub unit_rows: u32,
+    pub disable_fused_predicate: u32,
+    pub batch_mode: u32,       // 0 auto, 1 always the tcgen05 kernel for batches, 2 never
+    pub batch_cta_group: u32,  // 0 auto (CTA pairs), 1 single CTAs, 2 pairs
+    pub timing: u32,           // 0 auto, 1 always record phase events, 2 never
+}
+
 extern "C" {
+    pub fn otters_ctx_set_tuning(ctx: *mut otters_ctx, t: *const otters_scan_tuning) -> c_int;
+    /// Row-sharded search, NCCL flavour: the local top-k stays in HBM as k records ...
+    pub fn otters_query_local_device(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query,
+                                     filter: *const otters_filter, map: *const otters_shard_map, d_records: *mut c_void,
+                                     stats: *mut otters_query_stats) -> c_int;
+    /// ... and after the all-gather every rank merges world * k records.
+    pub fn otters_topk_merge_device(ctx: *mut otters_ctx, d_records: *const c_void, n_records: u64, k: u64, take_type: i32,
+                                    out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64) -> c_int;
+    /// Row-sharded search with the exchange fused into the selection kernel (peer stores over NVLink, no NCCL call).
+    pub fn otters_query_exchange(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query,
+                                 filter: *const otters_filter, map: *const otters_shard_map, ex: *const otters_peer_exchange,
+                                 seq: u64, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64,
+                                 out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
+
     pub fn otters_ctx_create(device: c_int, cuda_stream: *mut c_void, out: *mut *mut otters_ctx) -> c_int;
     pub fn otters_ctx_destroy(ctx: *mut otters_ctx) -> c_int;
     pub fn otters_last_error() -> *const c_char;

@@ -9,9 +9,9 @@ ctx = ob.default_context(0)
 s = ob.VecStore(dim, ctx); s.add_synthetic(0, rows, 0x7735)
 q = synth_fill_np(0, nq, dim, 0xBEEF)
 for cg in (1, 2):
-    for dbg in (0, 4, 5, 6, 7):
+    for dbg in (0, 16, 4, 20):
         os.environ["OTTERS_BATCH_DBG"] = str(dbg)
-        ctx.set_tuning(batch_mode=1, batch_cta_group=cg)
+        ctx.set_tuning(batch_mode=1, batch_cta_group=cg, timing=1)
         ts = []
         for _ in range(3):
             try:
@@ -19,4 +19,5 @@ for cg in (1, 2):
             except Exception as e:
                 print("err", e)
             ts.append(ctx.last_work()["scan_ms"])
-        print(f"cg={cg} dbg={dbg:2d} kernel_ms={min(ts):.3f}", flush=True)
+        w = ctx.last_work()
+        print(f"cg={cg} dbg={dbg:2d} kernel_ms={min(ts):.3f} used={w['batch_used']} fallback={w['batch_fallback']} max_err={w['batch_max_err']:.3e} delta={w['batch_delta']:.3e}", flush=True)

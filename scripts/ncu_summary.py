@@ -5,7 +5,8 @@ rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
-want = ['Kernel Name','gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+want = ['Kernel Name','gpu__time_duration.sum','sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed','sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+ 'sm__inst_executed_pipe_tensor.sum','sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed','lts__t_bytes.sum','lts__throughput.avg.pct_of_peak_sustained_elapsed','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
  'sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','launch__grid_size','launch__block_size','launch__shared_mem_per_block_dynamic',
  'smsp__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
  'lts__t_sector_hit_rate.pct','sm__throughput.avg.pct_of_peak_sustained_elapsed','smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio' ,
@@ -19,7 +20,10 @@ want = ['Kernel Name','gpu__time_duration.sum','dram__bytes_read.sum','dram__byt
  'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio','smsp__average_warps_issue_stalled_selected_per_issue_active.ratio']
 for r in rows[2:3]:
     for w in want:
-        if w in hdr: print(f"{w:90s} {r[hdr.index(w)]} {units[hdr.index(w)]}")
+        for i, h in enumerate(hdr):
+            if h == w or h.endswith("." + w):
+                print(f"{w:90s} {r[i]} {units[i]}")
+                break
 if len(sys.argv) > 2:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))

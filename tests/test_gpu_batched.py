@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 METRICS = [ob.Metric.Cosine, ob.Metric.Euclidean, ob.Metric.DotProduct]
 
 
-@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+@pytest.fixture(params=[1, 2], ids=["single_cta", "cta_pair"])
 def bctx(ctx, request):
-    """Forces the tensor-core kernel, once as CTA pairs (tcgen05 cta_group::2, the default) and once as single CTAs."""
+    """Forces the tensor-core kernel, once as single CTAs (the default) and once as CTA pairs (tcgen05 cta_group::2)."""
     ctx.set_tuning(batch_mode=1, batch_cta_group=request.param)
     yield ctx
     ctx.set_tuning()
