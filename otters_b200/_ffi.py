@@ -36,6 +36,8 @@ class ScanTuning(C.Structure):
         ("disable_fused_predicate", C.c_uint32),
         ("batch_mode", C.c_uint32),
         ("batch_cta_group", C.c_uint32),
+        ("scan_mode", C.c_uint32),
+        ("planners", C.c_uint32),
         ("timing", C.c_uint32),
     ]
 

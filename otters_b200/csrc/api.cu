@@ -73,6 +73,7 @@ struct otters_ctx {
     uint32_t* d_scratch_src = nullptr;
     uint32_t scratch_elems = 0;
     uint32_t scan_smem_configured[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t planner_smem_configured[3] = {0, 0, 0};
     uint32_t* d_mask = nullptr;         // uploaded VecStore row mask
     size_t d_mask_words = 0;
     Cand* d_emit = nullptr;             // emit-all path
@@ -390,6 +391,7 @@ struct ScanPlan {
     uint32_t off_filter;
     uint32_t kc, nkc, pitch_s, slots, unit_rows, n_units, cap;
     uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
+    uint32_t planners, off_ring;  // planner front-end (scan_planner.cu): planner warps per CTA (0 = autonomous warps)
 };
 
 static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, size_t filter_bytes, ScanPlan* out) {
@@ -399,7 +401,17 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     const uint32_t hdr = (uint32_t)round_up(16 + (uint64_t)pl.cap * 8, 128);
     pl.off_query = hdr;
     pl.off_filter = (uint32_t)round_up((uint64_t)hdr + (uint64_t)dim_pad * 4, 128);
-    pl.off_warps = (uint32_t)(pl.off_filter + filter_bytes);
+    // front-end: planner warps feeding worker warps (fused top-k only), or autonomous warps
+    // automatic choice (profiles/r1_planner_ab.log): the planner front-end wins where rows are wide or no predicate has to
+    // be evaluated (10Mx768 unfiltered 4.07 vs 4.18 ms, 5Mx1536 filtered 2.17 vs 2.26 ms) and loses on narrow filtered rows
+    // (10Mx128: 0.79 vs 0.50 ms), where the per-tile ring handshake and the planners' metadata round trips dominate
+    const bool planner_auto = filter_bytes == 0 ? dim_pad >= 256 : dim_pad >= 1024;
+    const bool planner = k_fused && t.scan_mode != 1 && (t.scan_mode == 2 || planner_auto);
+    pl.off_ring = (uint32_t)(pl.off_filter + filter_bytes);
+    pl.off_warps = pl.off_ring + (planner ? kPlannerRingBytes : 0);
+    // planner warps per CTA: a filtered unit costs a planner one memory round trip (~2 µs under load); narrow rows are
+    // consumed faster, so they need more planners to stay ahead of the workers
+    if (planner) pl.planners = t.planners ? std::min<uint32_t>(t.planners, 4) : (filter_bytes ? (dim_pad <= 256 ? 4 : 2) : 1);
     const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
     if (pl.off_warps + 4096 > budget) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
 
@@ -437,6 +449,7 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     uint32_t total_slots = (uint32_t)(avail / (slot_bytes + 256));
     if (total_slots < 1) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
     uint32_t S = t.slots_per_warp ? t.slots_per_warp : (total_slots >= 32 ? 2 : 1);
+    if (planner) S = 1;
     uint32_t W = t.warps_per_cta ? t.warps_per_cta : std::min<uint32_t>(total_slots / S, 16);
     if (W < 1) W = 1;
     if (W > 16) W = 16;
@@ -454,16 +467,19 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     // small stores (e.g. one shard of a row-sharded search) need finer units, or the last units of the dynamic schedule
     // leave most warps idle: measured on a 1.25M x 768 shard, 32-row units scan in 0.293 ms against 0.330 ms for 128-row
     // units (profiles/r1_unit_rows_shard.log); large stores keep 128-row units (fewer unit boundaries)
-    if (!t.unit_rows)
-        while (unit_rows > 32 && n_rows / unit_rows < (uint64_t)grid * W * 16) unit_rows >>= 1;
+    if (!t.unit_rows) {
+        // planner front-end: a unit is spread over all warps of its CTA, so only the per-CTA unit count matters
+        const uint64_t want = planner ? (uint64_t)grid * 16 : (uint64_t)grid * W * 16;
+        while (unit_rows > 32 && n_rows / unit_rows < want) unit_rows >>= 1;
+    }
     pl.unit_rows = unit_rows;
     pl.n_units = (uint32_t)((n_rows + unit_rows - 1) / unit_rows);
-    uint32_t need_ctas = (pl.n_units + W - 1) / W;
+    uint32_t need_ctas = planner ? pl.n_units : (pl.n_units + W - 1) / W;
     if (need_ctas < 1) need_ctas = 1;
     if (grid > need_ctas) grid = need_ctas;
     if (grid > c->grid_max) grid = c->grid_max;
     pl.launch.grid = grid;
-    pl.launch.block = W * 32;
+    pl.launch.block = (W + pl.planners) * 32;
     pl.launch.smem_bytes = pl.off_warps + W * pl.warp_bytes;
     *out = pl;
     return OTTERS_OK;
@@ -795,6 +811,8 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.nkc = pl.nkc;
     sp.pitch_s = pl.pitch_s;
     sp.slots = pl.slots;
+    sp.planners = pl.planners;
+    sp.off_ring = pl.off_ring;
     sp.off_query = pl.off_query;
     sp.off_warps = pl.off_warps;
     sp.warp_bytes = pl.warp_bytes;
@@ -819,7 +837,8 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             sp.qid = qi;
             sp.tau_in = qi ? c->d_tau : nullptr;
             if (qi == 0 && q->nq == 1) rec_event(c, 3);
-            rc = launch_scan(sp, pl.launch, q->metric, false, c->scan_smem_configured, s);
+            rc = pl.planners ? launch_scan_planner(sp, pl.launch, q->metric, c->planner_smem_configured, s)
+                             : launch_scan(sp, pl.launch, q->metric, false, c->scan_smem_configured, s);
             if (rc) return rc;
             if (qi == 0 && q->nq == 1) {
                 rec_event(c, 4);
@@ -992,6 +1011,7 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
         c->own_stream = true;
     }
     c->grid_max = (uint32_t)c->sm_count * 2;
+    if (const char* e = getenv("OTTERS_SCAN_MODE")) c->tuning.scan_mode = (uint32_t)atoi(e);
     c->d_io_bytes = 1 << 16;
     OTTERS_CUDA(cudaMalloc((void**)&c->d_io, c->d_io_bytes));
     OTTERS_CUDA(cudaMemset(c->d_io, 0, 256));
@@ -1056,6 +1076,9 @@ extern "C" int otters_ctx_synchronize(otters_ctx* c) {
 extern "C" int otters_ctx_set_tuning(otters_ctx* c, const otters_scan_tuning* t) {
     if (!c) return fail(OTTERS_ERR_INVALID, "null context");
     c->tuning = t ? *t : otters_scan_tuning{};
+    // test hook: OTTERS_SCAN_MODE selects the K1 front-end wherever the caller left it automatic
+    if (c->tuning.scan_mode == 0)
+        if (const char* e = getenv("OTTERS_SCAN_MODE")) c->tuning.scan_mode = (uint32_t)atoi(e);
     return OTTERS_OK;
 }
 

@@ -38,6 +38,8 @@ constexpr uint32_t kTileRows = 16;     // rows per staged tile (2 threads per ro
 constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work unit
 constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
 constexpr uint32_t kSelectSmemElems = 8192;
+constexpr uint32_t kPlannerRingTiles = 64;   // 16-row tiles in flight between the planner and the worker warps of K1
+constexpr uint32_t kPlannerRingBytes = 16 + 3 * 4 * 64 + 64 * 16 * 4 + 112;  // sizeof(Ring) rounded up to 128
 constexpr uint32_t kMaxPeers = 8;       // GPUs of one NVSwitch domain taking part in a row-sharded search
 constexpr uint32_t kBatchRows = 128;    // store rows per tile of the batched kernel (UMMA M)
 constexpr uint32_t kBatchQueries = 256; // queries per tile of the batched kernel (UMMA N)
@@ -82,6 +84,8 @@ struct ScanParams {
     uint32_t nkc;               // slots steps per tile
     uint32_t pitch_s;           // floats per staged row in shared memory (== 8 mod 32)
     uint32_t slots;             // slots per warp
+    uint32_t planners;          // planner front-end (scan_planner.cu): planner warps per CTA (0 = autonomous warps)
+    uint32_t off_ring;          // planner front-end: shared-memory offset of the tile ring
     uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
     // outputs (fused mode)
     uint64_t* cta_keys;         // [grid][k]
@@ -99,6 +103,7 @@ struct ScanLaunch {
 };
 
 int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, uint32_t* smem_configured, cudaStream_t s);
+int launch_scan_planner(const ScanParams& p, const ScanLaunch& l, int metric, uint32_t* smem_configured, cudaStream_t s);
 
 // ---- selection kernels ------------------------------------------------------------------------
 // Every result list in device memory is preceded by this 64-byte header, so that one D2H copy returns

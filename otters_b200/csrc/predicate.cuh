@@ -48,4 +48,74 @@ __device__ __forceinline__ bool row_passes(const DevLeaf* leaves, const uint32_t
     return keep;
 }
 
+// --- memory-level-parallel form for the planner warps of K1 (scan_planner.cu) ------------------------------------
+// A lane owns up to 4 consecutive rows r .. r+rpl-1 (all inside one 32-bit null word; bit j of `bits` = row r+j is
+// still a candidate).  Phase 1 issues EVERY value and null-word load of every (leaf, row) pair, phase 2 compares, so
+// a unit's metadata arrives in one memory round trip instead of one per leaf.  Same semantics as row_passes().
+constexpr uint32_t kMlpLeaves = 6;
+
+__device__ __forceinline__ bool leaf_sat_raw(const DevLeaf& lf, uint64_t raw) {
+    switch (lf.exec) {
+    case LEAF_I32: return row_sat<int32_t>(lf.op, (int32_t)(uint32_t)raw, lf.i32);
+    case LEAF_I64: return row_sat<int64_t>(lf.op, (int64_t)raw, lf.i64);
+    case LEAF_F32: return row_sat<float>(lf.op, __uint_as_float((uint32_t)raw), lf.f32);
+    case LEAF_F64: return row_sat<double>(lf.op, __longlong_as_double((long long)raw), lf.f64);
+    default: {
+        const bool eq = lf.code_valid && (uint32_t)raw == lf.code;
+        return lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
+    }
+    }
+}
+
+__device__ __forceinline__ uint32_t rows_pass_mlp(const DevLeaf* leaves, const uint32_t* clause_off, uint32_t n_clauses,
+                                                  uint32_t n_leaves, uint32_t r, uint32_t bits, uint32_t rpl) {
+    if (n_clauses == 0 || bits == 0) return bits;
+    if (n_leaves > kMlpLeaves) {  // large CNFs: row by row
+        uint32_t out = 0;
+        for (uint32_t j = 0; j < rpl; ++j)
+            if (((bits >> j) & 1u) && row_passes(leaves, clause_off, n_clauses, r + j)) out |= 1u << j;
+        return out;
+    }
+    uint64_t raw[kMlpLeaves][4];
+    uint32_t nul[kMlpLeaves];
+#pragma unroll
+    for (uint32_t li = 0; li < kMlpLeaves; ++li) {
+        nul[li] = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) raw[li][j] = 0;
+        if (li < n_leaves) {
+            const DevLeaf& lf = leaves[li];
+            if (lf.null_words) nul[li] = __ldg(lf.null_words + (r >> 5)) >> (r & 31);
+            const bool wide = lf.exec == LEAF_I64 || lf.exec == LEAF_F64;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (j < rpl && ((bits >> j) & 1u))
+                    raw[li][j] = wide ? __ldg(reinterpret_cast<const unsigned long long*>(lf.values) + r + j)
+                                      : (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(lf.values) + r + j);
+        }
+    }
+    uint32_t keep = bits, any = 0, ci = 0;
+    uint32_t next = clause_off[1];  // first leaf of the next clause
+#pragma unroll
+    for (uint32_t li = 0; li < kMlpLeaves; ++li) {
+        if (li < n_leaves) {
+            while (li == next && ci + 1 < n_clauses) {  // clause ci is complete (also steps over empty clauses)
+                keep &= any;
+                any = 0;
+                ++ci;
+                next = clause_off[ci + 1];
+            }
+            const DevLeaf& lf = leaves[li];
+            uint32_t m = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (j < rpl && leaf_sat_raw(lf, raw[li][j]) && !((nul[li] >> j) & 1u)) m |= 1u << j;
+            any |= m;
+        }
+    }
+    keep &= any;  // the clause the last leaf belongs to
+    for (++ci; ci < n_clauses; ++ci) keep = 0;  // trailing clauses without leaves can never be satisfied
+    return keep;
+}
+
 }  // namespace otters

@@ -1,0 +1,101 @@
+// scan_shared.cuh — pieces shared by the two front-ends of K1 (scan.cu: autonomous warps; scan_planner.cu: planner
+// warps feeding worker warps): the per-CTA lock-free candidate buffer and its compaction.
+#pragma once
+#include "internal.h"
+
+namespace otters {
+namespace scan_detail {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct CtaHdr {
+    unsigned long long tau;  // candidates must have key > tau
+    uint32_t count;          // slots reserved in the candidate buffer (may transiently exceed cap)
+    uint32_t written;        // slots whose key has been stored
+};
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// one warp: sort buf[0..cap) best-first (entries >= cnt are zeroed first); the best min(cnt,k) end up in front
+__device__ inline void warp_sort(uint64_t* buf, uint32_t cnt, uint32_t cap, int lane) {
+    for (uint32_t i = cnt + lane; i < cap; i += 32) buf[i] = 0ull;
+    __syncwarp();
+    for (uint32_t size = 2; size <= cap; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < (cap >> 1); t += 32) {
+                uint32_t lo = 2 * t - (t & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool desc = (lo & size) == 0;
+                uint64_t a = buf[lo], b = buf[hi];
+                if ((a < b) == desc) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Lock-free append of this warp's passing candidates to the CTA buffer.  A warp reserves slots with one
+// shared-memory atomicAdd, stores its keys and bumps `written`.  The single warp whose reservation crosses
+// the capacity becomes the compactor: it waits until every earlier reservation has been written, sorts,
+// keeps the best k, raises the threshold and reopens the buffer; later arrivals wait for the reopen and
+// retry against the new threshold.
+__device__ inline void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, bool has, uint64_t key, int lane) {
+    for (;;) {
+        const uint64_t tau = ld_volatile_u64(&hdr->tau);
+        has = has && key > tau;
+        const unsigned m = __ballot_sync(FULL, has);
+        const uint32_t n = __popc(m);
+        if (!n) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&hdr->count, n);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + n <= cap) {
+            if (has) buf[base + __popc(m & ((1u << lane) - 1u))] = key;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&hdr->written, n);
+            }
+            return;
+        }
+        if (base <= cap) {
+            // compactor: valid entries are [0, base)
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (ld_volatile_u32(&hdr->written) != base) {
+                    if (clock64() - t0 > 4000000000ll) __trap();  // watchdog
+                }
+            }
+            __syncwarp();
+            __threadfence_block();
+            warp_sort(buf, base, cap, lane);
+            if (lane == 0) {
+                const unsigned long long t = buf[k - 1];  // base > cap - 32 >= k
+                if (t > hdr->tau) *reinterpret_cast<volatile unsigned long long*>(&hdr->tau) = t;
+                *reinterpret_cast<volatile uint32_t*>(&hdr->written) = k;
+                __threadfence_block();
+                atomicExch(&hdr->count, k);
+            }
+            __syncwarp();
+        } else {
+            if (lane == 0) {
+                const long long t0 = clock64();
+                while (ld_volatile_u32(&hdr->count) > cap) {
+                    __nanosleep(32);
+                    if (clock64() - t0 > 4000000000ll) __trap();  // watchdog
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+
+}  // namespace scan_detail
+}  // namespace otters

@@ -138,6 +138,8 @@ pub struct otters_scan_tuning {
     pub disable_fused_predicate: u32,
     pub batch_mode: u32,       // 0 auto, 1 always the tcgen05 kernel for batches, 2 never
     pub batch_cta_group: u32,  // 0 auto (CTA pairs), 1 single CTAs, 2 pairs
+    pub scan_mode: u32,        // K1 front-end: 0 auto, 1 autonomous warps, 2 planner + worker warps
+    pub planners: u32,         // planner warps per CTA (0 auto)
     pub timing: u32,           // 0 auto, 1 always record phase events, 2 never
 }
 
