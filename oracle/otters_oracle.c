@@ -489,20 +489,28 @@ void oracle_bloom_params(uint64_t n_items, int mode, double fpr, uint64_t bits, 
     *k_hashes = k;
 }
 
+/* probe i = (a + i*b) mod m with a = h1 mod m, b = h2 mod m (1 if that is 0): double hashing in Z_m, stepped without
+ * a division per probe */
 static inline void bloom_insert(uint64_t *words, uint64_t m, uint32_t k, const uint8_t *s, uint64_t len) {
     uint64_t h1, h2;
     oracle_bloom_hash(s, len, &h1, &h2);
+    uint64_t bit = h1 % m, step = h2 % m;
+    if (step == 0) step = 1;
     for (uint32_t i = 0; i < k; ++i) {
-        uint64_t bit = (h1 + (uint64_t)i * h2) % m;
         words[bit >> 6] |= 1ULL << (bit & 63);
+        bit += step;
+        if (bit >= m) bit -= m;
     }
 }
 static inline int bloom_contains(const uint64_t *words, uint64_t m, uint32_t k, const uint8_t *s, uint64_t len) {
     uint64_t h1, h2;
     oracle_bloom_hash(s, len, &h1, &h2);
+    uint64_t bit = h1 % m, step = h2 % m;
+    if (step == 0) step = 1;
     for (uint32_t i = 0; i < k; ++i) {
-        uint64_t bit = (h1 + (uint64_t)i * h2) % m;
         if (!((words[bit >> 6] >> (bit & 63)) & 1)) return 0;
+        bit += step;
+        if (bit >= m) bit -= m;
     }
     return 1;
 }

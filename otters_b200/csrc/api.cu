@@ -1504,9 +1504,12 @@ static int build_column(otters_metastore* ms, const otters_column& in, const ott
                 if (!host_is_null(in, i)) {
                     uint64_t h1, h2;
                     bloom_hash(in.str_bytes + in.str_offsets[i], in.str_offsets[i + 1] - in.str_offsets[i], &h1, &h2);
+                    uint64_t bit = h1 % mbits[ch], step = h2 % mbits[ch];  // probe j = (a + j*b) mod m, stepped
+                    if (step == 0) step = 1;
                     for (uint32_t j = 0; j < kh[ch]; ++j) {
-                        uint64_t bit = (h1 + (uint64_t)j * h2) % mbits[ch];
                         w[bit >> 6] |= 1ull << (bit & 63);
+                        bit += step;
+                        if (bit >= mbits[ch]) bit -= mbits[ch];
                     }
                     ++cnt;
                 }
@@ -1691,6 +1694,12 @@ static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vecto
             d.code_valid = it != mc.dict.end();
             d.code = d.code_valid ? it->second : 0;
             bloom_hash((const uint8_t*)lit.data(), lit.size(), &d.h1, &d.h2);
+            // every full chunk has the same filter size m0: its start / step are precomputed so that the prune kernel
+            // only divides for the (shorter) last chunk
+            d.bloom_m0 = mc.bloom_stride * 64;
+            d.bloom_a0 = d.bloom_m0 ? d.h1 % d.bloom_m0 : 0;
+            d.bloom_b0 = d.bloom_m0 ? d.h2 % d.bloom_m0 : 0;
+            if (d.bloom_b0 == 0) d.bloom_b0 = 1;
             break;
         }
         default: return fail(OTTERS_ERR_INVALID, "unknown column dtype");

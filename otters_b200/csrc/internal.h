@@ -260,6 +260,7 @@ struct DevLeaf {         // one lowered leaf, self-contained: carries the device
     uint32_t code;
     uint32_t pad;
     uint64_t h1, h2;     // LEAF_STR: Bloom probe hashes of the literal
+    uint64_t bloom_m0, bloom_a0, bloom_b0;  // filter size of a full chunk and h1 % m0, h2 % m0 (step, never 0)
     const void* values;
     const uint32_t* null_words;
     const void* zmin;

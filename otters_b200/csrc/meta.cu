@@ -46,10 +46,22 @@ __device__ __forceinline__ bool chunk_leaf_rule(const DevLeaf& lf, uint32_t ch) 
         const uint64_t* w = lf.bloom + (size_t)ch * lf.bloom_stride;
         const uint64_t m = lf.bloom_mbits[ch];
         const uint32_t kh = lf.bloom_k[ch];
+        // probe i = (a + i*b) mod m, a = h1 mod m, b = h2 mod m (1 if 0), stepped without a division per probe; a and b
+        // come precomputed for the filter size of a full chunk
+        uint64_t bit, step;
+        if (m == lf.bloom_m0) {
+            bit = lf.bloom_a0;
+            step = lf.bloom_b0;
+        } else {
+            bit = lf.h1 % m;
+            step = lf.h2 % m;
+            if (step == 0) step = 1;
+        }
         bool all = true;  // every probe is issued (no early exit) so that the word loads overlap
         for (uint32_t i = 0; i < kh; ++i) {
-            uint64_t bit = (lf.h1 + (uint64_t)i * lf.h2) % m;
             all &= ((__ldg(w + (bit >> 6)) >> (bit & 63)) & 1ull) != 0;
+            bit += step;
+            if (bit >= m) bit -= m;
         }
         return all;
     }
@@ -102,6 +114,59 @@ __global__ void __launch_bounds__(64) prune_kernel(const __grid_constant__ MetaK
     }
 }
 
+// K0, leaf-parallel form (CNFs of up to 32 leaves): a block of 256 threads owns 32 chunks = one word of the keep
+// bitmask; 8 threads share a chunk and evaluate its leaves side by side, so the zonemap / Bloom loads of ALL leaves are
+// in flight at once (the thread-per-chunk form walks the leaves one after the other: one memory round trip each).
+__global__ void __launch_bounds__(256) prune_leafpar_kernel(const __grid_constant__ MetaKernelParams p, uint32_t n_leaves) {
+    __shared__ __align__(16) DevLeaf s_leaves[32];
+    __shared__ uint32_t s_off[33];
+    __shared__ uint32_t s_word;
+    __shared__ unsigned long long s_vc;
+    const uint32_t words = n_leaves * (uint32_t)(sizeof(DevLeaf) / 4);
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(s_leaves)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.leaves) + i);
+    for (uint32_t i = threadIdx.x; i <= p.n_clauses && i <= 32; i += blockDim.x) s_off[i] = __ldg(p.clause_off + i);
+    if (threadIdx.x == 0) {
+        s_word = 0;
+        s_vc = 0;
+    }
+    __syncthreads();
+    const uint32_t sub = threadIdx.x & 7u;              // which leaves of the chunk this thread evaluates
+    const uint32_t cl = threadIdx.x >> 3;               // chunk within the block's word
+    const uint32_t ch = blockIdx.x * 32 + cl;
+    uint32_t mask = 0;
+    if (ch < p.n_chunks)
+        for (uint32_t li = sub; li < n_leaves; li += 8)
+            if (chunk_leaf_sat(s_leaves[li], ch)) mask |= 1u << li;
+    mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, 1);
+    mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, 2);
+    mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, 4);
+    if (sub == 0 && ch < p.n_chunks) {
+        bool keep = true;
+        for (uint32_t ci = 0; ci < p.n_clauses; ++ci) {
+            const uint32_t a = s_off[ci], b = s_off[ci + 1];
+            const uint32_t cm = b > a ? (uint32_t)(((1ull << (b - a)) - 1ull) << a) : 0u;
+            keep &= (mask & cm) != 0;
+        }
+        if (keep) {
+            const uint64_t base = (uint64_t)ch * p.chunk_size;
+            const uint32_t len = (uint32_t)(base + p.chunk_size <= p.n_rows ? p.chunk_size : p.n_rows - base);
+            atomicOr(&s_word, 1u << cl);
+            atomicAdd(&s_vc, (unsigned long long)len * p.nq);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        p.chunk_keep[blockIdx.x] = s_word;
+        // stats: evaluated chunks and vectors_compared = sum over evaluated chunks of len * nq
+        // (src/meta_compute.rs:166, src/meta.rs:666-669)
+        if (s_word) {
+            atomicAdd(&p.stats[0], (unsigned long long)__popc(s_word));
+            atomicAdd(&p.stats[1], s_vc);
+        }
+    }
+}
+
 // no meta_filter: every chunk is evaluated (src/meta.rs:658)
 __global__ void count_all_kernel(const __grid_constant__ MetaKernelParams p) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -148,7 +213,10 @@ __global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ Me
 
 int launch_prune(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s) {
     if (p.n_chunks == 0) return OTTERS_OK;
-    prune_kernel<<<(p.n_chunks + 63) / 64, 64, 0, s>>>(p, n_leaves);
+    if (n_leaves >= 1 && n_leaves <= 32 && p.n_clauses <= 32)
+        prune_leafpar_kernel<<<(p.n_chunks + 31) / 32, 256, 0, s>>>(p, n_leaves);
+    else
+        prune_kernel<<<(p.n_chunks + 63) / 64, 64, 0, s>>>(p, n_leaves);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

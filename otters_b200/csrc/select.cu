@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(sm);
     uint32_t* s_src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
-    __shared__ uint32_t s_total, s_nel, s_retry, s_maxcount;
+    __shared__ uint32_t s_total, s_nel, s_retry, s_maxcount, s_nc;
+    __shared__ unsigned long long s_thr;
 
     const uint32_t first = WITH_PREV ? 0u : 1u;  // list 0 = running list
     const uint32_t n_lists = p.n_lists + 1;
@@ -143,12 +144,39 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
         }
         if (loc) atomicAdd(&s_nel, loc);
         __syncthreads();
+        // (a) a lower bound on the k-th key from the list heads alone: if there are at least kk lists, the kk-th best
+        //     HEAD has kk keys at or above it, so nothing below it can be part of the result
+        uint64_t* cand = s_keys + kRankSelectElems;  // [kRankSelectElems] compacted candidates
+        if (threadIdx.x == 0) {
+            s_thr = 0ull;
+            s_nc = 0;
+        }
+        __syncthreads();
+        if (kk > 0 && kk <= p.n_lists) {
+            for (uint32_t l = threadIdx.x; l < p.n_lists; l += blockDim.x) {
+                const uint64_t key = s_keys[l * L];
+                if (key == 0ull) continue;
+                uint32_t rank = 0;
+#pragma unroll 8
+                for (uint32_t l2 = 0; l2 < p.n_lists; ++l2) rank += s_keys[l2 * L] > key;
+                if (rank == kk - 1) s_thr = key;  // keys are distinct: exactly one head has this rank
+            }
+        }
+        __syncthreads();
+        // (b) compact the elements that can still matter
+        const uint64_t thr = s_thr;
         for (uint32_t e = threadIdx.x; e < nel_max; e += blockDim.x) {
             const uint64_t key = s_keys[e];
-            if (key == 0ull) continue;
+            if (key != 0ull && key >= thr) cand[atomicAdd(&s_nc, 1u)] = key;
+        }
+        __syncthreads();
+        // (c) final position = number of better candidates
+        const uint32_t nc = s_nc;
+        for (uint32_t e = threadIdx.x; e < nc; e += blockDim.x) {
+            const uint64_t key = cand[e];
             uint32_t rank = 0;
 #pragma unroll 8
-            for (uint32_t j = 0; j < nel_max; ++j) rank += s_keys[j] > key;
+            for (uint32_t j = 0; j < nc; ++j) rank += cand[j] > key;
             if (rank < kk) ranked[rank] = key;
         }
         __syncthreads();
@@ -301,9 +329,19 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
                 const uint64_t key = s_keys[e];
                 if (key == 0ull) continue;
                 const uint32_t tag = s_src[e];
+                // every rank's records arrive ordered: binary search per rank instead of comparing against all records
                 uint32_t rank = 0;
-#pragma unroll 4
-                for (uint32_t j = 0; j < n_in; ++j) rank += before(s_keys[j], s_src[j], key, tag);
+                for (uint32_t r2 = 0; r2 < p.ex_world; ++r2) {
+                    const uint64_t* kp = s_keys + r2 * p.ex_k;
+                    const uint32_t* tp = s_src + r2 * p.ex_k;
+                    uint32_t lo = 0, hi = p.ex_k;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (before(kp[mid], tp[mid], key, tag)) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    rank += lo;
+                }
                 if (rank < n_out) {
                     Cand c;
                     c.key = key;
@@ -337,8 +375,9 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
 
 // ---- sharded path: merge gathered records --------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
-merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int take_max, Cand* out, uint32_t* out_count,
-                     ResultHeader* hdr, const unsigned long long* rows_scored_src, uint64_t* scratch_keys, uint32_t* scratch_src) {
+merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, uint32_t list_len, int take_max, Cand* out,
+                     uint32_t* out_count, ResultHeader* hdr, const unsigned long long* rows_scored_src, uint64_t* scratch_keys,
+                     uint32_t* scratch_src) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm);
     uint32_t* src = reinterpret_cast<uint32_t*>(sm + (size_t)kSelectSmemElems * 8);
@@ -366,15 +405,40 @@ merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, int
     if (loc) atomicAdd(&s_valid, loc);
     __syncthreads();
     if (n <= kRankSelectElems) {
-        // few records (world * k): every thread counts the records ordered before its own — no sorting network
+        // few records (world * k): every thread counts the records ordered before its own — no sorting network.
+        // When the input is a concatenation of ordered lists of list_len records (what otters_query_local_device writes,
+        // one list per rank) the count is a binary search per list; the ordering is verified first.
+        __shared__ uint32_t s_ordered;
+        if (threadIdx.x == 0) s_ordered = (list_len && n % list_len == 0) ? 1u : 0u;
+        __syncthreads();
+        if (s_ordered)
+            for (uint32_t e = threadIdx.x; e + 1 < n; e += blockDim.x)
+                if ((e + 1) % list_len != 0 && before(keys[e + 1], src[e + 1], keys[e], src[e])) s_ordered = 0;
+        __syncthreads();
+        const bool ordered = s_ordered != 0;
         const uint32_t kr = s_valid < k ? s_valid : k;
         for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
             const uint64_t key = keys[e];
             if (key == 0ull) continue;
             const uint32_t tag = src[e];
             uint32_t rank = 0;
+            if (ordered) {
+                // the records are `n / list_len` ordered lists (one per rank): binary search per list
+                for (uint32_t l2 = 0; l2 < n / list_len; ++l2) {
+                    const uint64_t* kp = keys + l2 * list_len;
+                    const uint32_t* tp = src + l2 * list_len;
+                    uint32_t lo = 0, hi = list_len;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (before(kp[mid], tp[mid], key, tag)) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    rank += lo;
+                }
+            } else {
 #pragma unroll 4
-            for (uint32_t j = 0; j < n; ++j) rank += before(keys[j], src[j], key, tag);
+                for (uint32_t j = 0; j < n; ++j) rank += before(keys[j], src[j], key, tag);
+            }
             if (rank < kr) {
                 Cand c;
                 c.key = key;
@@ -549,7 +613,9 @@ int launch_merge_records(const otters_topk_record* recs, uint32_t n, uint32_t k,
     if (P > kSelectSmemElems && P > scratch_elems) return fail(OTTERS_ERR_UNSUPPORTED, "merge: too many records");
     OTTERS_CUDA(
         cudaFuncSetAttribute(merge_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelectSmemBytes));
-    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, take_max, out, out_count, hdr, rows_scored_src, scratch_keys, scratch_src);
+    // k records per rank, each rank's records ordered best-first (otters_query_local_device): n == world * k
+    merge_records_kernel<<<1, 1024, kSelectSmemBytes, s>>>(recs, n, k, k, take_max, out, out_count, hdr, rows_scored_src, scratch_keys,
+                                                           scratch_src);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }
