@@ -32,7 +32,14 @@ namespace {
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t BM = kBatchRows;     // 128 store rows per tile
 constexpr uint32_t BN = kBatchQueries;  // 256 queries per tile
-constexpr uint32_t BK = 32;             // fp32 columns per k-block (128 bytes)
+#ifndef OTTERS_BK
+#define OTTERS_BK 32
+#endif
+constexpr uint32_t BK = OTTERS_BK;      // fp32 columns per k-block: 32 (one 128-byte swizzle atom) or 16 (64-byte atoms, twice the stages)
+static_assert(BK == 32 || BK == 16, "k-block must be one 128-byte or one 64-byte swizzle atom");
+constexpr uint32_t kSwizzleBytes = BK * 4;
+// auxiliary shared memory behind the stages: mbarriers | TMEM base address | candidate-buffer header | candidates
+constexpr uint32_t kAuxTmemSlot = 448, kAuxHdr = 512, kAuxCand = 640;
 constexpr uint32_t UK = 8;              // K of one tcgen05.mma kind::tf32
 constexpr uint32_t A_BYTES = BM * BK * 4;  // 16 KB: the V tile of one CTA and one k-block
 constexpr uint32_t TMEM_COLS = 512;
@@ -101,7 +108,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
 //   [32,46) stride byte offset >> 4 = 1024 >> 4 | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    // stride byte offset = 8 rows of one swizzle atom; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((8u * kSwizzleBytes) >> 4) << 32) | (1ull << 46) |
+           ((kSwizzleBytes == 128 ? 2ull : 4ull) << 61);
 }
 // Instruction descriptor, kind::tf32 (Geo<CG>::IDESC): [4,6) D format = 1 (f32) | [7,10) A format = 2 (tf32) |
 // [10,13) B format = 2 | [15] A major = 0 (K) | [16] B major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
@@ -253,7 +262,7 @@ struct Geo {
     static constexpr uint32_t BN_LOAD = BN / CG;              // query rows staged per CTA
     static constexpr uint32_t B_BYTES = BN_LOAD * BK * 4;     // 32 KB / 16 KB
     static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // Vhi | Vlo | Qhi | Qlo
-    static constexpr uint32_t STAGES = CG == 2 ? 3 : 2;
+    static constexpr uint32_t STAGES = (192u * 1024u) / STAGE_BYTES;  // 2 / 3 at 128-byte k-blocks, 4 / 6 at 64-byte ones
     static constexpr uint32_t TILE_ROWS = BM * CG;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
 };
@@ -371,10 +380,11 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     uint64_t* bar_tfull = bar_empty + STAGES;                     // [2] accumulator complete
     uint64_t* bar_tempty = bar_tfull + 2;                         // [2] (rank 0) accumulator drained by every epilogue thread
     uint64_t* bar_full2 = bar_tempty + 2;                         // [STAGES] (rank 0, CG = 2) the loads of BOTH CTAs landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full2 + STAGES);
-    CtaHdr* hdr = reinterpret_cast<CtaHdr*>(aux + 128);
-    uint64_t* cand_keys = reinterpret_cast<uint64_t*>(aux + 256);
-    uint32_t* cand_qids = reinterpret_cast<uint32_t*>(aux + 256 + (size_t)p.cap * 8);
+    static_assert((4 * STAGES + 4) * 8 <= kAuxTmemSlot, "barriers overflow their shared-memory area");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + kAuxTmemSlot);
+    CtaHdr* hdr = reinterpret_cast<CtaHdr*>(aux + kAuxHdr);
+    uint64_t* cand_keys = reinterpret_cast<uint64_t*>(aux + kAuxCand);
+    uint32_t* cand_qids = reinterpret_cast<uint32_t*>(aux + kAuxCand + (size_t)p.cap * 8);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_v);
@@ -848,7 +858,8 @@ int make_tensor_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t
     cuuint32_t box[2] = {BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kSwizzleBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(OTTERS_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
     return OTTERS_OK;
@@ -894,7 +905,7 @@ int launch_batch_cg(const CUtensorMap& tv, const CUtensorMap& tqh, const CUtenso
 
 uint32_t batch_smem_bytes(uint32_t cap) {
     static_assert(Geo<1>::STAGES * Geo<1>::STAGE_BYTES == Geo<2>::STAGES * Geo<2>::STAGE_BYTES, "both geometries stage 192 KB");
-    return Geo<1>::STAGES * Geo<1>::STAGE_BYTES + 1024 + 256 + cap * 12;
+    return Geo<1>::STAGES * Geo<1>::STAGE_BYTES + 1024 + kAuxCand + cap * 12;
 }
 
 int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, float* qn2,

@@ -153,10 +153,14 @@ class CudaShard:
             self.store._flush()
             args = (self.store._handle(), None, C.byref(vq), None)
         if fetch:
-            idx, score, qid = np.zeros(k, np.uint64), np.zeros(k, np.float32), np.zeros(k, np.uint32)
-            rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, idx.ctypes.data_as(ffi.c_u64p),
-                                           score.ctypes.data_as(ffi.c_f32p), qid.ctypes.data_as(ffi.c_u32p), k, C.byref(out_len),
-                                           C.byref(st) if (want_stats or self.is_meta) else None)
+            if getattr(self, "_out_k", 0) < k:  # output buffers are reused from call to call (results are copied out below)
+                self._out = (np.zeros(k, np.uint64), np.zeros(k, np.float32), np.zeros(k, np.uint32))
+                self._out_ptr = (self._out[0].ctypes.data_as(ffi.c_u64p), self._out[1].ctypes.data_as(ffi.c_f32p),
+                                 self._out[2].ctypes.data_as(ffi.c_u32p))
+                self._out_k = k
+            idx, score, qid = self._out
+            rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, *self._out_ptr, k, C.byref(out_len),
+                                           C.byref(st) if want_stats else None)
         else:
             rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, None, None, None, 0, None,
                                            C.byref(st) if want_stats else None)
@@ -167,7 +171,7 @@ class CudaShard:
         if not fetch:
             return None, st
         m = min(out_len.value, k)
-        return (idx[:m], score[:m], qid[:m]), st
+        return (idx[:m].copy(), score[:m].copy(), qid[:m].copy()), st
 
     def enqueue(self, vq, fp, k: int, want_stats: bool = False):
         """Enqueues local search + all-gather on the context's stream; returns the gathered record tensor."""

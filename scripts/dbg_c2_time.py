@@ -9,7 +9,7 @@ ctx = ob.default_context(0)
 s = ob.VecStore(dim, ctx); s.add_synthetic(0, rows, 0x7735)
 q = synth_fill_np(0, nq, dim, 0xBEEF)
 for cg in (1, 2):
-    for dbg in (0, 16, 4, 20):
+    for dbg in (0, 4):
         os.environ["OTTERS_BATCH_DBG"] = str(dbg)
         ctx.set_tuning(batch_mode=1, batch_cta_group=cg, timing=1)
         ts = []
