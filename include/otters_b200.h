@@ -320,7 +320,9 @@ OTTERS_API int otters_query_exchange(otters_vecstore *vs, otters_metastore *ms, 
 
 /* Appends n_local rows of the synthetic generator whose global row ids follow `map` (bench/test utility). */
 OTTERS_API int otters_vecstore_add_synthetic_sharded(otters_vecstore *vs, const otters_shard_map *map, uint64_t n_local, uint64_t seed);
-/* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k.
+/* Merges n_records device records (e.g. world_size * k after the all-gather) into the global best k.  Any record
+ * order is accepted; when the input is a concatenation of blocks of k records ordered best-first — exactly what the
+ * ranks' otters_query_local_device calls leave — the merge is a binary search per block instead of an all-pairs count.
  * With out_idx = out_score = out_qid = NULL and cap = 0 the call only enqueues the merge (no copy, no sync). */
 OTTERS_API int otters_topk_merge_device(otters_ctx *ctx, const void *d_records, uint64_t n_records, uint64_t k, int32_t take_type,
                              uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap, uint64_t *out_len);

@@ -1,11 +1,9 @@
 #!/bin/bash
-# A/B of the K2 k-block size: 32 fp32 columns (128-byte swizzle, 2 stages) vs 16 (64-byte swizzle, 4 stages)
 mkdir -p gpurun_out
-cp otters_b200/libotters_b200.so /tmp/lib_orig.so
-for v in bk16 bk32; do
-  cp scripts/tmp/lib_$v.so otters_b200/libotters_b200.so
-  echo "== $v"
-  timeout 600 python -m pytest tests/test_gpu_batched.py -x -q 2>&1 | tail -2
-  timeout 300 python scripts/dbg_c2_time.py 2>&1 | grep "dbg= 0\|dbg= 4"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for w in target c3 c5; do
+timeout 600 python bench.py --workload $w --steps 50 --warmup 5 --no-cpu > gpurun_out/bench_${w}_n1.json 2> gpurun_out/bench_${w}_n1.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_${w}_n1.json')); print('$w n1', round(d['value'],1), round(d['ms_per_step'],4), round(d['e2e']['value'],1), d['phases_ms'], round(d['roofline']['frac'],3))"
 done
-cp /tmp/lib_orig.so otters_b200/libotters_b200.so
+timeout 600 python bench.py --workload target --rows 1250000 --steps 100 --warmup 10 --no-cpu > gpurun_out/b_shard.json 2> gpurun_out/b_shard.err; python -c "
+import json; d=json.load(open('gpurun_out/b_shard.json')); print('shard', 'step_ms', round(d['ms_per_step'],4), 'e2e_ms', round(d['e2e']['ms_per_step'],4), d['phases_ms'], round(d['roofline']['frac'],3))"
