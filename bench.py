@@ -285,6 +285,10 @@ def run_ours(args, wl):
     if args.tuning:
         w, s, kc, cps, ur = (int(x) for x in args.tuning.split(","))
         tune = dict(warps_per_cta=w, slots_per_warp=s, kc_floats=kc, ctas_per_sm=cps, unit_rows=ur)
+    if args.scan_mode:
+        tune["scan_mode"] = args.scan_mode
+    if args.planners:
+        tune["planners"] = args.planners
     ctx.set_tuning(**tune)
 
     rows, dim, chunk, k = wl["rows"], wl["dim"], wl["chunk"], wl["k"]
@@ -520,6 +524,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--phase-timing", action="store_true", help="print per-phase device/host times of the sharded step (debug)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--scan-mode", type=int, default=0, help="K1 front-end: 0 auto, 1 autonomous warps, 2 planner + workers")
+    ap.add_argument("--planners", type=int, default=0, help="planner warps per CTA (planner front-end; 0 = auto)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"], help="N > 1: fused peer-memory exchange when available, or force NCCL")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

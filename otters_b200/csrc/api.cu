@@ -824,6 +824,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.cta_keys = c->d_cta_keys;
     sp.cta_counts = c->d_cta_counts;
     sp.rows_scored = c->d_rows_scored;
+    sp.g_tau = reinterpret_cast<unsigned long long*>(c->d_ctrl + 96);  // zeroed with the control block
 
     uint32_t cur = 0;
     if (fused) {

@@ -78,6 +78,7 @@ struct ScanParams {
     float thr;
     int32_t cmp;
     const uint64_t* tau_in;     // device: running threshold key from earlier queries of a batch (0 = none)
+    unsigned long long* g_tau;  // device: grid-wide threshold shared by the CTAs of this launch (zeroed per query; may be null)
     uint32_t qid;
     // staging layout
     uint32_t kc;                // columns per slot

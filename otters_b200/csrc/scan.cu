@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
 
     // ---- producer state ----
     uint32_t u_pref = 0;  // lane 0: prefetched unit id
+    unsigned long long g_pref = 0;  // lane 0: grid-wide threshold read together with the unit id
     if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
     uint32_t list_n = 0, list_pos = 0, unit_row0 = 0, kc_i = 0, tile_cnt = 0;
     bool prod_done = false;
@@ -95,7 +96,12 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
                     prod_done = true;
                     return;
                 }
-                if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
+                if (lane == 0) {
+                    // adopt what the other CTAs have found so far (value read one unit ago: no extra round trip)
+                    if (!EMIT_ALL && g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
+                    u_pref = atomicAdd(p.unit_counter, 1u);
+                    if (!EMIT_ALL && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
+                }
                 uint32_t row0 = u * p.unit_rows;
                 uint32_t r = row0 + rpl * lane;  // this lane's first row; its rpl rows share one mask word
                 uint32_t bits = (1u << rpl) - 1u;
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
                 }
             } else {
                 ok = ok && key > ld_volatile_u64(&hdr->tau);
-                if (__ballot_sync(FULL, ok)) warp_push(hdr, cbuf, p.cap, p.k, ok, key, lane);
+                if (__ballot_sync(FULL, ok)) warp_push(hdr, cbuf, p.cap, p.k, ok, key, lane, p.g_tau);
             }
         }
         __syncwarp();

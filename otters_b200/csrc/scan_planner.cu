@@ -95,11 +95,17 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
         // =============================== planner ===============================
         const uint32_t rpl = p.unit_rows >> 5;  // rows per lane of a unit (1, 2 or 4); a lane's rows share one mask word
         uint32_t u_pref = 0;
+        unsigned long long g_pref = 0;  // grid-wide threshold, read together with the unit id
         if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
         for (;;) {
             const uint32_t u = __shfl_sync(FULL, u_pref, 0);
             if (u >= p.n_units) break;
-            if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
+            if (lane == 0) {
+                // adopt what the other CTAs have found so far (value read one unit ago: no extra round trip)
+                if (g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
+                u_pref = atomicAdd(p.unit_counter, 1u);
+                if (p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
+            }
             const uint32_t row0 = u * p.unit_rows;
             const uint32_t r = row0 + rpl * lane;
             uint32_t bits = (1u << rpl) - 1u;
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
                     if (p.has_filter) ok = ok && score_passes(score, p.thr, p.cmp);
                     const uint64_t key = make_key(score, my_row, take_max);
                     ok = ok && key > ld_volatile_u64(&hdr->tau);
-                    if (__ballot_sync(FULL, ok)) warp_push(hdr, cbuf, p.cap, p.k, ok, key, lane);
+                    if (__ballot_sync(FULL, ok)) warp_push(hdr, cbuf, p.cap, p.k, ok, key, lane, p.g_tau);
                 }
                 __syncwarp();  // every lane is done with the slot before the next copy lands in it
             }

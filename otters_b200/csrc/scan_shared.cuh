@@ -45,7 +45,11 @@ __device__ inline void warp_sort(uint64_t* buf, uint32_t cnt, uint32_t cap, int 
 // the capacity becomes the compactor: it waits until every earlier reservation has been written, sorts,
 // keeps the best k, raises the threshold and reopens the buffer; later arrivals wait for the reopen and
 // retry against the new threshold.
-__device__ inline void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, bool has, uint64_t key, int lane) {
+// g_tau (nullable): grid-wide threshold.  A CTA's k-th best key is a lower bound of the global k-th best key, so it is
+// published after every compaction and the largest published value is adopted: all CTAs tighten together instead of
+// each warming up its own threshold (which costs a small store several compactions per CTA).
+__device__ inline void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint32_t k, bool has, uint64_t key, int lane,
+                                 unsigned long long* g_tau = nullptr) {
     for (;;) {
         const uint64_t tau = ld_volatile_u64(&hdr->tau);
         has = has && key > tau;
@@ -76,7 +80,11 @@ __device__ inline void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint3
             __threadfence_block();
             warp_sort(buf, base, cap, lane);
             if (lane == 0) {
-                const unsigned long long t = buf[k - 1];  // base > cap - 32 >= k
+                unsigned long long t = buf[k - 1];  // base > cap - 32 >= k
+                if (g_tau) {
+                    const unsigned long long g = atomicMax(g_tau, t);
+                    if (g > t) t = g;
+                }
                 if (t > hdr->tau) *reinterpret_cast<volatile unsigned long long*>(&hdr->tau) = t;
                 *reinterpret_cast<volatile uint32_t*>(&hdr->written) = k;
                 __threadfence_block();

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
             const uint32_t* f = p.ex_flags[p.ex_rank] + par * p.ex_world + threadIdx.x;
             const long long t0 = clock64();
             while (ld_acquire_sys_u32(f) != p.ex_seq) {
-                if (clock64() - t0 > 20000000000ll) __trap();  // a rank never arrived (~10 s): fail instead of hanging
+                if (clock64() - t0 > 200000000000ll) __trap();  // a rank never arrived (~100 s): fail instead of hanging forever
             }
         }
         __syncthreads();
