@@ -394,9 +394,12 @@ def run_ours(args, wl):
     batch_info, phase_ms = [], []
     t0 = time.perf_counter()
     ev0.record()
+    io_bytes = [0, 0]
     for i in range(args.steps):
         step_e2e(args.warmup + i)
-        launches += int(ctx.last_work()["kernel_launches"])
+        w = ctx.last_work()
+        launches += int(w["kernel_launches"])
+        io_bytes = [int(w["h2d_bytes"]), int(w["d2h_bytes"])]
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
@@ -460,9 +463,8 @@ def run_ours(args, wl):
         if world == 1 and not args.no_cpu:
             c = cpu_arm(wl, args.workload, budget_s=args.cpu_budget)
             cpu = {kk: c[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-        h2d = nq * dim * 4  # the query vector(s)
-        if fp is not None:
-            h2d += 3 * 64 + 16  # three lowered leaves + clause offsets
+        # bytes the library copied for one step (one input image: control block + lowered filter + queries; one result read)
+        h2d, d2h = io_bytes
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
                 "traffic": measured_traffic(args.workload), "peak_source": peak_src, "kernel": "scan_kernel (K1)",
                 "scan_ms": float(np.mean(scan_ms)) if scan_ms else None,
@@ -496,7 +498,7 @@ def run_ours(args, wl):
                        "NOT flushed: the %.0f MB store is L2-resident between steps (latency-bound case; the HBM roofline does not apply)" % (rows * dim * 4 / 1e6)),
                 "store_build_s": build_s,
             },
-            "e2e": {"value": nq * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(k * 16 + 48),
+            "e2e": {"value": nq * 1e3 / e2e_ms, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms},
             "gpu_launches": launches,
             "phases_ms": dict(zip(("prune", "rowmask", "scan", "select"), (float(x) for x in np.mean(np.array(phase_ms), axis=0)))) if phase_ms else None,

@@ -117,6 +117,8 @@ typedef struct {
     uint64_t batch_candidates;  /* (row, query) pairs re-scored in the reference's exact arithmetic */
     float batch_max_err;        /* largest |tensor-core score - exact score| over the re-scored pairs */
     float batch_delta;          /* the error bound the selection assumed (must exceed batch_max_err) */
+    uint64_t h2d_bytes;         /* host-to-device bytes of the last query (input image: control block + filter + queries; row mask) */
+    uint64_t d2h_bytes;         /* device-to-host bytes of the last query (result header + candidates / stats) */
 } otters_last_work;
 OTTERS_API int otters_ctx_last_work(otters_ctx *ctx, otters_last_work *out);
 

@@ -57,6 +57,8 @@ class LastWork(C.Structure):
         ("batch_candidates", C.c_uint64),
         ("batch_max_err", C.c_float),
         ("batch_delta", C.c_float),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
     ]
 
 

@@ -236,6 +236,7 @@ static int io_flush(otters_ctx* c) {
     if (!c->io_open) return OTTERS_OK;
     const int sl = c->io_slot;
     OTTERS_CUDA(cudaMemcpyAsync(c->d_io, c->h_io[sl], c->io_used, cudaMemcpyHostToDevice, c->stream));
+    c->last.h2d_bytes += c->io_used;
     OTTERS_CUDA(cudaEventRecord(c->ev_io[sl], c->stream));
     c->io_pending[sl] = true;
     c->io_slot ^= 1;
@@ -706,6 +707,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (rc) return rc;
     OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[0], bytes, cudaMemcpyDeviceToHost, s));
     OTTERS_CUDA(cudaStreamSynchronize(s));
+    c->last.d2h_bytes += bytes;
     const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
     const Cand* list = reinterpret_cast<const Cand*>(c->h_result + sizeof(ResultHeader));
     const uint32_t flags = (uint32_t)hdr->extra[0];
@@ -1193,6 +1195,7 @@ static int upload_row_mask(otters_ctx* c, const otters_vec_query* q, uint64_t n_
     }
     if (bits & 31) h[w32 - 1] |= ~0u << (bits & 31);  // rows >= mask length are kept (src/vec.rs:234,297)
     OTTERS_CUDA(cudaMemcpyAsync(c->d_mask, h, w32 * 4, cudaMemcpyHostToDevice, c->stream));
+    c->last.h2d_bytes += w32 * 4;
     // the staging buffer is reused by run_queries: make sure the copy has been consumed
     OTTERS_CUDA(cudaStreamSynchronize(c->stream));
     *d_mask = c->d_mask;
