@@ -938,7 +938,8 @@ static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint
         if (rc) return rc;
         OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[run.result_list], bytes, cudaMemcpyDeviceToHost, s));
         OTTERS_CUDA(cudaStreamSynchronize(s));
-        }
+        c->last.d2h_bytes += bytes;
+    }
     const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
     const uint32_t n = hdr->count;
     c->last.rows_scored = hdr->rows_scored;
@@ -1816,7 +1817,8 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
         if (r2) return r2;
         OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         OTTERS_CUDA(cudaStreamSynchronize(s));
-            memcpy(hstats, c->h_result, 2 * sizeof(unsigned long long));
+        c->last.d2h_bytes += 2 * sizeof(unsigned long long);
+        memcpy(hstats, c->h_result, 2 * sizeof(unsigned long long));
         return OTTERS_OK;
     };
     const bool on_device = d_records || (c->ex_active && !out_len);  // result stays in HBM: no copy, no sync unless stats are wanted

@@ -141,29 +141,30 @@ class CudaShard:
         return self.peer is not None
 
     def search_fused(self, vq, fp, k: int, fetch: bool = True, want_stats: bool = False):
-        """Local search with the exchange and the merge fused into the selection kernel (no NCCL call)."""
+        """Local search with the exchange and the merge fused into the selection kernel (no NCCL call).
+        Returns ((rows, scores, query ids), stats); the arrays are views of buffers that the next call overwrites."""
         ffi = self._ffi
-        assert self.peer is not None
         self._seq += 1
-        st = ffi.QueryStats()
-        out_len = C.c_uint64(0)
+        cache = getattr(self, "_fused_cache", None)
+        if cache is None or cache[0] < k:
+            # everything that does not change from query to query is bound once: this call sits on the critical path
+            out = (np.zeros(k, np.uint64), np.zeros(k, np.float32), np.zeros(k, np.uint32))
+            cache = self._fused_cache = (
+                k, out, out[0].ctypes.data_as(ffi.c_u64p), out[1].ctypes.data_as(ffi.c_f32p), out[2].ctypes.data_as(ffi.c_u32p),
+                C.c_uint64(0), ffi.QueryStats(), C.byref(self.map), C.byref(self.peer))
+            if not self.is_meta:
+                self.store._flush()
+        _, out, p_idx, p_score, p_qid, out_len, st, map_ref, peer_ref = cache
         if self.is_meta:
-            args = (None, self.store.handle, C.byref(vq), fp.byref() if fp else None)
+            vs, ms, flt = None, self.store.handle, (fp.byref() if fp else None)
         else:
-            self.store._flush()
-            args = (self.store._handle(), None, C.byref(vq), None)
+            vs, ms, flt = self.store._handle(), None, None
+        st_ref = C.byref(st) if want_stats else None
         if fetch:
-            if getattr(self, "_out_k", 0) < k:  # output buffers are reused from call to call (results are copied out below)
-                self._out = (np.zeros(k, np.uint64), np.zeros(k, np.float32), np.zeros(k, np.uint32))
-                self._out_ptr = (self._out[0].ctypes.data_as(ffi.c_u64p), self._out[1].ctypes.data_as(ffi.c_f32p),
-                                 self._out[2].ctypes.data_as(ffi.c_u32p))
-                self._out_k = k
-            idx, score, qid = self._out
-            rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, *self._out_ptr, k, C.byref(out_len),
-                                           C.byref(st) if want_stats else None)
+            rc = ffi.otters_query_exchange(vs, ms, C.byref(vq), flt, map_ref, peer_ref, self._seq, p_idx, p_score, p_qid, k,
+                                           C.byref(out_len), st_ref)
         else:
-            rc = ffi.otters_query_exchange(*args, C.byref(self.map), C.byref(self.peer), self._seq, None, None, None, 0, None,
-                                           C.byref(st) if want_stats else None)
+            rc = ffi.otters_query_exchange(vs, ms, C.byref(vq), flt, map_ref, peer_ref, self._seq, None, None, None, 0, None, st_ref)
         if rc != 0:
             from .types import OttersError
 
@@ -171,7 +172,7 @@ class CudaShard:
         if not fetch:
             return None, st
         m = min(out_len.value, k)
-        return (idx[:m].copy(), score[:m].copy(), qid[:m].copy()), st
+        return (out[0][:m], out[1][:m], out[2][:m]), st
 
     def enqueue(self, vq, fp, k: int, want_stats: bool = False):
         """Enqueues local search + all-gather on the context's stream; returns the gathered record tensor."""

@@ -80,6 +80,7 @@ for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob
             fused_ok = True
             for rep in range(3):  # both parities of the double-buffered areas
                 got, _ = shv.search_fused(vq, None, k)
+                got = tuple(a.copy() for a in got)  # views of buffers the next call overwrites
                 assert_same_results(got, want, f"fused vec {metric.name} nq={nq} rank {rank} rep {rep}")
             assert shardc.enable_peer_exchange()
             got, st = shardc.search_fused(vq, fp, k, want_stats=True)
