@@ -112,6 +112,11 @@ struct otters_ctx {
     size_t h_stage_bytes = 0;
     uint8_t* h_result = nullptr;
     size_t h_result_bytes = 0;
+    // zero-copy result area of the fused-selection path: mapped pinned memory the selection kernel writes the final
+    // header + candidates into, so a blocking query ends with a stream sync instead of a D2H copy + sync
+    uint8_t* h_zc = nullptr;
+    uint8_t* d_zc = nullptr;     // device alias of h_zc
+    bool want_host_result = false;  // the entry point being served will read the result on the host
 
     cudaEvent_t ev[8]{};
     bool timing = false;          // record the phase events for the query being enqueued
@@ -217,6 +222,7 @@ static int begin_query(otters_ctx* c) {
     c->last = otters_last_work{};
     c->timed_single = c->timed_meta = c->timed_rowmask = false;
     c->timing = c->tuning.timing == 1;
+    c->want_host_result = false;
     return OTTERS_OK;
 }
 
@@ -506,6 +512,7 @@ struct QueryRun {
     uint64_t k_eff = 0;
     bool big = false;          // result lives in ctx->d_emit-sized list (emit-all path)
     bool prefetched = false;   // header + candidates already sit in ctx->h_result (batched path)
+    bool zero_copy = false;    // the selection kernel writes header + candidates into ctx->h_zc (mapped host memory)
 };
 
 static float host_inv_norm(const float* v, uint32_t dim) {
@@ -868,7 +875,13 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             se.hdr = list_hdr(c, cur ^ 1);
             se.rows_scored_src = c->d_rows_scored;
             se.stats_src = stats_src;
-            if (qi + 1 == q->nq) fill_exchange(c, &se);
+            if (qi + 1 == q->nq) {
+                fill_exchange(c, &se);
+                if (c->want_host_result && !d_records_out) {
+                    se.host_out = c->d_zc;
+                    run->zero_copy = true;
+                }
+            }
             rc = launch_select(se, s);
             if (rc) return rc;
             cur ^= 1;
@@ -933,21 +946,27 @@ static int fetch_results(otters_ctx* c, const QueryRun& run, bool take_max, uint
                          float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, unsigned long long* stats_out) {
     cudaStream_t s = c->stream;
     const size_t bytes = sizeof(ResultHeader) + (size_t)run.k_eff * sizeof(Cand);
-    if (!run.prefetched) {
+    const uint8_t* src = nullptr;
+    if (run.zero_copy) {
+        OTTERS_CUDA(cudaStreamSynchronize(s));  // the selection kernel has written the result into mapped host memory
+        c->last.d2h_bytes += bytes;
+        src = c->h_zc;
+    } else if (!run.prefetched) {
         int rc = ensure_pinned(&c->h_result, &c->h_result_bytes, bytes);
         if (rc) return rc;
         OTTERS_CUDA(cudaMemcpyAsync(c->h_result, c->d_list_raw[run.result_list], bytes, cudaMemcpyDeviceToHost, s));
         OTTERS_CUDA(cudaStreamSynchronize(s));
         c->last.d2h_bytes += bytes;
     }
-    const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(c->h_result);
+    if (!src) src = c->h_result;  // (after ensure_pinned, which may have reallocated it)
+    const ResultHeader* hdr = reinterpret_cast<const ResultHeader*>(src);
     const uint32_t n = hdr->count;
     c->last.rows_scored = hdr->rows_scored;
     if (stats_out) {
         stats_out[0] = hdr->stats[0];
         stats_out[1] = hdr->stats[1];
     }
-    const Cand* list = reinterpret_cast<const Cand*>(c->h_result + sizeof(ResultHeader));
+    const Cand* list = reinterpret_cast<const Cand*>(src + sizeof(ResultHeader));
     uint64_t m = std::min<uint64_t>(n, cap);
     for (uint64_t i = 0; i < m; ++i) {
         if (out_idx) out_idx[i] = row_base + key_row(list[i].key);
@@ -1021,6 +1040,8 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
     OTTERS_CUDA(cudaMemset(c->d_io, 0, 256));
     bind_io(c.get());
     for (auto& e : c->ev_io) OTTERS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    OTTERS_CUDA(cudaHostAlloc((void**)&c->h_zc, sizeof(ResultHeader) + kMaxFusedK * sizeof(Cand), cudaHostAllocMapped));
+    OTTERS_CUDA(cudaHostGetDevicePointer((void**)&c->d_zc, c->h_zc, 0));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_keys, (size_t)c->grid_max * kMaxFusedK * sizeof(uint64_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_counts, (size_t)c->grid_max * sizeof(uint32_t)));
     OTTERS_CUDA(cudaMalloc((void**)&c->d_cta_qids, (size_t)c->grid_max * kMaxFusedK * sizeof(uint32_t)));
@@ -1063,6 +1084,7 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     cudaFree(c->d_cta_qids);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->h_zc) cudaFreeHost(c->h_zc);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1217,6 +1239,7 @@ extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query
     if (q->k == 0 || vs->st.n == 0) return OTTERS_OK;  // take(0) / empty store (tests/vec_store_tests.rs:430-445,488-499)
     rc = begin_query(c);
     if (rc) return rc;
+    c->want_host_result = true;
     const uint32_t* d_mask = nullptr;
     uint32_t mask_words = 0;
     rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
@@ -1797,6 +1820,7 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     if (rc) return rc;
     // durations of otters_query_stats come from per-phase events: recorded only when the caller waits for stats
     if (c->tuning.timing == 0 && stats && !d_records && !(c->ex_active && !out_len)) c->timing = true;
+    c->want_host_result = !d_records && out_len != nullptr;
     // per-chunk collect() errors are swallowed by the reference (src/meta_compute.rs:182): an empty
     // batch or a wrong-dimension query returns no rows but still reports stats
     const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
@@ -2050,6 +2074,10 @@ static int exchange_only(otters_ctx* c, int take_max, const unsigned long long* 
     se.rows_scored_src = c->d_rows_scored;
     se.stats_src = stats_src;
     fill_exchange(c, &se);
+    if (c->want_host_result) {
+        se.host_out = c->d_zc;
+        run->zero_copy = true;
+    }
     int rc = launch_select(se, c->stream);
     if (rc) return rc;
     c->last.kernel_launches += 1;
@@ -2104,6 +2132,7 @@ extern "C" int otters_query_exchange(otters_vecstore* vs, otters_metastore* ms, 
     if (rc) return rc;
     rc = begin_query(c);
     if (rc) return rc;
+    c->want_host_result = want_fetch;
     QueryRun run;
     if (vs->st.n == 0) {
         rc = exchange_only(c, take_max, nullptr, &run);

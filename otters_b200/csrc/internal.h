@@ -142,6 +142,8 @@ struct SelectParams {
     ResultHeader* hdr;
     const unsigned long long* rows_scored_src;
     const unsigned long long* stats_src;
+    // optional zero-copy result: mapped host memory (ResultHeader + k candidates) the final list is also written to
+    uint8_t* host_out;
     // fused peer exchange of the row-sharded search (ex_world > 1): this rank's k records are stored straight into
     // every peer's record area over NVLink, a per-(query parity, rank) flag publishes them, and the same kernel
     // waits for the other ranks' records and merges all of them into `out`

@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
     }
 
     // emit the best kk, ordered
+    Cand* const host_cands = p.host_out ? reinterpret_cast<Cand*>(p.host_out + sizeof(ResultHeader)) : nullptr;
     const bool exchange = p.ex_world > 1;
     const uint32_t par = p.ex_seq & 1u;
     for (uint32_t i = threadIdx.x; i < (exchange ? p.ex_k : (p.records ? p.k : kk)); i += blockDim.x) {
@@ -268,7 +269,10 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
                 uint32_t l = s >> kPosBits, pos = s & ((1u << kPosBits) - 1u);
                 if (l == 0) c.qid = p.prev[pos].qid;
             }
-            if (!exchange) p.out[i] = c;
+            if (!exchange) {
+                p.out[i] = c;
+                if (host_cands) host_cands[i] = c;
+            }
         }
         if (exchange || p.records) {
             otters_topk_record r;
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
                     c.qid = tag;
                     c.pad = 0;
                     p.out[rank] = c;
+                    if (host_cands) host_cands[rank] = c;
                 }
             }
         } else {
@@ -358,18 +363,23 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const __grid_constant__
                 c.qid = s_src[i];
                 c.pad = 0;
                 p.out[i] = c;
+                if (host_cands) host_cands[i] = c;
             }
         }
     }
     if (threadIdx.x == 0) {
         *p.out_count = n_out;
         if (p.tau_out) *p.tau_out = (!exchange && kk == p.k && kk > 0) ? keys[kk - 1] : 0ull;
-        if (p.hdr) {
-            p.hdr->count = n_out;
-            p.hdr->rows_scored = p.rows_scored_src ? *p.rows_scored_src : 0ull;
-            p.hdr->stats[0] = p.stats_src ? p.stats_src[0] : 0ull;
-            p.hdr->stats[1] = p.stats_src ? p.stats_src[1] : 0ull;
-        }
+        ResultHeader h;
+        h.count = n_out;
+        h.pad = 0;
+        h.rows_scored = p.rows_scored_src ? *p.rows_scored_src : 0ull;
+        h.stats[0] = p.stats_src ? p.stats_src[0] : 0ull;
+        h.stats[1] = p.stats_src ? p.stats_src[1] : 0ull;
+        h.stats[2] = h.stats[3] = 0ull;
+        h.extra[0] = h.extra[1] = 0ull;
+        if (p.hdr) *p.hdr = h;
+        if (p.host_out) *reinterpret_cast<ResultHeader*>(p.host_out) = h;
     }
 }
 

@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 /usr/local/cuda/bin/compute-sanitizer --tool memcheck --print-limit 5 --error-exitcode 7 python -m pytest tests/test_gpu_planner.py tests/test_gpu_kats.py -x -q -k "not 60000 and not 20000" > gpurun_out/san1.log 2>&1; echo "memcheck planner+kats rc=$?"; tail -4 gpurun_out/san1.log; grep -c "Invalid\|misaligned" gpurun_out/san1.log
-timeout 1500 /usr/local/cuda/bin/compute-sanitizer --tool memcheck --print-limit 5 --error-exitcode 7 python -m pytest tests/test_gpu_batched.py -x -q -k "300-24-2 or 1000-7-9 or 129-32-256 or special or row_mask or metastore" > gpurun_out/san2.log 2>&1; echo "memcheck batched rc=$?"; tail -4 gpurun_out/san2.log; grep -c "Invalid\|misaligned" gpurun_out/san2.log
-timeout 900 /usr/local/cuda/bin/compute-sanitizer --tool memcheck --print-limit 5 --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q -k "meta_query_parity or row_mask or batch_merged or large_k or ties" > gpurun_out/san3.log 2>&1; echo "memcheck parity rc=$?"; tail -4 gpurun_out/san3.log; grep -c "Invalid\|misaligned" gpurun_out/san3.log
+timeout 900 python -m pytest tests -m gpu -x -q --tb=short 2>&1 | tail -30
