@@ -78,8 +78,6 @@ struct otters_ctx {
     size_t d_mask_words = 0;
     Cand* d_emit = nullptr;             // emit-all path
     size_t emit_cap = 0;
-    otters_topk_record* d_records = nullptr;
-    size_t records_cap = 0;
     // batched (tensor-core) path
     float* d_qh = nullptr;              // hi / lo tf32 split of the staged queries, padded to 256-query tiles
     float* d_ql = nullptr;
@@ -1077,7 +1075,6 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     cudaFree(c->d_scratch_src);
     cudaFree(c->d_mask);
     cudaFree(c->d_emit);
-    cudaFree(c->d_records);
     cudaFree(c->d_qh);
     cudaFree(c->d_ql);
     cudaFree(c->d_qscal);
