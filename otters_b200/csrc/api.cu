@@ -394,7 +394,7 @@ constexpr size_t kMaxFusedFilterBytes = 16 * 1024;
 struct ScanPlan {
     ScanLaunch launch;
     uint32_t off_filter;
-    uint32_t kc, nkc, pitch_s, slots, unit_rows, n_units, cap;
+    uint32_t kc, nkc, pitch_s, slots, unit_rows, unit_small, n_big, n_units, cap;
     uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
     uint32_t planners, off_ring;  // planner front-end (scan_planner.cu): planner warps per CTA (0 = autonomous warps)
 };
@@ -478,7 +478,16 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
         while (unit_rows > 32 && n_rows / unit_rows < want) unit_rows >>= 1;
     }
     pl.unit_rows = unit_rows;
-    pl.n_units = (uint32_t)((n_rows + unit_rows - 1) / unit_rows);
+    // guided schedule: the last ~2 units' worth of rows per warp (per CTA with the planner front-end) are cut into small
+    // units, so the warps finish within one small unit of each other instead of one big one (a 128-row unit of 768-d rows
+    // is 130 µs of one warp's bandwidth)
+    pl.unit_small = t.unit_rows ? unit_rows : (unit_rows > 32 ? 32 : 16);
+    {
+        const uint64_t tail_rows = std::min<uint64_t>(n_rows, (uint64_t)grid * (planner ? 4 : W * 2) * unit_rows);
+        pl.n_big = (uint32_t)((n_rows - tail_rows) / unit_rows);
+        const uint64_t rest = n_rows - (uint64_t)pl.n_big * unit_rows;
+        pl.n_units = pl.n_big + (uint32_t)((rest + pl.unit_small - 1) / pl.unit_small);
+    }
     uint32_t need_ctas = planner ? pl.n_units : (pl.n_units + W - 1) / W;
     if (need_ctas < 1) need_ctas = 1;
     if (grid > need_ctas) grid = need_ctas;
@@ -807,6 +816,8 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.off_filter = pl.off_filter;
     sp.n_units = pl.n_units;
     sp.unit_rows = pl.unit_rows;
+    sp.unit_small = pl.unit_small;
+    sp.n_big = pl.n_big;
     sp.unit_counter = c->d_counter;
     sp.k = (uint32_t)std::min<uint64_t>(k_eff, kMaxFusedK);
     sp.cap = pl.cap;

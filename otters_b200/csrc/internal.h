@@ -68,7 +68,9 @@ struct ScanParams {
     uint32_t chunk_size;
     uint32_t off_filter;        // shared-memory offset of the staged filter
     uint32_t n_units;
-    uint32_t unit_rows;         // 32, 64 or 128
+    uint32_t unit_rows;         // 32, 64 or 128: rows of the first n_big work units
+    uint32_t unit_small;        // 16 or 32: rows of the remaining units (the tail of the store)
+    uint32_t n_big;
     uint32_t* unit_counter;
     // selection
     uint32_t k;

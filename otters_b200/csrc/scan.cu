@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     const float q_inv = p.q_inv;
     const uint32_t dim8 = p.dim & ~7u;
     const uint32_t ntail = p.dim & 7u;
-    const uint32_t rpl = p.unit_rows >> 5;  // rows per lane when building a unit's row list (1, 2 or 4)
     const uint64_t l2pol = policy_evict_first();
 
     // ---- producer state ----
@@ -102,9 +101,15 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
                     u_pref = atomicAdd(p.unit_counter, 1u);
                     if (!EMIT_ALL && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
                 }
-                uint32_t row0 = u * p.unit_rows;
+                // guided schedule: the first n_big units are unit_rows long, the rest (the tail of the store, claimed last)
+                // unit_small long, so that the warps run out of work within one SMALL unit of each other
+                const bool big = u < p.n_big;
+                const uint32_t urows = big ? p.unit_rows : p.unit_small;
+                uint32_t row0 = big ? u * p.unit_rows : p.n_big * p.unit_rows + (u - p.n_big) * p.unit_small;
+                const uint32_t rpl = urows >= 32 ? urows >> 5 : 1;  // rows per lane when building the row list (1, 2 or 4)
                 uint32_t r = row0 + rpl * lane;  // this lane's first row; its rpl rows share one mask word
                 uint32_t bits = (1u << rpl) - 1u;
+                if (rpl * lane >= urows) bits = 0;  // 16-row units: the upper half of the warp has no row
                 if (p.row_mask) {
                     uint32_t w = (r >> 5) < p.row_mask_words ? __ldg(p.row_mask + (r >> 5)) : 0xFFFFFFFFu;
                     bits &= w >> (r & 31);

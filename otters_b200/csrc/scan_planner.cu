@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
     unsigned long long scored = 0;
     if (warp < (int)np) {
         // =============================== planner ===============================
-        const uint32_t rpl = p.unit_rows >> 5;  // rows per lane of a unit (1, 2 or 4); a lane's rows share one mask word
         uint32_t u_pref = 0;
         unsigned long long g_pref = 0;  // grid-wide threshold, read together with the unit id
         if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
@@ -106,9 +105,14 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
                 u_pref = atomicAdd(p.unit_counter, 1u);
                 if (p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
             }
-            const uint32_t row0 = u * p.unit_rows;
+            // guided schedule (see scan.cu): big units first, small units for the tail of the store
+            const bool big = u < p.n_big;
+            const uint32_t urows = big ? p.unit_rows : p.unit_small;
+            const uint32_t row0 = big ? u * p.unit_rows : p.n_big * p.unit_rows + (u - p.n_big) * p.unit_small;
+            const uint32_t rpl = urows >= 32 ? urows >> 5 : 1;  // rows per lane (1, 2 or 4); a lane's rows share one mask word
             const uint32_t r = row0 + rpl * lane;
             uint32_t bits = (1u << rpl) - 1u;
+            if (rpl * lane >= urows) bits = 0;
             if (p.row_mask) {
                 const uint32_t w = (r >> 5) < p.row_mask_words ? __ldg(p.row_mask + (r >> 5)) : 0xFFFFFFFFu;
                 bits &= w >> (r & 31);
