@@ -39,6 +39,7 @@ class ScanTuning(C.Structure):
         ("scan_mode", C.c_uint32),
         ("planners", C.c_uint32),
         ("timing", C.c_uint32),
+        ("batch_passes", C.c_uint32),
     ]
 
 
@@ -59,6 +60,8 @@ class LastWork(C.Structure):
         ("batch_delta", C.c_float),
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
+        ("batch_passes", C.c_uint32),
+        ("batch_attempts", C.c_uint32),
     ]
 
 

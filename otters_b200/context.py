@@ -33,13 +33,14 @@ class Context:
         check(_ffi.otters_ctx_synchronize(self._h))
 
     def set_tuning(self, warps_per_cta=0, slots_per_warp=0, kc_floats=0, ctas_per_sm=0, unit_rows=0, disable_fused_predicate=0,
-                   batch_mode=0, batch_cta_group=0, scan_mode=0, planners=0, timing=0) -> None:
+                   batch_mode=0, batch_cta_group=0, scan_mode=0, planners=0, timing=0, batch_passes=0) -> None:
         """batch_mode: 0 = automatic, 1 = always serve query batches with the tcgen05 kernel, 2 = never.
         batch_cta_group: 0 = automatic (single CTAs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2).
         scan_mode: K1 front-end, 0 = automatic, 1 = autonomous warps, 2 = planner + worker warps; planners: planner warps per CTA.
-        timing: per-phase CUDA events; 0 = only for blocking MetaStore queries with stats, 1 = always, 2 = never."""
+        timing: per-phase CUDA events; 0 = only for blocking MetaStore queries with stats, 1 = always, 2 = never.
+        batch_passes: tensor-core kernel, 0 = single-pass tf32 selection first and 3xTF32 if its certificate fails, 1 / 3 = only that."""
         t = _ffi.ScanTuning(warps_per_cta, slots_per_warp, kc_floats, ctas_per_sm, unit_rows, disable_fused_predicate, batch_mode,
-                            batch_cta_group, scan_mode, planners, timing)
+                            batch_cta_group, scan_mode, planners, timing, batch_passes)
         check(_ffi.otters_ctx_set_tuning(self._h, C.byref(t)))
 
     def last_work(self) -> Dict[str, float]:

@@ -303,8 +303,11 @@ struct DeviceGuard {
 };
 
 // ---- device vector storage shared by VecStore and MetaStore ---------------------------------------
+constexpr uint32_t kSinglePassBackoff = 16;
+
 struct VecStorage {
     otters_ctx* ctx = nullptr;
+    uint32_t single_pass_backoff = 0;  // batches left that skip the single-pass tf32 selection (see run_queries)
     uint32_t dim = 0;
     uint32_t pitch = 0;  // floats per stored row: dim rounded up to 4 (16-byte rows for TMA bulk copies)
     uint64_t n = 0, cap = 0;
@@ -583,8 +586,9 @@ static bool batch_eligible(const otters_ctx* c, const otters_vec_query* q, uint6
 
 static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
                        const uint32_t* d_row_mask, uint32_t row_mask_words, otters_topk_record* d_records_out, ShardMap map,
-                       const unsigned long long* stats_src, QueryRun* run, bool* accepted) {
+                       const unsigned long long* stats_src, QueryRun* run, uint32_t passes, bool* accepted) {
     *accepted = false;
+    c->last.batch_attempts += 1;
     cudaStream_t s = c->stream;
     const uint32_t dim_pad = st->pitch;
     const uint64_t k_eff = run->k_eff;
@@ -617,7 +621,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     }
     rc = launch_split_queries(c->d_query, q->nq, nq_pad, dim_pad, c->d_qh, c->d_ql, d_qn2, d_qmax2, s);
     if (rc) return rc;
-    rc = launch_batch_delta(q->metric, st->dim, d_qmax2, st->d_minv_bits, d_delta, s);
+    rc = launch_batch_delta(q->metric, st->dim, passes, d_qmax2, st->d_minv_bits, d_delta, s);
     if (rc) return rc;
 
     // single CTAs by default: with the raw-hi operand split they measured faster than CTA pairs (6.04 vs 6.33 ms on
@@ -658,6 +662,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bp.cta_keys = c->d_cta_keys;
     bp.cta_qids = c->d_cta_qids;
     bp.cta_counts = c->d_cta_counts;
+    bp.passes = passes;
     if (const char* e = getenv("OTTERS_BATCH_DBG")) bp.dbg = (uint32_t)atoi(e);  // timing experiments; results are garbage
     rec_event(c, 2);
     rec_event(c, 3);
@@ -743,8 +748,8 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         }
     }
     if (getenv("OTTERS_BATCH_TRACE"))
-        fprintf(stderr, "[otters batch] k=%llu count=%u flags=%u max_err=%g delta=%g excl=%g e_k=%g verified=%d\n",
-                (unsigned long long)k_eff, hdr->count, flags, max_err, delta, excl ? key_score((uint64_t)excl << 32, take_max) : NAN,
+        fprintf(stderr, "[otters batch] passes=%u k=%llu count=%u flags=%u max_err=%g delta=%g excl=%g e_k=%g verified=%d\n",
+                passes, (unsigned long long)k_eff, hdr->count, flags, max_err, delta, excl ? key_score((uint64_t)excl << 32, take_max) : NAN,
                 hdr->count ? key_score(list[hdr->count - 1].key, take_max) : NAN, (int)ok);
     c->last.batch_max_err = max_err;
     c->last.batch_delta = delta;
@@ -755,6 +760,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         return OTTERS_OK;
     }
     c->last.batch_used = 1;
+    c->last.batch_passes = passes;
     run->result_list = 0;
     run->big = false;
     run->prefetched = true;
@@ -779,12 +785,29 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (rc) return rc;
 
     if (!c->ex_active && batch_eligible(c, q, n_rows, k_eff)) {
+        // selection runs single-pass tf32 first (a third of the MMAs and of the operand traffic; error bound 2^-9 |q||v|);
+        // when its certificate fails the batch is redone with the 3xTF32 split (2^-15), and only then query by query.
+        // A store whose single-pass certificate failed goes straight to 3xTF32 for its next kSinglePassBackoff batches.
+        const uint32_t want = c->tuning.batch_passes;
+        const bool try_single = want == 1 || (want == 0 && st->single_pass_backoff == 0);
+        if (want == 0 && st->single_pass_backoff) st->single_pass_backoff -= 1;
         bool accepted = false;
-        rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, &accepted);
-        if (rc) return rc;
-        if (accepted) return OTTERS_OK;
-        rc = reset_scan_state(c);  // selection could not be verified: exact path, query by query
-        if (rc) return rc;
+        if (try_single) {
+            rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, 1, &accepted);
+            if (rc) return rc;
+            if (accepted) return OTTERS_OK;
+            if (want == 0) st->single_pass_backoff = kSinglePassBackoff;
+            rc = reset_scan_state(c);
+            if (rc) return rc;
+        }
+        if (want != 1) {
+            c->last.batch_fallback = 0;
+            rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, 3, &accepted);
+            if (rc) return rc;
+            if (accepted) return OTTERS_OK;
+            rc = reset_scan_state(c);  // selection could not be verified: exact path, query by query
+            if (rc) return rc;
+        }
     }
 
     // per-query inverse norms for the streaming kernel (a by-value kernel parameter)

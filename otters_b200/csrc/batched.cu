@@ -362,7 +362,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qh,
              const __grid_constant__ CUtensorMap tm_ql, const __grid_constant__ BatchParams p) {
     using G = Geo<CG>;
-    constexpr uint32_t STAGES = G::STAGES, STAGE_BYTES = G::STAGE_BYTES, B_BYTES = G::B_BYTES;
+    constexpr uint32_t B_BYTES = G::B_BYTES;
+    constexpr uint32_t RING_BYTES = G::STAGES * G::STAGE_BYTES;
+    constexpr uint32_t MAX_STAGES = RING_BYTES / (A_BYTES + B_BYTES);  // single-pass stages hold V | Qhi only
+    // the ring is cut at run time: 3xTF32 stages are Vhi | Vlo | Qhi | Qlo, single-pass stages V | Qhi (twice as many)
+    const bool single = p.passes == 1;  // one tf32 MMA per product (selection with a wider error bound) instead of the 3xTF32 split
+    const uint32_t STAGE_BYTES = single ? A_BYTES + B_BYTES : G::STAGE_BYTES;
+    const uint32_t STAGES = single ? MAX_STAGES : G::STAGES;
+    const uint32_t Q_OFF = single ? A_BYTES : 2 * A_BYTES;  // Qhi inside a stage
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -373,14 +380,14 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     // the operand tiles need 1024-byte alignment (128B swizzle atoms); both CTAs of a pair compute the same offsets
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* aux = smem + STAGES * STAGE_BYTES;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);       // [STAGES] this CTA's TMA loads landed
-    uint64_t* bar_cast = bar_full + STAGES;                       // [STAGES] (rank 0) V split into hi/lo in every CTA of the pair
-    uint64_t* bar_empty = bar_cast + STAGES;                      // [STAGES] MMAs reading the stage completed
-    uint64_t* bar_tfull = bar_empty + STAGES;                     // [2] accumulator complete
+    uint8_t* aux = smem + RING_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);       // [MAX_STAGES] this CTA's TMA loads landed
+    uint64_t* bar_cast = bar_full + MAX_STAGES;                   // [MAX_STAGES] (rank 0) V split into hi/lo in every CTA of the pair
+    uint64_t* bar_empty = bar_cast + MAX_STAGES;                  // [MAX_STAGES] MMAs reading the stage completed
+    uint64_t* bar_tfull = bar_empty + MAX_STAGES;                 // [2] accumulator complete
     uint64_t* bar_tempty = bar_tfull + 2;                         // [2] (rank 0) accumulator drained by every epilogue thread
-    uint64_t* bar_full2 = bar_tempty + 2;                         // [STAGES] (rank 0, CG = 2) the loads of BOTH CTAs landed
-    static_assert((4 * STAGES + 4) * 8 <= kAuxTmemSlot, "barriers overflow their shared-memory area");
+    uint64_t* bar_full2 = bar_tempty + 2;                         // [MAX_STAGES] (rank 0, CG = 2) the loads of BOTH CTAs landed
+    static_assert((4 * MAX_STAGES + 4) * 8 <= kAuxTmemSlot, "barriers overflow their shared-memory area");
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + kAuxTmemSlot);
     CtaHdr* hdr = reinterpret_cast<CtaHdr*>(aux + kAuxHdr);
     uint64_t* cand_keys = reinterpret_cast<uint64_t*>(aux + kAuxCand);
@@ -419,7 +426,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const bool raw_hi = (p.dbg & 16u) == 0;  // default; bit 16 of the debug word restores the in-place rounded-hi split for A/B runs
+    const bool raw_hi = single || (p.dbg & 16u) == 0;  // default; bit 16 of the debug word restores the in-place rounded-hi split for A/B runs
     const uint32_t n_rowtiles = (p.n_rows + G::TILE_ROWS - 1) / G::TILE_ROWS;
     const uint32_t n_tiles = n_rowtiles * p.n_qtiles;
     const uint32_t nkb = p.nkb;
@@ -439,10 +446,11 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                         mbar_arrive_expect_tx(&bar_full[s], 0);
                         continue;
                     }
-                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + 2 * B_BYTES);
+                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + (single ? 1u : 2u) * B_BYTES);
                     tma_load_2d(st, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full[s]);
-                    tma_load_2d(st + 2 * A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
+                    tma_load_2d(st + Q_OFF, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
+                    if (!single)
+                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
                 }
             }
         }
@@ -462,8 +470,18 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t d_vh = umma_desc_sw128(sa), d_vl = umma_desc_sw128(sa + A_BYTES);
-                    const uint64_t d_qh = umma_desc_sw128(sa + 2 * A_BYTES), d_ql = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
-                    if (raw_hi) {
+                    const uint64_t d_qh = umma_desc_sw128(sa + Q_OFF), d_ql = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+                    if (single) {
+                        // single-pass selection: one tf32 MMA per k-step on the landed tiles (V read at 19 bits, Q rounded)
+                        if constexpr (CG == 2) mbar_wait_cluster(&bar_full2[s], ph);
+                        else mbar_wait(&bar_full[s], ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (uint32_t kk = 0; kk < BK / UK; ++kk) {
+                            const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);
+                            umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
+                        }
+                    } else if (raw_hi) {
                         // the landed fp32 tile itself is the hi operand (the tensor core reads its upper 19 bits), so two
                         // thirds of the stage's MMAs start as soon as the loads land and hide the split of the lo tile
                         if constexpr (CG == 2) mbar_wait_cluster(&bar_full2[s], ph);
@@ -521,7 +539,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         // ===== split warps: V tile -> hi (in place) and lo =====
         const int tt = tid - 128;
         uint32_t it = 0;
-        for (uint32_t t = unit; t < n_tiles; t += n_units) {
+        for (uint32_t t = unit; t < n_tiles && !single; t += n_units) {  // single-pass selection needs no lo tile
             const uint32_t rt = t / p.n_qtiles;
             if (!tile_live<CG>(p, rt)) continue;
             for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
@@ -709,8 +727,11 @@ __global__ void split_queries_kernel(const float* q, uint32_t nq, uint32_t nq_pa
 
 // Bound on |tensor-core score - exact score| for this batch: kappa * |q|max * |v|max for dot
 // products, kappa for cosine, kappa * (|q|max + |v|max)^2 for squared distances, kappa = 2^-15 * max(1, dim / 1024).
-__global__ void batch_delta_kernel(int metric, uint32_t dim, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta) {
-    const double kappa = ldexp(1.0, -15) * fmax(1.0, (double)dim / 1024.0) * 1.01;
+__global__ void batch_delta_kernel(int metric, uint32_t dim, uint32_t passes, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits,
+                                   float* delta) {
+    // 3xTF32: products exact to 2^-22, truncating fp32 accumulation over 3*dim/8 MMA steps -> 2^-15 per 1024 columns.
+    // single pass: V is read at 19 bits (truncation, 2^-10), Q is rounded to tf32 (2^-11) -> 2^-9 covers both plus the accumulation.
+    const double kappa = (passes == 1 ? ldexp(1.0, -9) : ldexp(1.0, -15)) * fmax(1.0, (double)dim / 1024.0) * 1.01;
     double d;
     if (metric == OTTERS_METRIC_COSINE) {
         d = kappa;
@@ -916,8 +937,9 @@ int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t 
     return OTTERS_OK;
 }
 
-int launch_batch_delta(int metric, uint32_t dim, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta, cudaStream_t s) {
-    batch_delta_kernel<<<1, 1, 0, s>>>(metric, dim, qmax2_bits, vmin_inv_bits, delta);
+int launch_batch_delta(int metric, uint32_t dim, uint32_t passes, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta,
+                       cudaStream_t s) {
+    batch_delta_kernel<<<1, 1, 0, s>>>(metric, dim, passes, qmax2_bits, vmin_inv_bits, delta);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

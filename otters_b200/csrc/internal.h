@@ -191,6 +191,7 @@ struct BatchParams {
     uint64_t* cta_keys;          // [grid][k] approximate keys, best first
     uint32_t* cta_qids;          // [grid][k]
     uint32_t* cta_counts;        // [grid]
+    uint32_t passes;             // tf32 MMAs per product: 3 (3xTF32 split, fp32-faithful) or 1 (selection only, wider error bound)
     uint32_t dbg;                // timing experiments only (OTTERS_BATCH_DBG): 1 no loads, 2 no split, 4 no epilogue, 8 no MMAs
 };
 struct BatchLaunch {
@@ -225,7 +226,8 @@ struct RescoreParams {
 uint32_t batch_smem_bytes(uint32_t cap);
 int launch_split_queries(const float* q, uint32_t nq, uint32_t nq_pad, uint32_t dim_pad, float* qh, float* ql, float* qn2,
                          uint32_t* qmax2_bits, cudaStream_t s);
-int launch_batch_delta(int metric, uint32_t dim, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta, cudaStream_t s);
+int launch_batch_delta(int metric, uint32_t dim, uint32_t passes, const uint32_t* qmax2_bits, const uint32_t* vmin_inv_bits, float* delta,
+                       cudaStream_t s);
 int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s);
 int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s);
 int launch_min_inv_norm(const float* inv, uint64_t n, uint32_t* out_bits, cudaStream_t s);

@@ -141,6 +141,7 @@ pub struct otters_scan_tuning {
     pub scan_mode: u32,        // K1 front-end: 0 auto, 1 autonomous warps, 2 planner + worker warps
     pub planners: u32,         // planner warps per CTA (0 auto)
     pub timing: u32,           // 0 auto, 1 always record phase events, 2 never
+    pub batch_passes: u32,     // 0 auto (single-pass tf32 selection, then 3xTF32), 1 single pass only, 3 3xTF32 only
 }
 
 extern "C" {
