@@ -477,7 +477,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                         else mbar_wait(&bar_full[s], ph);
                         tc_fence_after();
 #pragma unroll
-                        for (uint32_t kk = 0; kk < BK / UK; ++kk) {
+                        for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
                             const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);
                             umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
                         }
@@ -625,7 +625,39 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 // threshold of this chunk as a float pre-test (the exact key test is inside the push)
                 const uint64_t tau = ld_volatile_u64(&hdr->tau);
                 const float tau_s = tau ? key_score(tau, take_max) : (take_max ? -INFINITY : INFINITY);
-                // fast path: straight-line scoring of the 32 columns, one bit per passing column
+                if (!p.has_filter && c * 32 + 32 <= nq_tile && !(p.dbg & 32u)) {  // warp-uniform
+                    // common case (unfiltered, full chunk): two or three instructions per pair.  In the signed domain
+                    // (larger = better) only the chunk maximum matters: below the threshold nothing can enter the list and
+                    // the maximum is the best excluded score.  z turns NaN iff some score is inf / NaN.
+                    const float tau_t = tau ? tau_s * sgn : -INFINITY;
+                    float cmax = -INFINITY, zz[4] = {0.f, 0.f, 0.f, 0.f};  // four short chains instead of one long one
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const float tj = batch_score<METRIC>(__uint_as_float(v[j]), p.q_scal, q_base + c * 32 + j, rs) * sgn;
+                        cmax = fmaxf(cmax, tj);
+                        zz[j & 3] = fmaf(tj, 0.f, zz[j & 3]);
+                    }
+                    const float z = (zz[0] + zz[1]) + (zz[2] + zz[3]);
+                    const bool hit = live && (!(z == 0.f) || cmax >= tau_t);
+                    if (!__any_sync(FULL, hit)) {
+                        if (live) xbest = fmaxf(xbest, cmax);
+                        continue;
+                    }
+                    // some lane has a candidate (or an odd value): column by column, re-read from TMEM, exact bookkeeping
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const uint32_t qi = q_base + c * 32 + j;
+                        const float sj = batch_score<METRIC>(__uint_as_float(tmem_ld_32x32b_x1(taddr + c * 32 + j)), p.q_scal, qi, rs);
+                        if (live && !(fabsf(sj) <= FLT_MAX)) nonfinite = true;
+                        const bool top = take_max ? sj >= tau_s : sj <= tau_s;
+                        if (live && !top) xbest = fmaxf(xbest, sj * sgn);
+                        const bool psh = live && top;
+                        if (__any_sync(FULL, psh))
+                            warp_push_pairs(hdr, cand_keys, cand_qids, p.cap, p.k, psh, make_key(sj, row, take_max), qi, p.g_tau, lane);
+                    }
+                    continue;
+                }
+                // general path (vec_filter, ragged last chunk): straight-line scoring of the 32 columns, one bit per passing column
                 uint32_t pass = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) {
