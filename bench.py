@@ -39,7 +39,7 @@ WORKLOADS = {
                    desc="MetaStore 10Mx768 fp32 Cosine top-100, chunk 1024, meta_filter price.gt & item.eq & ts.gte"),
     "c1": dict(rows=100_000, dim=128, chunk=0, metric="Cosine", k=10, meta=False, desc="VecStore 100kx128 fp32 Cosine top-10"),
     "c2": dict(rows=1_000_000, dim=768, chunk=0, metric="DotProduct", k=100, meta=False, nq=1024,
-               desc="VecStore 1Mx768 fp32 Dot, batch of 1024 queries, top-100 (one merged list; tcgen05 3xTF32 kernel + exact re-scoring)"),
+               desc="VecStore 1Mx768 fp32 Dot, batch of 1024 queries, top-100 (one merged list; tcgen05 tf32 selection + exact re-scoring)"),
     "c3": dict(rows=10_000_000, dim=128, chunk=1024, metric="Cosine", k=100, meta=True,
                desc="MetaStore 10Mx128 Cosine top-100, chunk 1024, meta_filter price.gt & item.eq & ts.gte"),
     "c4": dict(rows=10_000_000, dim=768, chunk=0, metric="Euclidean", k=100, meta=False, desc="VecStore 10Mx768 fp32 L2 top-100"),

@@ -1,4 +1,4 @@
-"""Parity of the batched tensor-core path (K2: TMA-fed tcgen05 3xTF32 contraction + exact re-scoring,
+"""Parity of the batched tensor-core path (K2: TMA-fed tcgen05 tf32 selection — single pass, then 3xTF32 — + exact re-scoring,
 otters_b200/csrc/batched.cu) against the CPU oracle: one merged list over all (row, query) pairs
 (reference src/vec.rs:217-219, :243-266), identical rows and query ids, bit-identical scores.
 The tests force the tensor-core kernel (batch_mode=1) and check that it — not the per-query fallback —
