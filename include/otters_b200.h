@@ -81,7 +81,10 @@ typedef struct otters_metastore otters_metastore;
  * ------------------------------------------------------------------------------------------- */
 OTTERS_API int otters_ctx_create(int device, void *cuda_stream, otters_ctx **out);
 OTTERS_API int otters_ctx_destroy(otters_ctx *ctx);
-OTTERS_API int otters_ctx_synchronize(otters_ctx *ctx);
+OTTERS_API int otters_ctx_synchronize(otters_ctx *ctx); /* waits for the context's stream and for every lane (otters_query_submit) */
+/* Orders the context's own stream after everything enqueued on its lanes so far (no host wait): work or events the caller
+ * enqueues on that stream afterwards run once all submitted queries have finished. */
+OTTERS_API int otters_ctx_join(otters_ctx *ctx);
 OTTERS_API const char *otters_last_error(void);
 OTTERS_API const char *otters_version(void);
 
@@ -102,6 +105,10 @@ typedef struct {
     uint32_t batch_passes; /* tensor-core kernel: 0 = automatic (single-pass tf32 selection first, 3xTF32 when its certificate
                               fails), 1 = single pass only, 3 = 3xTF32 only.  Results never change: every returned score is
                               re-computed in the reference's arithmetic and the selection is certified or redone */
+    uint32_t separate_select; /* 1: run the final selection (K3) as its own kernel instead of in the last CTA of the scan kernel */
+    uint32_t lazy_prune;      /* 1: evaluate the zonemap / Bloom chunk rules lazily inside the scan kernel (per work unit) instead
+                                 of running K0 first: one launch per query, but measured slower — every unit pays a dependent
+                                 L2 round trip and 8 units re-evaluate each 1024-row chunk (profiles/r2_prune_ab.txt) */
 } otters_scan_tuning;
 OTTERS_API int otters_ctx_set_tuning(otters_ctx *ctx, const otters_scan_tuning *t);
 
@@ -142,6 +149,10 @@ OTTERS_API int otters_vecstore_add_device(otters_vecstore *vs, const float *d_ro
 /* Appends n rows of the counter-based synthetic generator x = (splitmix64(seed ^ (row*dim+col)) >> 40) * 2^-23 - 1
  * (row = absolute row id starting at first_row), generated on the device.  Bench/test utility. */
 OTTERS_API int otters_vecstore_add_synthetic(otters_vecstore *vs, uint64_t first_row, uint64_t n, uint64_t seed);
+/* Overwrites n stored rows (row ids local to this store, any order; data = n * dim floats in host memory) and recomputes
+ * their inverse norms.  Bench/test utility: how near-duplicates of a query are planted into a synthetic store (SURVEY.md
+ * §8d, config C5).  Waits for every query in flight first. */
+OTTERS_API int otters_vecstore_set_rows(otters_vecstore *vs, const uint64_t *rows, const float *data, uint64_t n);
 OTTERS_API uint64_t otters_vecstore_len(const otters_vecstore *vs); /* VecStore::len */
 OTTERS_API uint32_t otters_vecstore_dim(const otters_vecstore *vs);
 /* debug/parity: copies inverse norms [first, first+n) to host */
@@ -230,6 +241,7 @@ typedef struct {
 OTTERS_API int otters_metastore_build(otters_ctx *ctx, const otters_build_params *p, otters_metastore **out,
                            otters_build_stats *stats /* nullable */);
 OTTERS_API int otters_metastore_destroy(otters_metastore *ms);
+OTTERS_API int otters_metastore_set_rows(otters_metastore *ms, const uint64_t *rows, const float *data, uint64_t n); /* as otters_vecstore_set_rows */
 OTTERS_API uint64_t otters_metastore_n_chunks(const otters_metastore *ms); /* MetaStore::n_chunks */
 OTTERS_API uint64_t otters_metastore_chunk_size(const otters_metastore *ms);
 OTTERS_API uint64_t otters_metastore_len(const otters_metastore *ms);
@@ -300,10 +312,13 @@ typedef struct {
 OTTERS_API int otters_query_local_device(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q,
                               const otters_filter *filter, const otters_shard_map *map, void *d_records,
                               otters_query_stats *stats /* nullable */);
-/* Fused exchange over peer memory (NVLink / NVSwitch).  Every rank owns a record area of 2 * world * k_max
- * otters_topk_record and a flag area of 2 * world uint32 (zero-initialised), both mapped into every peer process
- * (CUDA IPC / symmetric memory; otters_b200/sharded.py uses torch.distributed._symmetric_memory for the mapping).
- * peer_records[p] / peer_flags[p] are rank p's areas as mapped into THIS process (p == rank: the local areas). */
+/* Fused exchange over peer memory (NVLink / NVSwitch).  Every rank owns a record area of OTTERS_EXCHANGE_SLOTS * world *
+ * k_max otters_topk_record and a flag area of OTTERS_EXCHANGE_SLOTS * world uint32 (zero-initialised), both mapped into every
+ * peer process (CUDA IPC / symmetric memory; otters_b200/sharded.py uses torch.distributed._symmetric_memory for the mapping).
+ * peer_records[p] / peer_flags[p] are rank p's areas as mapped into THIS process (p == rank: the local areas).  The areas
+ * are OTTERS_EXCHANGE_SLOTS deep on the query sequence number: twice the two queries a context keeps in flight, so a rank
+ * that runs ahead never overwrites records a slower peer is still merging. */
+#define OTTERS_EXCHANGE_SLOTS 4
 typedef struct {
     uint32_t world;              /* 2..8 */
     uint32_t rank;
@@ -312,11 +327,10 @@ typedef struct {
     uint32_t *const *peer_flags; /* [world] */
 } otters_peer_exchange;
 
-/* Row-sharded query with the exchange fused into the selection kernel: local prune/scan, then ONE kernel selects
- * the local top-k, stores its k records straight into every peer's record area, publishes them with a release
- * flag, waits for the other ranks' flags and merges world * k records — no NCCL call and no extra launch on the
- * query path.  `seq` numbers the queries of this exchange (1, 2, 3, ... identical on every rank; areas are double
- * buffered on its parity).  Every rank must call it for every query.  With out_idx = out_score = out_qid = NULL and
+/* Row-sharded query with the exchange fused into the selection: ONE kernel per query prunes, scans, selects the local
+ * top-k (in its last CTA), stores its k records straight into every peer's record area, publishes them with a release
+ * flag, waits for the other ranks' flags and merges world * k records — no NCCL call and no extra launch on the query
+ * path.  `seq` numbers the queries of this exchange (1, 2, 3, ... identical on every rank; it selects the area slot).  Every rank must call it for every query.  With out_idx = out_score = out_qid = NULL and
  * cap = 0 the call only enqueues (no copy, no sync).  Returns OTTERS_ERR_UNSUPPORTED for plans the fused selection
  * does not serve (take counts above 1024 or above k_max, batches routed to the tensor-core kernel); callers then
  * use otters_query_local_device + an all-gather + otters_topk_merge_device.  Stats are local to the shard. */
@@ -324,6 +338,21 @@ OTTERS_API int otters_query_exchange(otters_vecstore *vs, otters_metastore *ms, 
                           const otters_filter *filter, const otters_shard_map *map, const otters_peer_exchange *ex,
                           uint64_t seq, uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap,
                           uint64_t *out_len, otters_query_stats *stats /* nullable */);
+
+/* Non-blocking queries.  otters_query_submit enqueues ONE query — chunk pruning, row predicate, scan, selection, and the peer
+ * exchange when `ex` is given — on one of the two lanes of the store's context (a lane = its own CUDA stream + scratch +
+ * pinned input / result buffers) and returns at once with a ticket; otters_query_wait blocks until that query has finished
+ * and copies its result and statistics out (durations are not split per phase on this path).  Two tickets may be
+ * outstanding per context: submit query i+1 before waiting for query i, and its input copy, its launch and the head of its
+ * scan overlap the tail, the selection and the exchange of query i — the per-call host cost no longer sits between two
+ * scans.  Inputs are copied before submit returns.  A lane holds one query: submitting twice more without waiting abandons
+ * the older result.  vs / ms / filter / map as in otters_query_local_device; ex == NULL: single-GPU query (seq ignored),
+ * else as in otters_query_exchange (every rank submits every query with the same seq).  otters_ctx_synchronize waits for
+ * all lanes.  The store must not be modified while tickets are outstanding. */
+OTTERS_API int otters_query_submit(otters_vecstore *vs, otters_metastore *ms, const otters_vec_query *q, const otters_filter *filter,
+                        const otters_shard_map *map, const otters_peer_exchange *ex, uint64_t seq, uint64_t *ticket);
+OTTERS_API int otters_query_wait(otters_ctx *ctx, uint64_t ticket, uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap,
+                      uint64_t *out_len, otters_query_stats *stats /* nullable */);
 
 /* Appends n_local rows of the synthetic generator whose global row ids follow `map` (bench/test utility). */
 OTTERS_API int otters_vecstore_add_synthetic_sharded(otters_vecstore *vs, const otters_shard_map *map, uint64_t n_local, uint64_t seed);

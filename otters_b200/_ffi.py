@@ -40,6 +40,8 @@ class ScanTuning(C.Structure):
         ("planners", C.c_uint32),
         ("timing", C.c_uint32),
         ("batch_passes", C.c_uint32),
+        ("separate_select", C.c_uint32),
+        ("lazy_prune", C.c_uint32),
     ]
 
 
@@ -188,6 +190,7 @@ def _sig(name, restype, *argtypes):
 otters_ctx_create = _sig("otters_ctx_create", C.c_int, C.c_int, _p, C.POINTER(_p))
 otters_ctx_destroy = _sig("otters_ctx_destroy", C.c_int, _p)
 otters_ctx_synchronize = _sig("otters_ctx_synchronize", C.c_int, _p)
+otters_ctx_join = _sig("otters_ctx_join", C.c_int, _p)
 otters_last_error = _sig("otters_last_error", C.c_char_p)
 otters_version = _sig("otters_version", C.c_char_p)
 otters_ctx_set_tuning = _sig("otters_ctx_set_tuning", C.c_int, _p, C.POINTER(ScanTuning))
@@ -198,6 +201,8 @@ otters_vecstore_reserve = _sig("otters_vecstore_reserve", C.c_int, _p, C.c_uint6
 otters_vecstore_add = _sig("otters_vecstore_add", C.c_int, _p, c_f32p, C.c_uint64)
 otters_vecstore_add_device = _sig("otters_vecstore_add_device", C.c_int, _p, _p, C.c_uint64)
 otters_vecstore_add_synthetic = _sig("otters_vecstore_add_synthetic", C.c_int, _p, C.c_uint64, C.c_uint64, C.c_uint64)
+otters_vecstore_set_rows = _sig("otters_vecstore_set_rows", C.c_int, _p, c_u64p, c_f32p, C.c_uint64)
+otters_metastore_set_rows = _sig("otters_metastore_set_rows", C.c_int, _p, c_u64p, c_f32p, C.c_uint64)
 otters_vecstore_len = _sig("otters_vecstore_len", C.c_uint64, _p)
 otters_vecstore_dim = _sig("otters_vecstore_dim", C.c_uint32, _p)
 otters_vecstore_inv_norms = _sig("otters_vecstore_inv_norms", C.c_int, _p, C.c_uint64, C.c_uint64, c_f32p)
@@ -248,6 +253,14 @@ otters_query_exchange = _sig(
     "otters_query_exchange", C.c_int, _p, _p, C.POINTER(VecQuery), C.POINTER(Filter), C.POINTER(ShardMap), C.POINTER(PeerExchange),
     C.c_uint64, c_u64p, c_f32p, c_u32p, C.c_uint64, c_u64p, C.POINTER(QueryStats)
 )
+otters_query_submit = _sig(
+    "otters_query_submit", C.c_int, _p, _p, C.POINTER(VecQuery), C.POINTER(Filter), C.POINTER(ShardMap), C.POINTER(PeerExchange),
+    C.c_uint64, c_u64p
+)
+otters_query_wait = _sig(
+    "otters_query_wait", C.c_int, _p, C.c_uint64, c_u64p, c_f32p, c_u32p, C.c_uint64, c_u64p, C.POINTER(QueryStats)
+)
+EXCHANGE_SLOTS = 4  # OTTERS_EXCHANGE_SLOTS
 
 BOUND_SYMBOLS = sorted(n for n in dir() if n.startswith("otters_"))
 

@@ -24,6 +24,7 @@ class Context:
         check(_ffi.otters_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
         self.device = int(device)
+        self.stream = int(stream) if stream else None  # None: the library's own non-blocking stream
 
     @property
     def handle(self):
@@ -32,15 +33,22 @@ class Context:
     def synchronize(self) -> None:
         check(_ffi.otters_ctx_synchronize(self._h))
 
+    def join(self) -> None:
+        """Orders this context's stream after all queries submitted on its lanes (no host wait)."""
+        check(_ffi.otters_ctx_join(self._h))
+
     def set_tuning(self, warps_per_cta=0, slots_per_warp=0, kc_floats=0, ctas_per_sm=0, unit_rows=0, disable_fused_predicate=0,
-                   batch_mode=0, batch_cta_group=0, scan_mode=0, planners=0, timing=0, batch_passes=0) -> None:
+                   batch_mode=0, batch_cta_group=0, scan_mode=0, planners=0, timing=0, batch_passes=0, separate_select=0,
+                   lazy_prune=0) -> None:
         """batch_mode: 0 = automatic, 1 = always serve query batches with the tcgen05 kernel, 2 = never.
         batch_cta_group: 0 = automatic (single CTAs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2).
         scan_mode: K1 front-end, 0 = automatic, 1 = autonomous warps, 2 = planner + worker warps; planners: planner warps per CTA.
         timing: per-phase CUDA events; 0 = only for blocking MetaStore queries with stats, 1 = always, 2 = never.
-        batch_passes: tensor-core kernel, 0 = single-pass tf32 selection first and 3xTF32 if its certificate fails, 1 / 3 = only that."""
+        batch_passes: tensor-core kernel, 0 = single-pass tf32 selection first and 3xTF32 if its certificate fails, 1 / 3 = only that.
+        separate_select: 1 = run the final selection (K3) as its own kernel instead of in the last CTA of the scan kernel.
+        lazy_prune: 1 = evaluate the chunk rules (K0) per work unit inside the scan kernel instead of as their own kernel."""
         t = _ffi.ScanTuning(warps_per_cta, slots_per_warp, kc_floats, ctas_per_sm, unit_rows, disable_fused_predicate, batch_mode,
-                            batch_cta_group, scan_mode, planners, timing, batch_passes)
+                            batch_cta_group, scan_mode, planners, timing, batch_passes, separate_select, lazy_prune)
         check(_ffi.otters_ctx_set_tuning(self._h, C.byref(t)))
 
     def last_work(self) -> Dict[str, float]:

@@ -40,6 +40,52 @@ static inline uint64_t pow2_at_least(uint64_t x) {
 
 using namespace otters;
 
+namespace otters {
+
+struct FusedFilter {  // device-side lowered filter evaluated inside the scan kernel
+    const DevLeaf* leaves = nullptr;
+    const uint32_t* clause_off = nullptr;
+    uint32_t n_clauses = 0, n_leaves = 0;
+    const uint32_t* chunk_keep = nullptr;  // null: the scan kernel prunes chunks itself (lazy pruning)
+    uint32_t chunk_size = 1;
+    uint32_t n_chunks = 0;
+    static size_t smem_bytes_for(uint32_t n_leaves, uint32_t n_clauses) {
+        return ((size_t)n_leaves * sizeof(DevLeaf) + ((size_t)n_clauses + 1) * 4 + 127) / 128 * 128;
+    }
+    size_t smem_bytes() const { return smem_bytes_for(n_leaves, n_clauses); }
+};
+constexpr size_t kMaxFusedFilterBytes = 16 * 1024;
+
+struct QueryRun {
+    uint32_t result_list = 0;  // index into ctx->d_list holding the final ordered candidates
+    uint64_t k_eff = 0;
+    bool big = false;          // result lives in ctx->d_emit-sized list (emit-all path)
+    bool prefetched = false;   // header + candidates already sit in ctx->h_result (batched path)
+    bool zero_copy = false;    // the selection writes header + candidates into ctx->h_zc (mapped host memory)
+};
+
+// A query that was enqueued by otters_query_submit and has not been waited for yet (one per lane).
+struct Pending {
+    bool active = false;
+    uint64_t ticket = 0;
+    bool meta = false;
+    otters_metastore* ms = nullptr;
+    QueryRun run;
+    bool take_max = true;
+    bool scan = false;           // a scan was enqueued (else: only statistics come back)
+    bool fetched = false;        // the blocking path already ran: results sit in h_idx / h_score / h_qid
+    uint32_t nq = 0;
+    bool has_filter = false;
+    uint64_t leaf_zm = 0, leaf_row = 0, n_leaves = 0;  // algorithmic metadata bytes per chunk / per evaluated row
+    double t_submit = 0.0;
+    std::vector<uint64_t> h_idx;
+    std::vector<float> h_score;
+    std::vector<uint32_t> h_qid;
+    otters_query_stats stats{};
+};
+
+}  // namespace otters
+
 // =================================================================================================
 // context
 // =================================================================================================
@@ -89,7 +135,8 @@ struct otters_ctx {
     uint32_t batch_smem_configured[6] = {0, 0, 0, 0, 0, 0};
     // fused peer exchange requested by otters_query_exchange for the query being enqueued
     bool ex_active = false;
-    uint32_t ex_world = 0, ex_rank = 0, ex_kmax = 0, ex_k = 0, ex_seq = 0;
+    bool ex_published = false;  // a kernel that publishes this rank's records for the current query has been launched
+    uint32_t ex_world = 0, ex_rank = 0, ex_kmax = 0, ex_k = 0, ex_seq = 0, ex_slot = 0;
     otters_topk_record* ex_records[kMaxPeers] = {};
     uint32_t* ex_flags[kMaxPeers] = {};
 
@@ -123,6 +170,22 @@ struct otters_ctx {
     bool timed_rowmask = false;   // ev[1]/ev[6] bracket the stand-alone row-mask kernel of the last query
     uint32_t last_dim = 0;        // of the last scan (for the algorithmic-bytes figure)
     int32_t last_metric = 0;
+
+    // per-query MetaStore scratch (stores are immutable after build: everything a query writes lives in the context
+    // that runs it, so two lanes can search the same store at the same time)
+    uint32_t* d_chunk_keep = nullptr;   // stand-alone prune kernel: one bit per chunk
+    size_t chunk_keep_words = 0;
+    uint32_t* d_meta_mask = nullptr;    // stand-alone row-mask kernel: one bit per row
+    size_t meta_mask_words = 0;
+    FusedFilter cur_filter;             // where the last lowered filter lives on the device
+
+    // lanes: queries in flight (otters_query_submit / otters_query_wait).  lane[0] is this context itself, lane[1..] are
+    // child contexts with their own stream and scratch, created on first use.
+    otters_ctx* parent = nullptr;
+    otters_ctx* lane[kMaxLanes] = {};
+    uint32_t next_lane = 0;
+    uint64_t tickets = 0;
+    Pending pend;
 };
 
 namespace otters {
@@ -372,6 +435,20 @@ struct VecStorage {
         minv_valid = false;
         return OTTERS_OK;
     }
+    // overwrites individual rows (host data, dim floats each) and recomputes their inverse norms
+    int set_rows(const uint64_t* rows, const float* data, uint64_t cnt) {
+        for (uint64_t i = 0; i < cnt; ++i)
+            if (rows[i] >= n) return fail(OTTERS_ERR_INVALID, "row index out of bounds");
+        for (uint64_t i = 0; i < cnt; ++i) {
+            OTTERS_CUDA(cudaMemcpyAsync(d_rows + rows[i] * pitch, data + i * dim, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice,
+                                        ctx->stream));
+            int rc = launch_inv_norms(d_rows, pitch, dim, rows[i], 1, d_inv, ctx->stream);
+            if (rc) return rc;
+        }
+        OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
+        minv_valid = false;
+        return OTTERS_OK;
+    }
     void release() {
         cudaFree(d_rows);
         cudaFree(d_inv);
@@ -384,16 +461,6 @@ struct VecStorage {
 };
 
 // ---- scan planning ---------------------------------------------------------------------------------
-struct FusedFilter {  // device-side lowered filter evaluated inside the scan kernel
-    const DevLeaf* leaves = nullptr;
-    const uint32_t* clause_off = nullptr;
-    uint32_t n_clauses = 0, n_leaves = 0;
-    const uint32_t* chunk_keep = nullptr;
-    uint32_t chunk_size = 1;
-    size_t smem_bytes() const { return round_up((size_t)n_leaves * sizeof(DevLeaf) + ((size_t)n_clauses + 1) * 4, 128); }
-};
-constexpr size_t kMaxFusedFilterBytes = 16 * 1024;
-
 struct ScanPlan {
     ScanLaunch launch;
     uint32_t off_filter;
@@ -402,7 +469,8 @@ struct ScanPlan {
     uint32_t planners, off_ring;  // planner front-end (scan_planner.cu): planner warps per CTA (0 = autonomous warps)
 };
 
-static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, size_t filter_bytes, ScanPlan* out) {
+static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, size_t filter_bytes, bool fuse_select,
+                     ScanPlan* out) {
     ScanPlan pl{};
     const otters_scan_tuning& t = c->tuning;
     pl.cap = k_fused ? (uint32_t)pow2_at_least(std::max<uint32_t>(2 * k_fused, 64)) : 0;
@@ -498,6 +566,8 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     pl.launch.grid = grid;
     pl.launch.block = (W + pl.planners) * 32;
     pl.launch.smem_bytes = pl.off_warps + W * pl.warp_bytes;
+    // the last CTA runs the selection in the same shared memory (select_body.cuh)
+    if (fuse_select && pl.launch.smem_bytes < kSelectSmemBytes) pl.launch.smem_bytes = kSelectSmemBytes;
     *out = pl;
     return OTTERS_OK;
 }
@@ -508,6 +578,7 @@ static void fill_exchange(const otters_ctx* c, SelectParams* se) {
     se->ex_rank = c->ex_rank;
     se->ex_kmax = c->ex_kmax;
     se->ex_seq = c->ex_seq;
+    se->ex_slot = c->ex_slot;
     se->ex_k = c->ex_k;
     for (uint32_t i = 0; i < c->ex_world; ++i) {
         se->ex_records[i] = c->ex_records[i];
@@ -517,14 +588,6 @@ static void fill_exchange(const otters_ctx* c, SelectParams* se) {
 }
 
 // ---- the query core: scan + select for every query of the batch --------------------------------------
-struct QueryRun {
-    uint32_t result_list = 0;  // index into ctx->d_list holding the final ordered candidates
-    uint64_t k_eff = 0;
-    bool big = false;          // result lives in ctx->d_emit-sized list (emit-all path)
-    bool prefetched = false;   // header + candidates already sit in ctx->h_result (batched path)
-    bool zero_copy = false;    // the selection kernel writes header + candidates into ctx->h_zc (mapped host memory)
-};
-
 static float host_inv_norm(const float* v, uint32_t dim) {
     // src/vec.rs:390-397: serial f32 sum of squares, sqrt, reciprocal (0 for a zero vector).  The host code is
     // built with -ffp-contract=off and without fast-math, so the loop is neither contracted nor reassociated.
@@ -663,7 +726,11 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bp.cta_qids = c->d_cta_qids;
     bp.cta_counts = c->d_cta_counts;
     bp.passes = passes;
-    if (const char* e = getenv("OTTERS_BATCH_DBG")) bp.dbg = (uint32_t)atoi(e);  // timing experiments; results are garbage
+#ifdef OTTERS_K2_EXPERIMENTS
+    // timing experiments only (role-by-role timing of K2, scripts/dbg_passes_roles.py): results are garbage, so the hooks are
+    // compiled out of the shipped library and a run with them on is never accepted (see below)
+    if (const char* e = getenv("OTTERS_BATCH_DBG")) bp.dbg = (uint32_t)atoi(e);
+#endif
     rec_event(c, 2);
     rec_event(c, 3);
     rc = launch_batch(bl, bp, q->metric, c->batch_smem_configured, s);
@@ -736,7 +803,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     float max_err, delta;
     memcpy(&max_err, &err_bits, 4);
     memcpy(&delta, &delta_bits, 4);
-    bool ok = (flags & 1u) == 0 && delta <= FLT_MAX && max_err <= delta;
+    bool ok = (flags & 1u) == 0 && delta <= FLT_MAX && max_err <= delta && bp.dbg == 0;
     if (ok && excl != 0) {
         // some pair was left out of the candidate lists: its exact score is within delta of its tensor-core
         // score, so it cannot belong to the result iff even that bound stays strictly outside the k-th score
@@ -815,8 +882,10 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     for (uint32_t i = 0; i < q->nq; ++i) q_inv[i] = host_inv_norm(q->queries + (size_t)i * q->dim, q->dim);
 
     const bool fused = k_eff <= kMaxFusedK;
+    // single queries: the selection (K3) runs in the last CTA of the scan kernel — one launch per query
+    const bool fuse_select = fused && q->nq == 1 && !c->tuning.separate_select;
     ScanPlan pl;
-    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, ff ? ff->smem_bytes() : 0, &pl);
+    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, ff ? ff->smem_bytes() : 0, fuse_select, &pl);
     if (rc) return rc;
 
     ScanParams sp{};
@@ -833,8 +902,11 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         sp.flt_clause_off = ff->clause_off;
         sp.flt_n_clauses = ff->n_clauses;
         sp.flt_n_leaves = ff->n_leaves;
-        sp.chunk_keep = ff->chunk_keep;
+        sp.chunk_keep = ff->chunk_keep;  // null: lazy pruning inside the scan kernel
         sp.chunk_size = ff->chunk_size;
+        sp.n_chunks = ff->n_chunks;
+        sp.nq_stats = q->nq;
+        sp.stats = c->d_stats;
     }
     sp.off_filter = pl.off_filter;
     sp.n_units = pl.n_units;
@@ -878,14 +950,6 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             sp.q_inv = q_inv[qi];
             sp.qid = qi;
             sp.tau_in = qi ? c->d_tau : nullptr;
-            if (qi == 0 && q->nq == 1) rec_event(c, 3);
-            rc = pl.planners ? launch_scan_planner(sp, pl.launch, q->metric, c->planner_smem_configured, s)
-                             : launch_scan(sp, pl.launch, q->metric, false, c->scan_smem_configured, s);
-            if (rc) return rc;
-            if (qi == 0 && q->nq == 1) {
-                rec_event(c, 4);
-                c->timed_single = true;
-            }
             SelectParams se{};
             se.cta_keys = c->d_cta_keys;
             se.cta_counts = c->d_cta_counts;
@@ -914,10 +978,25 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
                     run->zero_copy = true;
                 }
             }
-            rc = launch_select(se, s);
+            sp.fuse_select = fuse_select ? 1u : 0u;
+            sp.done_counter = reinterpret_cast<uint32_t*>(c->d_ctrl + 104);  // zeroed with the control block
+            if (fuse_select) sp.sel = se;
+            if (qi == 0 && q->nq == 1) rec_event(c, 3);
+            rc = pl.planners ? launch_scan_planner(sp, pl.launch, q->metric, c->planner_smem_configured, s)
+                             : launch_scan(sp, pl.launch, q->metric, false, c->scan_smem_configured, s);
             if (rc) return rc;
+            if (qi == 0 && q->nq == 1) {
+                rec_event(c, 4);
+                c->timed_single = true;
+            }
+            c->last.kernel_launches += 1;
+            if (!fuse_select) {
+                rc = launch_select(se, s);
+                if (rc) return rc;
+                c->last.kernel_launches += 1;
+            }
+            if (c->ex_active && qi + 1 == q->nq) c->ex_published = true;
             cur ^= 1;
-            c->last.kernel_launches += 2;
         }
         rec_event(c, 5);
         run->result_list = cur;
@@ -951,19 +1030,21 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             sp.tau_in = qi ? c->d_tau : nullptr;
             rc = launch_scan(sp, pl.launch, q->metric, true, c->scan_smem_configured, s);
             if (rc) return rc;
-            // the running list lives in d_list[0] (single buffer: it is copied into the sort array first)
-            rc = launch_append_prev(c->d_emit, c->d_counter + 1, qi ? c->d_list[0] : nullptr, qi ? c->d_list_count : nullptr,
-                                    n_sort, s);
+            // the running list lives in d_list[0] (single buffer: it is copied into the sort array first); its length
+            // alternates between the two count slots, so that take_sorted's block 0 never writes the count other blocks read
+            const uint32_t* prev_cnt = qi ? c->d_list_count + (qi & 1u) : nullptr;
+            uint32_t* out_cnt = c->d_list_count + ((qi + 1u) & 1u);
+            rc = launch_append_prev(c->d_emit, c->d_counter + 1, qi ? c->d_list[0] : nullptr, prev_cnt, n_sort, s);
             if (rc) return rc;
             rc = launch_global_sort(c->d_emit, n_sort, s);
             if (rc) return rc;
-            rc = launch_take_sorted(c->d_emit, c->d_counter + 1, qi ? c->d_list_count : nullptr, k_eff, c->d_list[0],
-                                    c->d_list_count, c->d_tau, list_hdr(c, 0), c->d_rows_scored, stats_src, s);
+            rc = launch_take_sorted(c->d_emit, c->d_counter + 1, prev_cnt, k_eff, c->d_list[0], out_cnt, c->d_tau, list_hdr(c, 0),
+                                    c->d_rows_scored, stats_src, s);
             if (rc) return rc;
             c->last.kernel_launches += 4;
         }
         if (d_records_out) {
-            rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, sp.take_max, d_records_out, s);
+            rc = launch_cands_to_records(c->d_list[0], c->d_list_count + (q->nq & 1u), (uint32_t)k_eff, map, sp.take_max, d_records_out, s);
             if (rc) return rc;
         }
         rec_event(c, 5);
@@ -1043,7 +1124,8 @@ static int validate_query(const otters_vec_query* q, uint32_t store_dim, bool me
 extern "C" const char* otters_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* otters_version(void) { return "otters_b200 0.1.0 (sm_100a)"; }
 
-extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out) {
+namespace otters {
+static int ctx_create_impl(int device, void* cuda_stream, otters_ctx** out) {
     if (!out) return fail(OTTERS_ERR_INVALID, "null output pointer");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1091,11 +1173,20 @@ extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out
     *out = c.release();
     return OTTERS_OK;
 }
+}  // namespace otters
+
+extern "C" int otters_ctx_create(int device, void* cuda_stream, otters_ctx** out) { return ctx_create_impl(device, cuda_stream, out); }
 
 extern "C" int otters_ctx_destroy(otters_ctx* c) {
     if (!c) return OTTERS_OK;
     DeviceGuard g(c->device);
+    for (uint32_t i = 1; i < kMaxLanes; ++i) {
+        if (c->lane[i]) otters_ctx_destroy(c->lane[i]);
+        c->lane[i] = nullptr;
+    }
     cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_chunk_keep);
+    cudaFree(c->d_meta_mask);
     cudaFree(c->d_io);
     for (auto& e : c->ev_io)
         if (e) cudaEventDestroy(e);
@@ -1127,6 +1218,20 @@ extern "C" int otters_ctx_synchronize(otters_ctx* c) {
     if (!c) return fail(OTTERS_ERR_INVALID, "null context");
     DeviceGuard g(c->device);
     OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 1; i < kMaxLanes; ++i)
+        if (c->lane[i]) OTTERS_CUDA(cudaStreamSynchronize(c->lane[i]->stream));
+    return OTTERS_OK;
+}
+
+extern "C" int otters_ctx_join(otters_ctx* c) {
+    if (!c) return fail(OTTERS_ERR_INVALID, "null context");
+    DeviceGuard g(c->device);
+    for (uint32_t i = 1; i < kMaxLanes; ++i) {
+        otters_ctx* l = c->lane[i];
+        if (!l) continue;
+        OTTERS_CUDA(cudaEventRecord(l->ev_io[0], l->stream));  // (ev_io events carry no timing: cheap to record)
+        OTTERS_CUDA(cudaStreamWaitEvent(c->stream, l->ev_io[0], 0));
+    }
     return OTTERS_OK;
 }
 
@@ -1136,6 +1241,8 @@ extern "C" int otters_ctx_set_tuning(otters_ctx* c, const otters_scan_tuning* t)
     // test hook: OTTERS_SCAN_MODE selects the K1 front-end wherever the caller left it automatic
     if (c->tuning.scan_mode == 0)
         if (const char* e = getenv("OTTERS_SCAN_MODE")) c->tuning.scan_mode = (uint32_t)atoi(e);
+    for (uint32_t i = 1; i < kMaxLanes; ++i)
+        if (c->lane[i]) c->lane[i]->tuning = c->tuning;
     return OTTERS_OK;
 }
 
@@ -1217,6 +1324,14 @@ extern "C" int otters_vecstore_add_synthetic_sharded(otters_vecstore* vs, const 
     return vs->st.add_synth(to_map(map), n_local, seed);
 }
 
+extern "C" int otters_vecstore_set_rows(otters_vecstore* vs, const uint64_t* rows, const float* data, uint64_t n) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    if (n && (!rows || !data)) return fail(OTTERS_ERR_INVALID, "null rows");
+    DeviceGuard g(vs->st.ctx->device);
+    OTTERS_CUDA(otters_ctx_synchronize(vs->st.ctx) == OTTERS_OK ? cudaSuccess : cudaErrorUnknown);  // no query may be in flight
+    return vs->st.set_rows(rows, data, n);
+}
+
 extern "C" uint64_t otters_vecstore_len(const otters_vecstore* vs) { return vs ? vs->st.n : 0; }
 extern "C" uint32_t otters_vecstore_dim(const otters_vecstore* vs) { return vs ? vs->st.dim : 0; }
 
@@ -1258,32 +1373,23 @@ static int upload_row_mask(otters_ctx* c, const otters_vec_query* q, uint64_t n_
 }
 }  // namespace otters
 
+namespace otters {
+static int vec_enqueue(otters_ctx* c, otters_vecstore* vs, const otters_vec_query* q, otters_topk_record* d_records, ShardMap map,
+                       bool want_host, Pending* pd);
+static int vec_finish(otters_ctx* c, Pending* pd, bool fetch, uint64_t* out_idx, float* out_score, uint32_t* out_qid, uint64_t cap,
+                      uint64_t* out_len);
+}  // namespace otters
+
 extern "C" int otters_vecstore_query(otters_vecstore* vs, const otters_vec_query* q, uint64_t* out_idx, float* out_score,
                                      uint32_t* out_qid, uint64_t cap, uint64_t* out_len) {
     if (!vs || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
-    int rc = validate_query(q, vs->st.dim, false);
-    if (rc) return rc;
     otters_ctx* c = vs->st.ctx;
     DeviceGuard g(c->device);
     *out_len = 0;
-    c->last = otters_last_work{};
-    if (q->k == 0 || vs->st.n == 0) return OTTERS_OK;  // take(0) / empty store (tests/vec_store_tests.rs:430-445,488-499)
-    rc = begin_query(c);
+    Pending pd;
+    int rc = vec_enqueue(c, vs, q, nullptr, ShardMap{}, true, &pd);
     if (rc) return rc;
-    c->want_host_result = true;
-    const uint32_t* d_mask = nullptr;
-    uint32_t mask_words = 0;
-    rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
-    if (rc) return rc;
-    rc = stage_queries(c, q, vs->st.pitch);
-    if (rc) return rc;
-    QueryRun run;
-    rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, ShardMap{}, nullptr, nullptr, &run);
-    if (rc) return rc;
-    rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
-    if (rc) return rc;
-    finish_work_stats(c);
-    return OTTERS_OK;
+    return vec_finish(c, &pd, true, out_idx, out_score, out_qid, cap, out_len);
 }
 
 // =================================================================================================
@@ -1302,6 +1408,7 @@ struct MetaColumn {
     uint32_t* d_non_null = nullptr;
     uint64_t* d_bloom = nullptr;
     uint64_t bloom_stride = 0;
+    uint32_t bloom_k0 = 0;              // probes of a full chunk's filter
     uint64_t* d_bloom_mbits = nullptr;
     uint32_t* d_bloom_k = nullptr;
     // host copies kept for the parity exports
@@ -1356,9 +1463,6 @@ struct otters_metastore {
     uint64_t n_chunks = 0;
     std::vector<MetaColumn> cols;
     DevColumn* d_cols = nullptr;
-    uint32_t* d_chunk_keep = nullptr;
-    uint32_t* d_row_mask = nullptr;
-    FusedFilter cur_filter;       // where the last lowered filter lives on the device
     bool has_stats = false;
     otters_query_stats last{};
 };
@@ -1378,8 +1482,6 @@ extern "C" int otters_metastore_destroy(otters_metastore* ms) {
         cudaFree(c.d_bloom_k);
     }
     cudaFree(ms->d_cols);
-    cudaFree(ms->d_chunk_keep);
-    cudaFree(ms->d_row_mask);
     ms->st.release();
     delete ms;
     return OTTERS_OK;
@@ -1550,6 +1652,7 @@ static int build_column(otters_metastore* ms, const otters_column& in, const ott
         uint32_t k0;
         bloom_params(std::min<uint64_t>(cs, std::max<uint64_t>(n, 1)), p->bloom_mode, bloom_fpr, bloom_bits, &m0, &k0);
         mc->bloom_stride = m0 / 64;
+        mc->bloom_k0 = k0;
         std::vector<uint64_t> words(std::max<uint64_t>(nc, 1) * mc->bloom_stride, 0);
         std::vector<uint64_t> mbits(std::max<uint64_t>(nc, 1), 64);
         std::vector<uint32_t> kh(std::max<uint64_t>(nc, 1), 1);
@@ -1664,10 +1767,6 @@ extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* 
     if ((rc = upload(&ms->d_cols, dcols.data(), dcols.size() * sizeof(DevColumn)))) return cleanup(rc);
     const double zone_s = now_s() - t_zone;
 
-    const size_t keep_words = (ms->n_chunks + 31) / 32 + 1, mask_words = (p->n_rows + 31) / 32 + 1;
-    if (cudaMalloc((void**)&ms->d_chunk_keep, keep_words * 4) != cudaSuccess ||
-        cudaMalloc((void**)&ms->d_row_mask, mask_words * 4) != cudaSuccess)
-        return cleanup(fail(OTTERS_ERR_NOMEM, "device allocation for masks failed"));
     if (stats) {  // src/meta.rs:292-299
         stats->n_rows = p->n_rows;
         stats->dim = p->dim;
@@ -1678,6 +1777,14 @@ extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* 
     }
     *out = ms.release();
     return OTTERS_OK;
+}
+
+extern "C" int otters_metastore_set_rows(otters_metastore* ms, const uint64_t* rows, const float* data, uint64_t n) {
+    if (!ms) return fail(OTTERS_ERR_INVALID, "null store");
+    if (n && (!rows || !data)) return fail(OTTERS_ERR_INVALID, "null rows");
+    DeviceGuard g(ms->ctx->device);
+    OTTERS_CUDA(otters_ctx_synchronize(ms->ctx) == OTTERS_OK ? cudaSuccess : cudaErrorUnknown);  // no query may be in flight
+    return ms->st.set_rows(rows, data, n);
 }
 
 extern "C" uint64_t otters_metastore_n_chunks(const otters_metastore* ms) { return ms ? ms->n_chunks : 0; }
@@ -1759,6 +1866,8 @@ static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vecto
             d.bloom_a0 = d.bloom_m0 ? d.h1 % d.bloom_m0 : 0;
             d.bloom_b0 = d.bloom_m0 ? d.h2 % d.bloom_m0 : 0;
             if (d.bloom_b0 == 0) d.bloom_b0 = 1;
+            d.bloom_k0 = mc.bloom_k0;
+            d.bloom_full_chunks = ms->st.n / ms->chunk_size;
             break;
         }
         default: return fail(OTTERS_ERR_INVALID, "unknown column dtype");
@@ -1768,32 +1877,39 @@ static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vecto
     return OTTERS_OK;
 }
 
-// enqueues K0 (+K0b); leaves chunk_keep / row_mask / stats on the device
-static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_t nq, bool want_row_mask, bool force_row_mask,
-                           uint64_t* meta_bytes) {
-    otters_ctx* c = ms->ctx;
+// What a query needs from the stand-alone metadata kernels.
+enum MetaMode {
+    META_LAZY = 0,     // nothing: the scan kernel prunes chunks (zonemaps + Bloom) and evaluates the row predicate itself
+    META_PRUNE = 1,    // K0 only: chunk mask + statistics (rows are evaluated inside the scan kernel, or nothing is scanned)
+    META_ROWMASK = 2,  // K0 + K0b: chunk mask, statistics and the row bitmask in ctx->d_meta_mask
+};
+
+static int ensure_meta_scratch(otters_ctx* c, const otters_metastore* ms, bool rows) {
+    int rc = ensure_dev(&c->d_chunk_keep, &c->chunk_keep_words, (size_t)((ms->n_chunks + 31) / 32 + 1), c->stream);
+    if (rc) return rc;
+    if (rows) rc = ensure_dev(&c->d_meta_mask, &c->meta_mask_words, (size_t)((ms->st.n + 31) / 32 + 1), c->stream);
+    return rc;
+}
+
+// Lowers the filter into the input image of the current query, sends the image, and enqueues the stand-alone metadata
+// kernels `mode` asks for; leaves ctx->cur_filter pointing at the lowered filter on the device.
+static int run_meta_filter(otters_ctx* c, otters_metastore* ms, const otters_filter* f, uint32_t nq, MetaMode mode) {
     cudaStream_t s = c->stream;
-    MetaKernelParams mp{};
-    mp.cols = ms->d_cols;
-    mp.n_rows = (uint32_t)ms->st.n;
-    mp.chunk_size = (uint32_t)ms->chunk_size;
-    mp.n_chunks = (uint32_t)ms->n_chunks;
-    mp.nq = nq;
-    mp.chunk_keep = ms->d_chunk_keep;
-    mp.row_mask = ms->d_row_mask;
-    mp.stats = c->d_stats;
-    *meta_bytes = 0;
     if (!f) {
-        int rc0 = io_flush(c);
-        if (rc0) return rc0;
-        mp.stats = c->d_stats;
-        c->last.kernel_launches += 1;
-        return launch_count_all_chunks(mp, s);
+        // no meta_filter: every chunk is evaluated (src/meta.rs:658) — the statistics travel inside the control block image
+        unsigned long long* hs = reinterpret_cast<unsigned long long*>(c->h_io[c->io_slot] + 32);
+        hs[0] = ms->n_chunks;
+        hs[1] = (unsigned long long)ms->st.n * nq;
+        return io_flush(c);
     }
     std::vector<uint32_t> offs;
     std::vector<DevLeaf> leaves;
     int rc = lower_filter(ms, f, &offs, &leaves);
     if (rc) return rc;
+    if (mode != META_LAZY) {
+        rc = ensure_meta_scratch(c, ms, mode == META_ROWMASK);
+        if (rc) return rc;
+    }
     const size_t off_bytes = round_up(offs.size() * 4, 16);
     const size_t total = off_bytes + leaves.size() * sizeof(DevLeaf);
     uint8_t* hf = nullptr;
@@ -1804,69 +1920,124 @@ static int run_meta_filter(otters_metastore* ms, const otters_filter* f, uint32_
     if (!leaves.empty()) memcpy(hf + off_bytes, leaves.data(), leaves.size() * sizeof(DevLeaf));
     rc = io_flush(c);  // control block reset + lowered filter + staged queries: one copy
     if (rc) return rc;
+    FusedFilter& cf = c->cur_filter;
+    cf.clause_off = reinterpret_cast<const uint32_t*>(c->d_io + f_off);
+    cf.leaves = reinterpret_cast<const DevLeaf*>(c->d_io + f_off + off_bytes);
+    cf.n_clauses = f->n_clauses;
+    cf.n_leaves = (uint32_t)leaves.size();
+    cf.chunk_keep = mode == META_LAZY ? nullptr : c->d_chunk_keep;
+    cf.chunk_size = (uint32_t)ms->chunk_size;
+    cf.n_chunks = (uint32_t)ms->n_chunks;
+    if (mode == META_LAZY) return OTTERS_OK;
+    MetaKernelParams mp{};
+    mp.cols = ms->d_cols;
+    mp.n_rows = (uint32_t)ms->st.n;
+    mp.chunk_size = (uint32_t)ms->chunk_size;
+    mp.n_chunks = (uint32_t)ms->n_chunks;
+    mp.nq = nq;
+    mp.chunk_keep = c->d_chunk_keep;
+    mp.row_mask = c->d_meta_mask;
     mp.stats = c->d_stats;
-    mp.clause_off = reinterpret_cast<const uint32_t*>(c->d_io + f_off);
-    mp.leaves = reinterpret_cast<const DevLeaf*>(c->d_io + f_off + off_bytes);
+    mp.clause_off = cf.clause_off;
+    mp.leaves = cf.leaves;
     mp.n_clauses = f->n_clauses;
-    ms->cur_filter.leaves = mp.leaves;
-    ms->cur_filter.clause_off = mp.clause_off;
-    ms->cur_filter.n_clauses = f->n_clauses;
-    ms->cur_filter.n_leaves = (uint32_t)leaves.size();
-    ms->cur_filter.chunk_keep = ms->d_chunk_keep;
-    ms->cur_filter.chunk_size = (uint32_t)ms->chunk_size;
-    if (want_row_mask && !force_row_mask && !c->tuning.disable_fused_predicate &&
-        ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes)
-        want_row_mask = false;  // the scan kernel evaluates the predicate itself (fused K0b)
     rec_event(c, 0);
     rc = launch_prune(mp, (uint32_t)leaves.size(), s);
     if (rc) return rc;
     rec_event(c, 1);
     c->timed_meta = true;
     c->last.kernel_launches += 1;
-    if (want_row_mask) {
+    if (mode == META_ROWMASK) {
         rc = launch_rowmask(mp, (uint32_t)leaves.size(), s);
         if (rc) return rc;
         c->last.kernel_launches += 1;
         rec_event(c, 6);
         c->timed_rowmask = true;
     }
-    // algorithmic metadata bytes: zonemap entries per leaf + column values/null bits of evaluated rows are
-    // accounted by the caller once the evaluated-chunk count is known
     return OTTERS_OK;
 }
 
 static int exchange_only(otters_ctx* c, int take_max, const unsigned long long* stats_src, QueryRun* run);
 
-static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
-                           otters_topk_record* d_records, ShardMap map, uint64_t* out_idx, float* out_score,
-                           uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
-    const double t_total = now_s();
-    otters_ctx* c = ms->ctx;
+// ---- MetaQueryPlan::collect in two halves: enqueue (everything up to the last kernel launch) and finish (wait, copy the
+// result out, assemble the statistics).  The blocking entry points run both back to back; otters_query_submit runs the
+// first and otters_query_wait the second.
+static int meta_enqueue(otters_ctx* c, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                        otters_topk_record* d_records, ShardMap map, bool want_host, bool want_stats, Pending* pd) {
+    *pd = Pending{};
+    pd->t_submit = now_s();
+    pd->meta = true;
+    pd->ms = ms;
     int rc = validate_query(q, ms->st.dim, true);
     if (rc) return rc;
     if (q->row_mask_words) return fail(OTTERS_ERR_INVALID, "row masks are not part of MetaQueryPlan");
-    if (out_len) *out_len = 0;
     cudaStream_t s = c->stream;
     rc = begin_query(c);
     if (rc) return rc;
     // durations of otters_query_stats come from per-phase events: recorded only when the caller waits for stats
-    if (c->tuning.timing == 0 && stats && !d_records && !(c->ex_active && !out_len)) c->timing = true;
-    c->want_host_result = !d_records && out_len != nullptr;
+    if (c->tuning.timing == 0 && want_stats && want_host) c->timing = true;
+    c->want_host_result = want_host;
     // per-chunk collect() errors are swallowed by the reference (src/meta_compute.rs:182): an empty
     // batch or a wrong-dimension query returns no rows but still reports stats
     const bool chunk_err = q->nq == 0 || q->dim != ms->st.dim || !q->queries;
     const bool scan = !chunk_err && q->k > 0 && ms->st.n > 0;
-    uint64_t meta_bytes = 0;
     if (scan) {
         rc = stage_queries(c, q, ms->st.pitch);
         if (rc) return rc;
     }
     // the batched tensor-core kernel gates rows with a precomputed mask (K0b) instead of the fused predicate
     const bool batched = scan && !c->ex_active && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
-    rc = run_meta_filter(ms, filter, q->nq, scan && filter, batched && filter, &meta_bytes);
+    const uint32_t n_leaves = filter && filter->clause_offsets ? filter->clause_offsets[filter->n_clauses] : 0;
+    // the scan kernel evaluates the row predicate itself (fused K0b) unless the CNF is too large for its shared memory
+    const bool fuse = scan && filter && !batched && !c->tuning.disable_fused_predicate &&
+                      FusedFilter::smem_bytes_for(n_leaves, filter->n_clauses) <= kMaxFusedFilterBytes;
+    // ... and can prune the chunks itself as well (lazy K0, opt-in: measured slower than the stand-alone kernel, whose 9-12 us
+    // hide under the other lane's scan when two queries are in flight)
+    const bool lazy = fuse && q->nq == 1 && c->tuning.lazy_prune;
+    rc = run_meta_filter(c, ms, filter, q->nq, lazy ? META_LAZY : ((scan && filter && !fuse) ? META_ROWMASK : META_PRUNE));
     if (rc) return rc;
+    pd->scan = scan;
+    pd->take_max = q->take_type == OTTERS_TAKE_MAX;
+    pd->nq = q->nq;
+    pd->has_filter = filter != nullptr;
+    if (filter) {
+        for (uint32_t li = 0; li < n_leaves; ++li) {
+            const MetaColumn& mc = ms->cols[filter->leaves[li].col];
+            pd->leaf_zm += 2 * mc.value_bytes + 4;
+            pd->leaf_row += mc.value_bytes;
+        }
+        pd->n_leaves = n_leaves;
+    }
+    if (scan) {
+        rc = run_queries(c, &ms->st, q, (filter && !fuse) ? c->d_meta_mask : nullptr,
+                         (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, map, c->d_stats,
+                         fuse ? &c->cur_filter : nullptr, &pd->run);
+        if (rc) return rc;
+    } else if (c->ex_active) {
+        // nothing to scan on this rank, but it still takes part in the exchange
+        rc = exchange_only(c, pd->take_max, c->d_stats, &pd->run);
+        if (rc) return rc;
+    } else if (d_records) {
+        // no scan: the record buffer must still hold k empty slots
+        const uint64_t k_eff = std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq);
+        if (k_eff) {
+            rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, 1, d_records, s);
+            if (rc) return rc;
+        }
+    }
+    pd->active = true;
+    return OTTERS_OK;
+}
+
+// `fetch`: copy the ordered result to the caller (else it stays on the device and only the statistics come back, and
+// those only when `stats` is given — the one case that does not synchronise).
+static int meta_finish(otters_ctx* c, Pending* pd, bool fetch, uint64_t* out_idx, float* out_score, uint32_t* out_qid, uint64_t cap,
+                       uint64_t* out_len, otters_query_stats* stats) {
+    otters_metastore* ms = pd->ms;
+    cudaStream_t s = c->stream;
     unsigned long long hstats[4] = {0, 0, 0, 0};
     uint64_t n_out = 0;
+    bool synced = false;
     auto fetch_stats_only = [&]() -> int {
         int r2 = ensure_pinned(&c->h_result, &c->h_result_bytes, 64);
         if (r2) return r2;
@@ -1874,49 +2045,17 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
         OTTERS_CUDA(cudaStreamSynchronize(s));
         c->last.d2h_bytes += 2 * sizeof(unsigned long long);
         memcpy(hstats, c->h_result, 2 * sizeof(unsigned long long));
+        synced = true;
         return OTTERS_OK;
     };
-    const bool on_device = d_records || (c->ex_active && !out_len);  // result stays in HBM: no copy, no sync unless stats are wanted
-    if (scan) {
-        QueryRun run;
-        const bool fuse = filter && !batched && !c->tuning.disable_fused_predicate && ms->cur_filter.smem_bytes() <= kMaxFusedFilterBytes;
-        rc = run_queries(c, &ms->st, q, (filter && !fuse) ? ms->d_row_mask : nullptr,
-                         (filter && !fuse) ? (uint32_t)((ms->st.n + 31) / 32) : 0, d_records, map, c->d_stats,
-                         fuse ? &ms->cur_filter : nullptr, &run);
+    const bool have_list = pd->scan || pd->run.k_eff > 0 || pd->run.zero_copy;  // a selection ran (scan or exchange-only)
+    int rc;
+    if (have_list && fetch) {
+        rc = fetch_results(c, pd->run, pd->take_max, 0, out_idx, out_score, out_qid, cap, &n_out, hstats);
         if (rc) return rc;
-        if (on_device) {
-            if (stats) {  // device-resident result: only the stats come back (this synchronises)
-                rc = fetch_stats_only();
-                if (rc) return rc;
-            }
-        } else {
-            rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, &n_out, hstats);
-            if (rc) return rc;
-            finish_work_stats(c);
-        }
-    } else if (c->ex_active) {
-        // nothing to scan on this rank, but it still takes part in the exchange
-        QueryRun run;
-        rc = exchange_only(c, q->take_type == OTTERS_TAKE_MAX, c->d_stats, &run);
-        if (rc) return rc;
-        if (on_device) {
-            if (stats) {
-                rc = fetch_stats_only();
-                if (rc) return rc;
-            }
-        } else {
-            rc = fetch_results(c, run, q->take_type == OTTERS_TAKE_MAX, 0, out_idx, out_score, out_qid, cap, &n_out, hstats);
-            if (rc) return rc;
-        }
-    } else {
-        if (d_records) {
-            // no scan: the record buffer must still hold k empty slots
-            const uint64_t k_eff = std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq);
-            if (k_eff) {
-                rc = launch_cands_to_records(c->d_list[0], c->d_list_count, (uint32_t)k_eff, map, 1, d_records, s);
-                if (rc) return rc;
-            }
-        }
+        synced = true;
+        if (pd->scan) finish_work_stats(c);
+    } else if (!have_list || stats) {
         rc = fetch_stats_only();
         if (rc) return rc;
     }
@@ -1927,15 +2066,14 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
     st.evaluated_chunks = hstats[0];
     st.pruned_chunks = st.total_chunks - st.evaluated_chunks;
     st.vectors_compared = hstats[1];
-    // every path above synchronised the stream unless the result stays on the device without stats
-    const bool synced = c->timing && !(on_device && !stats && (scan || c->ex_active));
+    const bool timed = c->timing && synced;
     float ms_f = 0.f;
-    if (synced && c->timed_meta && elapsed_ms(c->ev[0], c->ev[1], &ms_f)) {
+    if (timed && c->timed_meta && elapsed_ms(c->ev[0], c->ev[1], &ms_f)) {
         st.prune_s = ms_f * 1e-3;
         c->last.prune_ms = ms_f;
     }
-    if (synced && c->timed_rowmask && elapsed_ms(c->ev[1], c->ev[6], &ms_f)) c->last.rowmask_ms = ms_f;
-    if (synced && scan) {
+    if (timed && c->timed_rowmask && elapsed_ms(c->ev[1], c->ev[6], &ms_f)) c->last.rowmask_ms = ms_f;
+    if (timed && pd->scan) {
         if (elapsed_ms(c->ev[2], c->ev[5], &ms_f)) st.score_s = ms_f * 1e-3 + c->last.rowmask_ms * 1e-3;
         if (c->timed_single && elapsed_ms(c->ev[4], c->ev[5], &ms_f)) {
             st.merge_s = ms_f * 1e-3;
@@ -1943,23 +2081,31 @@ static int meta_query_impl(otters_metastore* ms, const otters_vec_query* q, cons
             c->last.select_ms = ms_f;
         }
     }
-    // algorithmic bytes of the metadata kernels
-    if (filter) {
-        uint64_t leaf_zm = 0, leaf_row = 0;
-        const uint32_t nl = filter->clause_offsets[filter->n_clauses];
-        for (uint32_t li = 0; li < nl; ++li) {
-            const MetaColumn& mc = ms->cols[filter->leaves[li].col];
-            leaf_zm += 2 * mc.value_bytes + 4;
-            leaf_row += mc.value_bytes;
-        }
-        const uint64_t rows_eval = q->nq ? st.vectors_compared / q->nq : 0;
-        c->last.meta_bytes = ms->n_chunks * leaf_zm + (scan ? rows_eval * leaf_row + rows_eval / 8 * nl + ms->st.n / 8 : 0);
+    // algorithmic bytes of the metadata evaluation
+    if (pd->has_filter) {
+        const uint64_t rows_eval = pd->nq ? st.vectors_compared / pd->nq : 0;
+        c->last.meta_bytes = ms->n_chunks * pd->leaf_zm +
+                             (pd->scan ? rows_eval * pd->leaf_row + rows_eval / 8 * pd->n_leaves + ms->st.n / 8 : 0);
     }
-    st.total_s = now_s() - t_total;
-    ms->last = st;
-    ms->has_stats = true;
+    st.total_s = now_s() - pd->t_submit;
+    if (synced) {
+        ms->last = st;
+        ms->has_stats = true;
+    }
     if (stats) *stats = st;
+    pd->active = false;
     return OTTERS_OK;
+}
+
+static int meta_query_impl(otters_ctx* c, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                           otters_topk_record* d_records, ShardMap map, uint64_t* out_idx, float* out_score,
+                           uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
+    if (out_len) *out_len = 0;
+    const bool want_host = !d_records && out_len != nullptr;
+    Pending pd;
+    int rc = meta_enqueue(c, ms, q, filter, d_records, map, want_host, stats != nullptr, &pd);
+    if (rc) return rc;
+    return meta_finish(c, &pd, want_host, out_idx, out_score, out_qid, cap, out_len, stats);
 }
 
 }  // namespace otters
@@ -1969,7 +2115,7 @@ extern "C" int otters_metastore_query(otters_metastore* ms, const otters_vec_que
                                       otters_query_stats* stats) {
     if (!ms || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
     DeviceGuard g(ms->ctx->device);
-    return meta_query_impl(ms, q, filter, nullptr, ShardMap{}, out_idx, out_score, out_qid, cap, out_len, stats);
+    return meta_query_impl(ms->ctx, ms, q, filter, nullptr, ShardMap{}, out_idx, out_score, out_qid, cap, out_len, stats);
 }
 
 extern "C" int otters_metastore_last_stats(const otters_metastore* ms, otters_query_stats* out) {
@@ -1982,10 +2128,9 @@ extern "C" int otters_metastore_last_stats(const otters_metastore* ms, otters_qu
 namespace otters {
 static int export_mask(otters_metastore* ms, const otters_filter* filter, bool rows, uint8_t* keep) {
     otters_ctx* c = ms->ctx;
-    uint64_t mb;
     int rc = begin_query(c);
     if (rc) return rc;
-    rc = run_meta_filter(ms, filter, 1, rows, true, &mb);
+    rc = run_meta_filter(c, ms, filter, 1, rows ? META_ROWMASK : META_PRUNE);
     if (rc) return rc;
     const uint64_t n = rows ? ms->st.n : ms->n_chunks;
     if (!filter) {
@@ -1994,7 +2139,7 @@ static int export_mask(otters_metastore* ms, const otters_filter* filter, bool r
         return OTTERS_OK;
     }
     std::vector<uint32_t> words((n + 31) / 32 + 1);
-    OTTERS_CUDA(cudaMemcpyAsync(words.data(), rows ? ms->d_row_mask : ms->d_chunk_keep, ((n + 31) / 32) * 4,
+    OTTERS_CUDA(cudaMemcpyAsync(words.data(), rows ? c->d_meta_mask : c->d_chunk_keep, ((n + 31) / 32) * 4,
                                 cudaMemcpyDeviceToHost, c->stream));
     OTTERS_CUDA(cudaStreamSynchronize(c->stream));
     for (uint64_t i = 0; i < n; ++i) keep[i] = (words[i >> 5] >> (i & 31)) & 1u;
@@ -2043,46 +2188,59 @@ extern "C" int otters_metastore_inv_norms(const otters_metastore* ms, uint64_t f
 }
 
 // =================================================================================================
-// row-sharded multi-GPU helpers
+// row-sharded multi-GPU helpers, non-blocking queries
 // =================================================================================================
-extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q,
-                                         const otters_filter* filter, const otters_shard_map* map_in, void* d_records,
-                                         otters_query_stats* stats) {
-    ShardMap map;
-    if (map_in) {
-        map.row_base = map_in->row_base;
-        map.world = map_in->world;
-        map.rank = map_in->rank;
-        map.block = map_in->block_rows;
-    }
-    if ((!vs && !ms) || (vs && ms) || !d_records) return fail(OTTERS_ERR_INVALID, "pass exactly one store and a record buffer");
-    if (ms) {
-        DeviceGuard g(ms->ctx->device);
-        return meta_query_impl(ms, q, filter, (otters_topk_record*)d_records, map, nullptr, nullptr, nullptr, 0, nullptr,
-                               stats);
-    }
-    if (filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
+namespace otters {
+
+// VecQueryPlan::collect in two halves (see meta_enqueue / meta_finish)
+static int vec_enqueue(otters_ctx* c, otters_vecstore* vs, const otters_vec_query* q, otters_topk_record* d_records, ShardMap map,
+                       bool want_host, Pending* pd) {
+    *pd = Pending{};
+    pd->t_submit = now_s();
     int rc = validate_query(q, vs->st.dim, false);
     if (rc) return rc;
-    otters_ctx* c = vs->st.ctx;
-    DeviceGuard g(c->device);
+    pd->take_max = q->take_type == OTTERS_TAKE_MAX;
+    pd->nq = q->nq;
+    c->last = otters_last_work{};
     const uint64_t k_eff = std::min<uint64_t>(q->k, vs->st.n * (uint64_t)q->nq);
-    if (q->k == 0) return OTTERS_OK;
-    if (k_eff == 0) return OTTERS_OK;
+    if (k_eff == 0 && !c->ex_active) {  // take(0) / empty store (tests/vec_store_tests.rs:430-445,488-499)
+        pd->active = true;
+        return OTTERS_OK;
+    }
     rc = begin_query(c);
     if (rc) return rc;
-    const uint32_t* d_mask = nullptr;
-    uint32_t mask_words = 0;
-    rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
+    c->want_host_result = want_host;
+    if (vs->st.n == 0) {  // (only with an exchange attached: the rank still contributes k empty records)
+        rc = exchange_only(c, pd->take_max, nullptr, &pd->run);
+    } else {
+        const uint32_t* d_mask = nullptr;
+        uint32_t mask_words = 0;
+        rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
+        if (rc) return rc;
+        rc = stage_queries(c, q, vs->st.pitch);
+        if (rc) return rc;
+        rc = run_queries(c, &vs->st, q, d_mask, mask_words, d_records, map, nullptr, nullptr, &pd->run);
+        pd->scan = true;
+    }
     if (rc) return rc;
-    rc = stage_queries(c, q, vs->st.pitch);
-    if (rc) return rc;
-    QueryRun run;
-    return run_queries(c, &vs->st, q, d_mask, mask_words, (otters_topk_record*)d_records, map, nullptr, nullptr, &run);
+    pd->active = true;
+    return OTTERS_OK;
 }
 
+static int vec_finish(otters_ctx* c, Pending* pd, bool fetch, uint64_t* out_idx, float* out_score, uint32_t* out_qid, uint64_t cap,
+                      uint64_t* out_len) {
+    if (out_len) *out_len = 0;
+    pd->active = false;
+    const bool have_list = pd->scan || pd->run.k_eff > 0 || pd->run.zero_copy;
+    if (!have_list || !fetch) return OTTERS_OK;
+    uint64_t n = 0;
+    int rc = fetch_results(c, pd->run, pd->take_max, 0, out_idx, out_score, out_qid, cap, &n, nullptr);
+    if (rc) return rc;
+    if (out_len) *out_len = n;
+    if (pd->scan) finish_work_stats(c);
+    return OTTERS_OK;
+}
 
-namespace otters {
 // no local scan on this rank (empty shard, take(0) locally impossible, swallowed per-chunk error): the rank still
 // contributes k empty records and merges everybody else's
 static int exchange_only(otters_ctx* c, int take_max, const unsigned long long* stats_src, QueryRun* run) {
@@ -2111,80 +2269,155 @@ static int exchange_only(otters_ctx* c, int take_max, const unsigned long long* 
     }
     int rc = launch_select(se, c->stream);
     if (rc) return rc;
+    c->ex_published = true;
     c->last.kernel_launches += 1;
     run->result_list = 1;
     run->k_eff = c->ex_k;
     run->big = false;
     return OTTERS_OK;
 }
-}  // namespace otters
 
-extern "C" int otters_query_exchange(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
-                                     const otters_shard_map* map_in, const otters_peer_exchange* ex, uint64_t seq, uint64_t* out_idx,
-                                     float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
-    if ((!vs && !ms) || (vs && ms) || !q || !ex) return fail(OTTERS_ERR_INVALID, "pass exactly one store, a query and an exchange");
+static int check_exchange(const otters_vec_query* q, const otters_peer_exchange* ex, uint64_t seq) {
     if (ex->world < 2 || ex->world > kMaxPeers || ex->rank >= ex->world || !ex->peer_records || !ex->peer_flags)
         return fail(OTTERS_ERR_INVALID, "peer exchange: world must be 2..8 with mapped record and flag areas");
     if (seq == 0) return fail(OTTERS_ERR_INVALID, "peer exchange: sequence numbers start at 1");
     if (q->k == 0 || q->k > kMaxFusedK || q->k > ex->k_max)
         return fail(OTTERS_ERR_UNSUPPORTED, "peer exchange serves take counts 1..min(1024, k_max)");
-    if (vs && filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
-    otters_ctx* c = vs ? vs->st.ctx : ms->ctx;
-    DeviceGuard g(c->device);
-    const bool want_fetch = out_idx || out_score || out_qid || cap;
-    if (want_fetch && !out_len) return fail(OTTERS_ERR_INVALID, "null out_len");
+    return OTTERS_OK;
+}
+
+static void attach_exchange(otters_ctx* c, const otters_vec_query* q, const otters_peer_exchange* ex, uint64_t seq) {
     c->ex_active = true;
+    c->ex_published = false;
     c->ex_world = ex->world;
     c->ex_rank = ex->rank;
     c->ex_kmax = (uint32_t)ex->k_max;
     c->ex_k = (uint32_t)q->k;
-    c->ex_seq = (uint32_t)seq;
+    c->ex_seq = (uint32_t)(seq % 0xFFFFFFFFull) + 1u;  // the flag value: never 0 (the areas start zeroed), unique within any
+                                                      // window of kExchangeSlots consecutive queries
+    c->ex_slot = (uint32_t)(seq % kExchangeSlots);
     for (uint32_t i = 0; i < ex->world; ++i) {
         c->ex_records[i] = (otters_topk_record*)ex->peer_records[i];
         c->ex_flags[i] = ex->peer_flags[i];
+    }
+}
+
+// A rank that fails after the exchange was attached but before a kernel published its records would leave the peers
+// spinning on its flag: publish k empty records instead (best effort; the caller still gets the original error).
+static void exchange_bail_out(otters_ctx* c, bool take_max) {
+    if (!c->ex_active || c->ex_published) return;
+    const std::string err = g_last_error;
+    QueryRun run;
+    c->want_host_result = false;
+    c->io_open = false;
+    if (exchange_only(c, take_max, nullptr, &run) != OTTERS_OK) cudaGetLastError();
+    g_last_error = err;
+}
+
+// the enqueue half of every query entry point: exactly one of vs / ms; ex nullable
+static int enqueue_any(otters_ctx* c, otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                       const otters_shard_map* map_in, const otters_peer_exchange* ex, uint64_t seq, bool want_host, bool want_stats,
+                       Pending* pd) {
+    if (ex) {
+        int rc = check_exchange(q, ex, seq);
+        if (rc) return rc;
+        attach_exchange(c, q, ex, seq);
     }
     struct Reset {
         otters_ctx* c;
         ~Reset() { c->ex_active = false; }
     } reset{c};
     const ShardMap map = to_map(map_in);
-    const bool take_max = q->take_type == OTTERS_TAKE_MAX;
-    int rc;
+    int rc = ms ? meta_enqueue(c, ms, q, filter, nullptr, map, want_host, want_stats, pd)
+                : vec_enqueue(c, vs, q, nullptr, map, want_host, pd);
+    if (rc) exchange_bail_out(c, q->take_type == OTTERS_TAKE_MAX);
+    return rc;
+}
+
+static int ctx_create_impl(int device, void* cuda_stream, otters_ctx** out);
+
+static otters_ctx* get_lane(otters_ctx* parent, uint32_t i) {
+    if (i == 0) return parent;
+    if (!parent->lane[i]) {
+        otters_ctx* child = nullptr;
+        if (ctx_create_impl(parent->device, nullptr, &child) != OTTERS_OK) return nullptr;
+        child->parent = parent;
+        child->tuning = parent->tuning;
+        parent->lane[i] = child;
+    }
+    return parent->lane[i];
+}
+
+}  // namespace otters
+
+extern "C" int otters_query_local_device(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q,
+                                         const otters_filter* filter, const otters_shard_map* map_in, void* d_records,
+                                         otters_query_stats* stats) {
+    if ((!vs && !ms) || (vs && ms) || !d_records) return fail(OTTERS_ERR_INVALID, "pass exactly one store and a record buffer");
+    const ShardMap map = to_map(map_in);
     if (ms) {
-        // meta_query_impl drives prune + scan + fused select/exchange; with want_fetch it also copies the result
-        uint64_t n = 0;
-        rc = meta_query_impl(ms, q, filter, nullptr, map, out_idx, out_score, out_qid, want_fetch ? cap : 0, want_fetch ? &n : nullptr,
-                             stats);
-        if (rc) return rc;
-        if (out_len) *out_len = n;
-        return OTTERS_OK;
+        DeviceGuard g(ms->ctx->device);
+        return meta_query_impl(ms->ctx, ms, q, filter, (otters_topk_record*)d_records, map, nullptr, nullptr, nullptr, 0, nullptr, stats);
     }
-    rc = validate_query(q, vs->st.dim, false);
+    if (filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
+    otters_ctx* c = vs->st.ctx;
+    DeviceGuard g(c->device);
+    Pending pd;
+    return vec_enqueue(c, vs, q, (otters_topk_record*)d_records, map, false, &pd);
+}
+
+extern "C" int otters_query_exchange(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                                     const otters_shard_map* map_in, const otters_peer_exchange* ex, uint64_t seq, uint64_t* out_idx,
+                                     float* out_score, uint32_t* out_qid, uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
+    if ((!vs && !ms) || (vs && ms) || !q || !ex) return fail(OTTERS_ERR_INVALID, "pass exactly one store, a query and an exchange");
+    if (vs && filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
+    otters_ctx* c = vs ? vs->st.ctx : ms->ctx;
+    DeviceGuard g(c->device);
+    const bool want_fetch = out_idx || out_score || out_qid || cap;
+    if (want_fetch && !out_len) return fail(OTTERS_ERR_INVALID, "null out_len");
+    if (out_len) *out_len = 0;
+    Pending pd;
+    int rc = enqueue_any(c, vs, ms, q, filter, map_in, ex, seq, want_fetch, stats != nullptr, &pd);
     if (rc) return rc;
-    rc = begin_query(c);
+    if (ms) return meta_finish(c, &pd, want_fetch, out_idx, out_score, out_qid, cap, out_len, stats);
+    return vec_finish(c, &pd, want_fetch, out_idx, out_score, out_qid, cap, out_len);
+}
+
+extern "C" int otters_query_submit(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                                   const otters_shard_map* map_in, const otters_peer_exchange* ex, uint64_t seq, uint64_t* ticket) {
+    if ((!vs && !ms) || (vs && ms) || !q || !ticket) return fail(OTTERS_ERR_INVALID, "pass exactly one store, a query and a ticket");
+    if (vs && filter) return fail(OTTERS_ERR_INVALID, "meta_filter needs a MetaStore");
+    otters_ctx* parent = vs ? vs->st.ctx : ms->ctx;
+    DeviceGuard g(parent->device);
+    const uint32_t li = parent->next_lane % kMaxLanes;
+    otters_ctx* c = get_lane(parent, li);
+    if (!c) return OTTERS_ERR_CUDA;
+    // a ticket of this lane that was never waited for is abandoned here: its result buffers are reused
+    c->pend.active = false;
+    Pending pd;
+    int rc = enqueue_any(c, vs, ms, q, filter, map_in, ex, seq, true, true, &pd);
     if (rc) return rc;
-    c->want_host_result = want_fetch;
-    QueryRun run;
-    if (vs->st.n == 0) {
-        rc = exchange_only(c, take_max, nullptr, &run);
-    } else {
-        const uint32_t* d_mask = nullptr;
-        uint32_t mask_words = 0;
-        rc = upload_row_mask(c, q, vs->st.n, &d_mask, &mask_words);
-        if (rc) return rc;
-        rc = stage_queries(c, q, vs->st.pitch);
-        if (rc) return rc;
-        rc = run_queries(c, &vs->st, q, d_mask, mask_words, nullptr, map, nullptr, nullptr, &run);
-    }
-    if (rc) return rc;
-    if (!want_fetch) {
-        if (out_len) *out_len = 0;
-        return OTTERS_OK;
-    }
-    rc = fetch_results(c, run, take_max, 0, out_idx, out_score, out_qid, cap, out_len, nullptr);
-    if (rc) return rc;
-    finish_work_stats(c);
+    parent->next_lane += 1;
+    parent->tickets += 1;
+    pd.ticket = (parent->tickets << 8) | li;
+    c->pend = pd;
+    *ticket = pd.ticket;
     return OTTERS_OK;
+}
+
+extern "C" int otters_query_wait(otters_ctx* parent, uint64_t ticket, uint64_t* out_idx, float* out_score, uint32_t* out_qid,
+                                 uint64_t cap, uint64_t* out_len, otters_query_stats* stats) {
+    if (!parent || !out_len) return fail(OTTERS_ERR_INVALID, "null argument");
+    *out_len = 0;
+    const uint32_t li = (uint32_t)(ticket & 0xFFu);
+    otters_ctx* c = li < kMaxLanes ? (li == 0 ? parent : parent->lane[li]) : nullptr;
+    if (!c || !c->pend.active || c->pend.ticket != ticket)
+        return fail(OTTERS_ERR_INVALID, "unknown or expired ticket (a lane holds one query: wait for a ticket before submitting two more)");
+    DeviceGuard g(c->device);
+    int rc = c->pend.meta ? meta_finish(c, &c->pend, true, out_idx, out_score, out_qid, cap, out_len, stats)
+                          : vec_finish(c, &c->pend, true, out_idx, out_score, out_qid, cap, out_len);
+    if (c != parent) parent->last = c->last;
+    return rc;
 }
 
 extern "C" int otters_topk_merge_device(otters_ctx* c, const void* d_records, uint64_t n_records, uint64_t k, int32_t take_type,

@@ -38,77 +38,18 @@ constexpr uint32_t kTileRows = 16;     // rows per staged tile (2 threads per ro
 constexpr uint32_t kMaxUnitRows = 128; // rows per dynamically scheduled work unit
 constexpr uint32_t kMaxFusedK = 1024;  // largest k served by the fused per-CTA top-k buffers
 constexpr uint32_t kSelectSmemElems = 8192;
+constexpr uint32_t kSelectSmemBytes = kSelectSmemElems * 12;  // working set of K3: 64-bit keys + 32-bit source tags
 constexpr uint32_t kPlannerRingTiles = 64;   // 16-row tiles in flight between the planner and the worker warps of K1
 constexpr uint32_t kPlannerRingBytes = 16 + 3 * 4 * 64 + 64 * 16 * 4 + 112;  // sizeof(Ring) rounded up to 128
 constexpr uint32_t kMaxPeers = 8;       // GPUs of one NVSwitch domain taking part in a row-sharded search
+constexpr uint32_t kExchangeSlots = 4;  // depth of the peer-exchange record / flag areas: twice the queries a context keeps in flight
+constexpr uint32_t kMaxLanes = 2;       // queries a context keeps in flight (otters_query_submit / otters_query_wait)
 constexpr uint32_t kBatchRows = 128;    // store rows per tile of the batched kernel (UMMA M)
 constexpr uint32_t kBatchQueries = 256; // queries per tile of the batched kernel (UMMA N)
 
 struct DevLeaf;
 
-// ---- scan kernel ------------------------------------------------------------------------------
-struct ScanParams {
-    const float* vectors;       // [n_rows][pitch_g]
-    const float* inv_norms;     // [n_rows]
-    const float* query;         // [dim_pad] zero padded, device
-    float q_inv;                // 1/|q| (0 for a zero query), computed like src/vec.rs:390-397
-    uint64_t pitch_g;           // floats per stored row (dim rounded up to 4)
-    uint32_t dim;
-    uint32_t dim_pad;
-    uint32_t n_rows;
-    const uint32_t* row_mask;   // Lsb0 32-bit words, bit=1 keep; null = all rows
-    uint32_t row_mask_words;    // words available; rows past them are kept
-    // fused predicate (MetaStore): when flt_leaves != null the producer evaluates the CNF itself for the
-    // rows of every unit whose chunk survived pruning, instead of reading a precomputed row mask
-    const DevLeaf* flt_leaves;
-    const uint32_t* flt_clause_off;
-    uint32_t flt_n_clauses;
-    uint32_t flt_n_leaves;
-    const uint32_t* chunk_keep; // Lsb0 words, one bit per chunk
-    uint32_t chunk_size;
-    uint32_t off_filter;        // shared-memory offset of the staged filter
-    uint32_t n_units;
-    uint32_t unit_rows;         // 32, 64 or 128: rows of the first n_big work units
-    uint32_t unit_small;        // 16 or 32: rows of the remaining units (the tail of the store)
-    uint32_t n_big;
-    uint32_t* unit_counter;
-    // selection
-    uint32_t k;
-    uint32_t cap;               // per-CTA candidate buffer capacity (power of two >= 2k)
-    int32_t take_max;
-    int32_t has_filter;
-    float thr;
-    int32_t cmp;
-    const uint64_t* tau_in;     // device: running threshold key from earlier queries of a batch (0 = none)
-    unsigned long long* g_tau;  // device: grid-wide threshold shared by the CTAs of this launch (zeroed per query; may be null)
-    uint32_t qid;
-    // staging layout
-    uint32_t kc;                // columns per slot
-    uint32_t nkc;               // slots steps per tile
-    uint32_t pitch_s;           // floats per staged row in shared memory (== 8 mod 32)
-    uint32_t slots;             // slots per warp
-    uint32_t planners;          // planner front-end (scan_planner.cu): planner warps per CTA (0 = autonomous warps)
-    uint32_t off_ring;          // planner front-end: shared-memory offset of the tile ring
-    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
-    // outputs (fused mode)
-    uint64_t* cta_keys;         // [grid][k]
-    uint32_t* cta_counts;       // [grid]
-    // outputs (emit-all mode)
-    Cand* emit;                 // candidate array
-    uint32_t* emit_count;
-    uint32_t emit_cap;
-    // instrumentation
-    unsigned long long* rows_scored;
-};
-
-struct ScanLaunch {
-    uint32_t grid, block, smem_bytes;
-};
-
-int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, uint32_t* smem_configured, cudaStream_t s);
-int launch_scan_planner(const ScanParams& p, const ScanLaunch& l, int metric, uint32_t* smem_configured, cudaStream_t s);
-
-// ---- selection kernels ------------------------------------------------------------------------
+// ---- selection (K3; stand-alone kernel or fused into the last CTA of a scan kernel) --------------
 // Every result list in device memory is preceded by this 64-byte header, so that one D2H copy returns
 // the count, the instrumentation counters and the ordered candidates together.
 struct ResultHeader {
@@ -149,11 +90,93 @@ struct SelectParams {
     // fused peer exchange of the row-sharded search (ex_world > 1): this rank's k records are stored straight into
     // every peer's record area over NVLink, a per-(query parity, rank) flag publishes them, and the same kernel
     // waits for the other ranks' records and merges all of them into `out`
-    uint32_t ex_world, ex_rank, ex_kmax, ex_seq;
+    uint32_t ex_world, ex_rank, ex_kmax, ex_seq;  // ex_seq != 0: the flag value that publishes this query's records
+    uint32_t ex_slot;                           // which of the kExchangeSlots record / flag areas this query uses
     uint32_t ex_k;                              // records every rank contributes (the caller's take count)
-    otters_topk_record* ex_records[kMaxPeers];  // peer p's record area as mapped here: [2][world][k_max]
-    uint32_t* ex_flags[kMaxPeers];              // peer p's flag area: [2][world]
+    otters_topk_record* ex_records[kMaxPeers];  // peer p's record area as mapped here: [kExchangeSlots][world][k_max]
+    uint32_t* ex_flags[kMaxPeers];              // peer p's flag area: [kExchangeSlots][world]
 };
+// The opt-in dynamic shared-memory limit belongs to (kernel function, device) and is shared by every context of the
+// process (a context's lanes included): it is tracked per device in a static of each launch wrapper and only ever raised.
+// (Tracking it per context let a second context LOWER the limit under the first one's feet: invalid-argument launches.)
+inline uint32_t& smem_limit_slot(uint32_t (&slots)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return slots[dev & 63];
+}
+
+// ---- scan kernel ------------------------------------------------------------------------------
+struct ScanParams {
+    const float* vectors;       // [n_rows][pitch_g]
+    const float* inv_norms;     // [n_rows]
+    const float* query;         // [dim_pad] zero padded, device
+    float q_inv;                // 1/|q| (0 for a zero query), computed like src/vec.rs:390-397
+    uint64_t pitch_g;           // floats per stored row (dim rounded up to 4)
+    uint32_t dim;
+    uint32_t dim_pad;
+    uint32_t n_rows;
+    const uint32_t* row_mask;   // Lsb0 32-bit words, bit=1 keep; null = all rows
+    uint32_t row_mask_words;    // words available; rows past them are kept
+    // fused predicate (MetaStore): when flt_leaves != null the producer evaluates the CNF itself for the
+    // rows of every unit whose chunk survived pruning, instead of reading a precomputed row mask
+    const DevLeaf* flt_leaves;
+    const uint32_t* flt_clause_off;
+    uint32_t flt_n_clauses;
+    uint32_t flt_n_leaves;
+    const uint32_t* chunk_keep; // Lsb0 words, one bit per chunk (stand-alone prune kernel); null with flt_leaves set = LAZY
+                                // pruning: every warp evaluates the zonemap / Bloom rules of its unit's chunks itself and the
+                                // unit holding a chunk's first row accounts it in `stats` (no K0 launch on the query path)
+    uint32_t chunk_size;
+    uint32_t n_chunks;
+    uint32_t nq_stats;          // lazy pruning: queries of the batch (vectors_compared = sum over kept chunks of len * nq)
+    unsigned long long* stats;  // lazy pruning: [0] evaluated chunks, [1] vectors_compared
+    uint32_t off_filter;        // shared-memory offset of the staged filter
+    uint32_t n_units;
+    uint32_t unit_rows;         // 32, 64 or 128: rows of the first n_big work units
+    uint32_t unit_small;        // 16 or 32: rows of the remaining units (the tail of the store)
+    uint32_t n_big;
+    uint32_t* unit_counter;
+    // selection
+    uint32_t k;
+    uint32_t cap;               // per-CTA candidate buffer capacity (power of two >= 2k)
+    int32_t take_max;
+    int32_t has_filter;
+    float thr;
+    int32_t cmp;
+    const uint64_t* tau_in;     // device: running threshold key from earlier queries of a batch (0 = none)
+    unsigned long long* g_tau;  // device: grid-wide threshold shared by the CTAs of this launch (zeroed per query; may be null)
+    uint32_t qid;
+    // staging layout
+    uint32_t kc;                // columns per slot
+    uint32_t nkc;               // slots steps per tile
+    uint32_t pitch_s;           // floats per staged row in shared memory (== 8 mod 32)
+    uint32_t slots;             // slots per warp
+    uint32_t planners;          // planner front-end (scan_planner.cu): planner warps per CTA (0 = autonomous warps)
+    uint32_t off_ring;          // planner front-end: shared-memory offset of the tile ring
+    uint32_t off_query, off_warps, warp_bytes, off_w_rows, off_w_info, off_w_inv, off_w_list, off_w_slots;
+    // outputs (fused mode)
+    uint64_t* cta_keys;         // [grid][k]
+    uint32_t* cta_counts;       // [grid]
+    // outputs (emit-all mode)
+    Cand* emit;                 // candidate array
+    uint32_t* emit_count;
+    uint32_t emit_cap;
+    // instrumentation
+    unsigned long long* rows_scored;
+    // fused selection: the last CTA to publish its list (ticket from done_counter) runs K3 itself — one launch per query
+    uint32_t fuse_select;
+    uint32_t* done_counter;
+    SelectParams sel;
+};
+
+struct ScanLaunch {
+    uint32_t grid, block, smem_bytes;
+};
+
+int launch_scan(const ScanParams& p, const ScanLaunch& l, int metric, bool emit_all, uint32_t* smem_configured, cudaStream_t s);
+int launch_scan_planner(const ScanParams& p, const ScanLaunch& l, int metric, uint32_t* smem_configured, cudaStream_t s);
+
+// ---- selection kernels ------------------------------------------------------------------------
 int launch_select(const SelectParams& p, cudaStream_t s);
 
 // records (after all-gather) -> global best k
@@ -265,9 +288,10 @@ struct DevLeaf {         // one lowered leaf, self-contained: carries the device
     float f32;
     int32_t i32;
     uint32_t code;
-    uint32_t pad;
+    uint32_t bloom_k0;   // LEAF_STR: probes of a full chunk's filter
     uint64_t h1, h2;     // LEAF_STR: Bloom probe hashes of the literal
     uint64_t bloom_m0, bloom_a0, bloom_b0;  // filter size of a full chunk and h1 % m0, h2 % m0 (step, never 0)
+    uint64_t bloom_full_chunks;             // chunks [0, n_rows / chunk_size) are full: m = m0, k = k0 without a load
     const void* values;
     const uint32_t* null_words;
     const void* zmin;

@@ -15,59 +15,6 @@
 namespace otters {
 namespace {
 
-__device__ __forceinline__ bool chunk_leaf_rule(const DevLeaf& lf, uint32_t ch);
-
-template <typename T>
-__device__ __forceinline__ bool range_sat(int op, T mn, T mx, T t) {
-    switch (op) {
-    case OTTERS_OP_EQ: return mn <= t && t <= mx;
-    case OTTERS_OP_LT: return mn < t;
-    case OTTERS_OP_LTE: return mn <= t;
-    case OTTERS_OP_GT: return mx > t;
-    case OTTERS_OP_GTE: return mx >= t;
-    default: return true;  // Neq
-    }
-}
-
-__device__ __forceinline__ bool chunk_leaf_sat(const DevLeaf& lf, uint32_t ch) {
-    const bool has_rows = __ldg(lf.non_null + ch) != 0;  // every rule is ANDed with non_null > 0
-    return chunk_leaf_rule(lf, ch) && has_rows;
-}
-
-__device__ __forceinline__ bool chunk_leaf_rule(const DevLeaf& lf, uint32_t ch) {
-    switch (lf.exec) {
-    case LEAF_I32: return range_sat<int32_t>(lf.op, ((const int32_t*)lf.zmin)[ch], ((const int32_t*)lf.zmax)[ch], lf.i32);
-    case LEAF_I64: return range_sat<int64_t>(lf.op, ((const int64_t*)lf.zmin)[ch], ((const int64_t*)lf.zmax)[ch], lf.i64);
-    case LEAF_F32: return range_sat<float>(lf.op, ((const float*)lf.zmin)[ch], ((const float*)lf.zmax)[ch], lf.f32);
-    case LEAF_F64: return range_sat<double>(lf.op, ((const double*)lf.zmin)[ch], ((const double*)lf.zmax)[ch], lf.f64);
-    default: {  // LEAF_STR — src/meta.rs:523-544
-        if (lf.op == OTTERS_OP_NEQ) return true;
-        if (lf.op != OTTERS_OP_EQ) return false;
-        const uint64_t* w = lf.bloom + (size_t)ch * lf.bloom_stride;
-        const uint64_t m = lf.bloom_mbits[ch];
-        const uint32_t kh = lf.bloom_k[ch];
-        // probe i = (a + i*b) mod m, a = h1 mod m, b = h2 mod m (1 if 0), stepped without a division per probe; a and b
-        // come precomputed for the filter size of a full chunk
-        uint64_t bit, step;
-        if (m == lf.bloom_m0) {
-            bit = lf.bloom_a0;
-            step = lf.bloom_b0;
-        } else {
-            bit = lf.h1 % m;
-            step = lf.h2 % m;
-            if (step == 0) step = 1;
-        }
-        bool all = true;  // every probe is issued (no early exit) so that the word loads overlap
-        for (uint32_t i = 0; i < kh; ++i) {
-            all &= ((__ldg(w + (bit >> 6)) >> (bit & 63)) & 1ull) != 0;
-            bit += step;
-            if (bit >= m) bit -= m;
-        }
-        return all;
-    }
-    }
-}
-
 // K0: one thread per chunk.  The lowered filter is staged in shared memory first and every leaf is evaluated
 // unconditionally, so the zonemap / Bloom loads of all leaves are in flight together (three dependent memory
 // round trips in total instead of one chain per leaf).

@@ -23,6 +23,7 @@
 #include "internal.h"
 #include "predicate.cuh"
 #include "scan_shared.cuh"
+#include "select_body.cuh"
 
 namespace otters {
 
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     bool prod_done = false;
     uint32_t prod_step = 0, cons_step = 0;
     unsigned long long scored = 0;
+    unsigned long long st_chunks = 0, st_vecs = 0;  // lazy pruning: chunks kept / rows of kept chunks x queries (per lane)
 
     auto issue = [&]() {
         if (prod_done) return;
@@ -116,20 +118,46 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
                 }
                 if (r >= p.n_rows) bits = 0;
                 else if (p.n_rows - r < rpl) bits &= (1u << (p.n_rows - r)) - 1u;
-                if (p.flt_leaves) {
-                    // fused K0b: chunk bit from the prune kernel, then the CNF over the row's metadata
-                    uint32_t ch = r / p.chunk_size;
-                    uint64_t ch_end = (uint64_t)(ch + 1) * p.chunk_size;  // first row of the next chunk
-                    uint32_t keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                if (p.flt_leaves && r < p.n_rows) {
                     uint32_t out = 0;
-                    for (uint32_t j = 0; j < rpl; ++j) {
-                        const uint32_t row = r + j;
-                        if ((uint64_t)row >= ch_end) {  // crossed into the next chunk
-                            ch = row / p.chunk_size;
-                            ch_end = (uint64_t)(ch + 1) * p.chunk_size;
-                            keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                    if (p.chunk_keep) {
+                        // fused K0b: chunk bit from the prune kernel, then the CNF over the row's metadata
+                        uint32_t ch = r / p.chunk_size;
+                        uint64_t ch_end = (uint64_t)(ch + 1) * p.chunk_size;  // first row of the next chunk
+                        uint32_t keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                        for (uint32_t j = 0; j < rpl; ++j) {
+                            const uint32_t row = r + j;
+                            if (row >= p.n_rows) break;
+                            if ((uint64_t)row >= ch_end) {  // crossed into the next chunk
+                                ch = row / p.chunk_size;
+                                ch_end = (uint64_t)(ch + 1) * p.chunk_size;
+                                keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                            }
+                            if (((bits >> j) & 1u) && keep_ch && row_passes(f_leaves, f_off, p.flt_n_clauses, row)) out |= 1u << j;
                         }
-                        if (((bits >> j) & 1u) && keep_ch && row_passes(f_leaves, f_off, p.flt_n_clauses, row)) out |= 1u << j;
+                    } else if (rpl * lane < urows) {
+                        // fused K0 + K0b (lazy pruning): the zonemap / Bloom rules of the chunk(s) this lane's rows fall into are
+                        // evaluated right here (uniform addresses across the warp for the usual chunk >= unit case: broadcast
+                        // loads that hit L2), and the lane holding a chunk's FIRST row accounts the chunk in the statistics —
+                        // every row of the store belongs to exactly one lane of one unit, so every chunk is counted once
+                        // (src/meta.rs:666-669, src/meta_compute.rs:166)
+                        uint32_t ch = 0;
+                        uint64_t ch_end = 0;
+                        bool keep_ch = false;
+                        for (uint32_t j = 0; j < rpl; ++j) {
+                            const uint32_t row = r + j;
+                            if (row >= p.n_rows) break;
+                            if ((uint64_t)row >= ch_end) {
+                                ch = row / p.chunk_size;
+                                ch_end = (uint64_t)(ch + 1) * p.chunk_size;
+                                keep_ch = chunk_passes(f_leaves, f_off, p.flt_n_clauses, ch);
+                            }
+                            if (keep_ch && (uint64_t)row + p.chunk_size == ch_end) {  // first row of its chunk
+                                st_chunks += 1ull;
+                                st_vecs += (unsigned long long)(ch_end <= p.n_rows ? p.chunk_size : p.n_rows - row) * p.nq_stats;
+                            }
+                            if (((bits >> j) & 1u) && keep_ch && row_passes(f_leaves, f_off, p.flt_n_clauses, row)) out |= 1u << j;
+                        }
                     }
                     bits = out;
                 }
@@ -287,8 +315,21 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         for (int d = 16; d > 0; d >>= 1) scored += __shfl_xor_sync(FULL, scored, d);
         if (lane == 0 && scored) atomicAdd(p.rows_scored, scored);
     }
+    if (p.flt_leaves && !p.chunk_keep && p.stats) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            st_chunks += __shfl_xor_sync(FULL, st_chunks, d);
+            st_vecs += __shfl_xor_sync(FULL, st_vecs, d);
+        }
+        if (lane == 0 && st_chunks) {
+            atomicAdd(&p.stats[0], st_chunks);
+            atomicAdd(&p.stats[1], st_vecs);
+        }
+    }
 
     if (!EMIT_ALL) {
+        if (p.fuse_select && lane == 0)
+            for (uint32_t s = 0; s < p.slots; ++s) mbar_inval(&bars[s]);  // the shared memory is about to be repurposed
         __syncthreads();
         if (warp == 0) {
             const uint32_t cnt = hdr->count;  // every push has completed: cnt <= cap and written == cnt
@@ -297,6 +338,22 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
             for (uint32_t i = lane; i < n; i += 32) p.cta_keys[(size_t)blockIdx.x * p.k + i] = cbuf[i];
             if (lane == 0) p.cta_counts[blockIdx.x] = n;
         }
+        if (p.fuse_select) {
+            // K3 fused into the scan: the CTA that publishes its list LAST (ticket from a global counter; the lists, the
+            // row / chunk counters and the ticket are ordered by the fences) selects the final top-k — and, in a row-sharded
+            // search, exchanges it with the peers — with the threads and the shared memory it already owns.  The other
+            // CTAs have exited by then, so the next query's scan (enqueued on the context's other lane) already fills
+            // their SMs: selection and exchange overlap the next scan instead of sitting between two launches.
+            __shared__ uint32_t s_last;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1u;
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                select_detail::select_body<false>(p.sel, smem);
+            }
+        }
     }
 }
 
@@ -304,7 +361,9 @@ template <int METRIC, bool EMIT>
 int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
     auto kern = scan_kernel<METRIC, EMIT>;
     // the opt-in shared-memory limit is sticky per function and device: raise it only when it grows
-    uint32_t& have = smem_configured[METRIC * 2 + (EMIT ? 1 : 0)];
+    static uint32_t limits[64];
+    uint32_t& have = smem_limit_slot(limits);
+    (void)smem_configured;
     if (l.smem_bytes > have) {
         OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
         have = l.smem_bytes;

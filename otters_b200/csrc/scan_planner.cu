@@ -17,6 +17,7 @@
 #include "internal.h"
 #include "predicate.cuh"
 #include "scan_shared.cuh"
+#include "select_body.cuh"
 
 namespace otters {
 
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
         // =============================== planner ===============================
         uint32_t u_pref = 0;
         unsigned long long g_pref = 0;  // grid-wide threshold, read together with the unit id
+        unsigned long long st_chunks = 0, st_vecs = 0;  // lazy pruning: chunks kept / rows of kept chunks x queries (per lane)
         if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
         for (;;) {
             const uint32_t u = __shfl_sync(FULL, u_pref, 0);
@@ -119,19 +121,47 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
             }
             if (r >= p.n_rows) bits = 0;
             else if (p.n_rows - r < rpl) bits &= (1u << (p.n_rows - r)) - 1u;
-            if (p.flt_leaves && r < p.n_rows) {
+            if (p.flt_leaves && r < p.n_rows && rpl * lane < urows) {  // (lanes past the unit's rows own nothing)
                 // chunk bits from the prune kernel AND the CNF over the row's metadata (fused K0b).  The chunk words are
                 // requested first but only used after the predicate, so that all loads of the unit — chunk words, null
                 // words, column values — are in flight together: under a saturated HBM every dependent round trip costs
                 // microseconds.  (Rows of pruned chunks get their metadata read for nothing: ~20 B against 0.5-6 KB per row.)
-                uint32_t kw[4];
+                uint32_t kwm = 0;
+                if (p.chunk_keep) {
 #pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) {
-                    const uint32_t ch = (r + (j < rpl ? j : 0)) / p.chunk_size;
-                    kw[j] = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        if (j < rpl && r + j < p.n_rows) {
+                            const uint32_t ch = (r + j) / p.chunk_size;
+                            kwm |= ((__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u) << j;
+                        }
+                    }
+                } else {
+                    // lazy pruning (see scan.cu): zonemap / Bloom rules of the chunks of this lane's rows, evaluated here; the
+                    // lane holding a chunk's first row accounts it in the statistics
+                    uint32_t ch_prev = 0xFFFFFFFFu;
+                    bool keep_ch = false;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        if (j < rpl && r + j < p.n_rows) {
+                            const uint32_t row = r + j;
+                            const uint32_t ch = row / p.chunk_size;
+                            if (ch != ch_prev) {
+                                keep_ch = chunk_passes(f_leaves, f_off, p.flt_n_clauses, ch);
+                                ch_prev = ch;
+                            }
+                            if (keep_ch) {
+                                kwm |= 1u << j;
+                                if ((uint64_t)row == (uint64_t)ch * p.chunk_size) {  // first row of its chunk
+                                    st_chunks += 1ull;
+                                    const uint64_t ch_end = (uint64_t)(ch + 1) * p.chunk_size;
+                                    st_vecs += (unsigned long long)(ch_end <= p.n_rows ? p.chunk_size : p.n_rows - row) * p.nq_stats;
+                                }
+                            }
+                        }
+                    }
                 }
                 bits = rows_pass_mlp(f_leaves, f_off, p.flt_n_clauses, p.flt_n_leaves, r, bits, rpl);
-                bits &= kw[0] | (kw[1] << 1) | (kw[2] << 2) | (kw[3] << 3);
+                bits &= kwm;
             }
             const uint32_t c = __popc(bits);
             uint32_t incl = c;
@@ -177,6 +207,17 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
         if (lane == 0) {
             __threadfence_block();
             atomicAdd(&ring->done, 1u);
+        }
+        if (p.flt_leaves && !p.chunk_keep && p.stats) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                st_chunks += __shfl_xor_sync(FULL, st_chunks, d);
+                st_vecs += __shfl_xor_sync(FULL, st_vecs, d);
+            }
+            if (lane == 0 && st_chunks) {
+                atomicAdd(&p.stats[0], st_chunks);
+                atomicAdd(&p.stats[1], st_vecs);
+            }
         }
     } else {
         // =============================== worker ===============================
@@ -300,6 +341,7 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
         for (int d = 16; d > 0; d >>= 1) scored += __shfl_xor_sync(FULL, scored, d);
         if (lane == 0 && scored) atomicAdd(p.rows_scored, scored);
     }
+    if (p.fuse_select && bar && lane == 0) mbar_inval(bar);  // the shared memory is about to be repurposed
     __syncthreads();
     if (warp == 0) {
         const uint32_t cnt = hdr->count;  // every push has completed: cnt <= cap and written == cnt
@@ -308,12 +350,26 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
         for (uint32_t i = lane; i < n; i += 32) p.cta_keys[(size_t)blockIdx.x * p.k + i] = cbuf[i];
         if (lane == 0) p.cta_counts[blockIdx.x] = n;
     }
+    if (p.fuse_select) {
+        // K3 fused into the scan (see scan.cu): the CTA that publishes its list last selects the final top-k
+        __shared__ uint32_t s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            select_detail::select_body<false>(p.sel, smem);
+        }
+    }
 }
 
 template <int METRIC>
 int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
     auto kern = scan_planner_kernel<METRIC>;
-    uint32_t& have = smem_configured[METRIC];
+    static uint32_t limits[64];
+    uint32_t& have = smem_limit_slot(limits);
+    (void)smem_configured;
     if (l.smem_bytes > have) {
         OTTERS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes));
         have = l.smem_bytes;

@@ -349,6 +349,12 @@ class MetaStore:
             )
         return mn[:nc], mx[:nc], nn[:nc]
 
+    def set_rows(self, rows, data) -> None:
+        """Overwrites stored vectors (bench/test utility: planting near-duplicates into a synthetic store)."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.float32).reshape(len(rows), -1)
+        check(_ffi.otters_metastore_set_rows(self._h, rows.ctypes.data_as(_ffi.c_u64p), data.ctypes.data_as(_ffi.c_f32p), len(rows)))
+
     def inv_norms(self) -> np.ndarray:
         out = np.zeros(max(self._n_rows, 1), np.float32)
         check(_ffi.otters_metastore_inv_norms(self._h, 0, self._n_rows, out.ctypes.data_as(_ffi.c_f32p)))
@@ -445,7 +451,10 @@ class MetaQueryPlan:
                 C.byref(st),
             )
         )
-        m = min(out_len.value, cap)
+        return self._results(idx, score, qid, min(out_len.value, cap), st)
+
+    def _results(self, idx, score, qid, m, st) -> MetaQueryResults:
+        store = self._store
         store._last_stats = MetaQueryStats(
             st.total_chunks, st.pruned_chunks, st.evaluated_chunks, st.vectors_compared, st.prune_s, st.score_s, st.merge_s, st.total_s
         )
@@ -453,3 +462,28 @@ class MetaQueryPlan:
         names = sorted(store.schema().keys())  # src/meta.rs:723-724
         data = {n: store.columns()[n].gather(indices) for n in names}
         return MetaQueryResults(names, data, indices, [float(s) for s in score[:m]], [int(x) for x in qid[:m]])
+
+    def submit(self) -> "PendingMetaQuery":
+        """Non-blocking form of collect() (``otters_query_submit``): the query is enqueued on one of the context's two lanes and
+        runs while the caller prepares the next one; ``wait()`` on the returned object gives what collect() would have returned.
+        Keep at most two queries outstanding per context."""
+        if self._meta_error is not None:
+            raise OttersError(self._meta_error)
+        vq, fp, q, k, nq = self.build_query()
+        ticket = C.c_uint64(0)
+        check(_ffi.otters_query_submit(None, self._store.handle, C.byref(vq), fp.byref() if fp else None, None, None, 0, C.byref(ticket)))
+        return PendingMetaQuery(self, ticket.value, max(min(k, self._store.len() * max(nq, 1)), 1))
+
+
+class PendingMetaQuery:
+    def __init__(self, plan: MetaQueryPlan, ticket: int, cap: int):
+        self._plan, self.ticket, self._cap = plan, ticket, cap
+
+    def wait(self) -> MetaQueryResults:
+        cap = self._cap
+        idx, score, qid = np.zeros(cap, np.uint64), np.zeros(cap, np.float32), np.zeros(cap, np.uint32)
+        out_len = C.c_uint64(0)
+        st = _ffi.QueryStats()
+        check(_ffi.otters_query_wait(self._plan._store.ctx.handle, self.ticket, idx.ctypes.data_as(_ffi.c_u64p),
+                                     score.ctypes.data_as(_ffi.c_f32p), qid.ctypes.data_as(_ffi.c_u32p), cap, C.byref(out_len), C.byref(st)))
+        return self._plan._results(idx, score, qid, min(out_len.value, cap), st)

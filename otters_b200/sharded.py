@@ -98,6 +98,9 @@ class CudaShard:
         self.peer = None      # _ffi.PeerExchange once enable_peer_exchange() succeeded
         self.peer_error = None
         self._seq = 0
+        # The NCCL path mixes work of two producers: the library enqueues on the context's stream, torch.distributed on
+        # torch's current stream.  They are ordered for free only when both are the SAME stream (build the Context from
+        # torch.cuda.current_stream().cuda_stream); otherwise enqueue()/merge() fall back to host-side synchronisation.
 
     # ---- fused exchange over peer memory -------------------------------------------------------------------
     def enable_peer_exchange(self) -> bool:
@@ -110,8 +113,8 @@ class CudaShard:
         try:
             import torch.distributed._symmetric_memory as symm
 
-            flag_bytes = 256  # 2 * world uint32, padded
-            rec_bytes = 2 * self.world * self.k_max * 16
+            flag_bytes = 256  # EXCHANGE_SLOTS * world uint32, padded
+            rec_bytes = ffi.EXCHANGE_SLOTS * self.world * self.k_max * 16
             dev = torch.device("cuda", self.ctx.device)
             buf = symm.empty(flag_bytes + rec_bytes, dtype=torch.uint8, device=dev)
             group = self.group if self.group is not None else dist.group.WORLD
@@ -174,6 +177,42 @@ class CudaShard:
         m = min(out_len.value, k)
         return (out[0][:m], out[1][:m], out[2][:m]), st
 
+    def submit(self, vq, fp) -> int:
+        """Non-blocking search (``otters_query_submit``): enqueues the query on one of the context's two lanes — with the fused
+        peer exchange when it is enabled and world > 1 — and returns a ticket for ``wait``.  Keep at most two tickets outstanding."""
+        ffi = self._ffi
+        self._seq += 1
+        if self.is_meta:
+            vs, ms, flt = None, self.store.handle, (fp.byref() if fp else None)
+        else:
+            self.store._flush()
+            vs, ms, flt = self.store._handle(), None, None
+        ticket = C.c_uint64(0)
+        rc = ffi.otters_query_submit(vs, ms, C.byref(vq), flt, C.byref(self.map), C.byref(self.peer) if self.peer is not None else None,
+                                     self._seq, C.byref(ticket))
+        if rc != 0:
+            from .types import OttersError
+
+            raise OttersError(ffi.last_error())
+        return ticket.value
+
+    def wait(self, ticket: int, k: int, want_stats: bool = False):
+        """Blocks until the query behind ``ticket`` has finished; returns ((rows, scores, query ids), stats) like search_fused."""
+        ffi = self._ffi
+        cache = getattr(self, "_wait_cache", None)
+        if cache is None or cache[0] < k:
+            out = (np.zeros(k, np.uint64), np.zeros(k, np.float32), np.zeros(k, np.uint32))
+            cache = self._wait_cache = (k, out, out[0].ctypes.data_as(ffi.c_u64p), out[1].ctypes.data_as(ffi.c_f32p),
+                                        out[2].ctypes.data_as(ffi.c_u32p), C.c_uint64(0), ffi.QueryStats())
+        _, out, p_idx, p_score, p_qid, out_len, st = cache
+        rc = ffi.otters_query_wait(self.ctx.handle, ticket, p_idx, p_score, p_qid, k, C.byref(out_len), C.byref(st) if want_stats else None)
+        if rc != 0:
+            from .types import OttersError
+
+            raise OttersError(ffi.last_error())
+        m = min(out_len.value, k)
+        return (out[0][:m], out[1][:m], out[2][:m]), st
+
     def enqueue(self, vq, fp, k: int, want_stats: bool = False):
         """Enqueues local search + all-gather on the context's stream; returns the gathered record tensor."""
         ffi = self._ffi
@@ -192,14 +231,21 @@ class CudaShard:
             raise OttersError(ffi.last_error())
         if self.world > 1:
             gathered = self.gathered[: self.world * k]
+            if not self._stream_shared():
+                self.ctx.synchronize()  # the records must be complete before NCCL (on torch's stream) reads them
             self._dist.all_gather_into_tensor(gathered, local, group=self.group)
         else:
             gathered = local
         return gathered, st
 
+    def _stream_shared(self) -> bool:
+        return self.ctx.stream is not None and self.ctx.stream == self._torch.cuda.current_stream().cuda_stream
+
     def merge(self, gathered, k: int, take_max: bool, fetch: bool = True):
         ffi = self._ffi
         n = gathered.shape[0]
+        if self.world > 1 and not self._stream_shared():
+            self._torch.cuda.current_stream().synchronize()  # the all-gather must have landed before the merge kernel reads it
         out_len = C.c_uint64(0)
         if not fetch:
             rc = ffi.otters_topk_merge_device(self.ctx.handle, C.c_void_p(gathered.data_ptr()), n, k, 1 if take_max else 0,

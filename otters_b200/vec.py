@@ -126,6 +126,13 @@ class VecStore:
     def is_empty(self) -> bool:
         return self._n == 0
 
+    def set_rows(self, rows, data) -> None:
+        """Overwrites stored rows (bench/test utility: planting near-duplicates into a synthetic store)."""
+        self._flush()
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.float32).reshape(len(rows), self.dim)
+        check(_ffi.otters_vecstore_set_rows(self._handle(), rows.ctypes.data_as(_ffi.c_u64p), data.ctypes.data_as(_ffi.c_f32p), len(rows)))
+
     def inv_norms(self) -> np.ndarray:
         self._flush()
         out = np.zeros(self._n, dtype=np.float32)
@@ -219,8 +226,7 @@ class VecQueryPlan:
                     f"Query vector length {q.shape[0]} does not match expected dimension {self._store.dim}"
                 )
 
-    def collect_arrays(self):
-        """Returns (indices u64, scores f32, query ids u32) best-first."""
+    def _build_query(self):
         self._validate()
         store = self._store
         store._flush()
@@ -228,8 +234,6 @@ class VecQueryPlan:
         k = self._take_count if self._take_count is not None else n  # src/vec.rs:213
         tt = self._take_type if self._take_type is not None else TakeType.Max  # src/vec.rs:214
         nq = len(self._queries)
-        if n == 0 or k == 0:
-            return np.zeros(0, np.uint64), np.zeros(0, np.float32), np.zeros(0, np.uint32)
         q = np.ascontiguousarray(np.stack(self._queries), dtype=np.float32)
         vq = _ffi.VecQuery()
         vq.queries = q.ctypes.data_as(_ffi.c_f32p)
@@ -242,7 +246,14 @@ class VecQueryPlan:
             words = pack_mask_words(self._row_mask)
             vq.row_mask_words = words.ctypes.data_as(_ffi.c_u64p)
             vq.row_mask_bits = len(self._row_mask)
-        cap = min(k, n * nq)
+        return vq, (q, words), min(k, n * nq)
+
+    def collect_arrays(self):
+        """Returns (indices u64, scores f32, query ids u32) best-first."""
+        vq, keep, cap = self._build_query()
+        store = self._store
+        if cap == 0:
+            return np.zeros(0, np.uint64), np.zeros(0, np.float32), np.zeros(0, np.uint32)
         idx = np.zeros(cap, np.uint64)
         score = np.zeros(cap, np.float32)
         qid = np.zeros(cap, np.uint32)
@@ -261,7 +272,29 @@ class VecQueryPlan:
         m = min(out_len.value, cap)
         return idx[:m], score[:m], qid[:m]
 
+    def submit(self) -> "PendingVecQuery":
+        """Non-blocking form of collect_arrays() (``otters_query_submit``); at most two outstanding per context."""
+        vq, keep, cap = self._build_query()
+        ticket = C.c_uint64(0)
+        check(_ffi.otters_query_submit(self._store._handle(), None, C.byref(vq), None, None, None, 0, C.byref(ticket)))
+        return PendingVecQuery(self._store, ticket.value, cap)
+
     def collect(self) -> List[SearchResult]:
         """src/vec.rs:206-311."""
         idx, score, _ = self.collect_arrays()
         return [SearchResult(int(i), float(s)) for i, s in zip(idx, score)]
+
+
+class PendingVecQuery:
+    def __init__(self, store: VecStore, ticket: int, cap: int):
+        self._store, self.ticket, self._cap = store, ticket, cap
+
+    def wait(self):
+        """(indices u64, scores f32, query ids u32) best-first, as collect_arrays() returns them."""
+        cap = max(self._cap, 1)
+        idx, score, qid = np.zeros(cap, np.uint64), np.zeros(cap, np.float32), np.zeros(cap, np.uint32)
+        out_len = C.c_uint64(0)
+        check(_ffi.otters_query_wait(self._store.ctx.handle, self.ticket, idx.ctypes.data_as(_ffi.c_u64p),
+                                     score.ctypes.data_as(_ffi.c_f32p), qid.ctypes.data_as(_ffi.c_u32p), cap, C.byref(out_len), None))
+        m = min(out_len.value, self._cap)
+        return idx[:m], score[:m], qid[:m]

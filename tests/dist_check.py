@@ -78,7 +78,7 @@ for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob
         # fused exchange over peer memory (select + NVLink stores + flags + merge in one kernel), when the box maps it
         if shv.enable_peer_exchange():
             fused_ok = True
-            for rep in range(3):  # both parities of the double-buffered areas
+            for rep in range(5):  # wraps around the OTTERS_EXCHANGE_SLOTS-deep areas
                 got, _ = shv.search_fused(vq, None, k)
                 got = tuple(a.copy() for a in got)  # views of buffers the next call overwrites
                 assert_same_results(got, want, f"fused vec {metric.name} nq={nq} rank {rank} rep {rep}")
@@ -88,6 +88,33 @@ for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob
             tot = torch.tensor([st.evaluated_chunks, st.vectors_compared, st.total_chunks], dtype=torch.int64, device="cuda")
             dist.all_reduce(tot)
             assert tot.tolist() == [ostats["evaluated_chunks"], ostats["vectors_compared"], ostats["total_chunks"]], (tot.tolist(), ostats)
+            # two queries in flight per rank (otters_query_submit / otters_query_wait), exchange attached: the areas are
+            # OTTERS_EXCHANGE_SLOTS deep, ranks drift apart by up to two queries
+            if nq == 1:
+                qs8 = ora.synth_fill(0, 9, dim, 9)
+                vqs = []
+                for i in range(9):
+                    v8 = _ffi.VecQuery()
+                    v8.queries = qs8[i:i + 1].ctypes.data_as(_ffi.c_f32p)
+                    v8.nq, v8.dim, v8.metric, v8.take_type, v8.k = 1, dim, int(metric), int(tt), k
+                    vqs.append(v8)
+                for sh, flt, is_meta in ((shv, None, False), (shardc, fp, True)):
+                    tickets = [sh.submit(vqs[0], flt)]
+                    for i in range(9):
+                        if i + 1 < 9:
+                            tickets.append(sh.submit(vqs[i + 1], flt))
+                        got, st = sh.wait(tickets[i], k, want_stats=is_meta)
+                        got = tuple(a.copy() for a in got)
+                        if is_meta:
+                            oi8, os8, oq8, ostats8 = ost.query(qs8[i:i + 1], metric, tt, k, None, ofp)
+                            assert_same_results(got, (oi8, os8, oq8), f"pipelined meta {metric.name} query {i} rank {rank}")
+                            tot = torch.tensor([st.evaluated_chunks, st.vectors_compared], dtype=torch.int64, device="cuda")
+                            dist.all_reduce(tot)
+                            assert tot.tolist() == [ostats8["evaluated_chunks"], ostats8["vectors_compared"]], (tot.tolist(), ostats8)
+                        else:
+                            assert_same_results(got, ora.vecstore_query(vectors, qs8[i:i + 1], metric, tt, k),
+                                                f"pipelined vec {metric.name} query {i} rank {rank}")
+                pipelined_ok = True
             # a rank whose shard is empty still takes part
             vse = ob.VecStore(dim, ctx)
             if rank == 0:
@@ -100,5 +127,5 @@ for metric, tt in ((ob.Metric.Cosine, ob.TakeType.Max), (ob.Metric.Euclidean, ob
             print("peer exchange unavailable:", shv.peer_error)
 dist.barrier()
 if rank == 0:
-    print("DIST_CHECK_OK", "fused_exchange=%s" % ("fused_ok" in globals()))
+    print("DIST_CHECK_OK", "fused_exchange=%s" % ("fused_ok" in globals()), "pipelined=%s" % ("pipelined_ok" in globals()))
 dist.destroy_process_group()
