@@ -384,7 +384,7 @@ def run_ours(args, wl):
     if args.tuning:
         w, s, kc, cps, ur = (int(x) for x in args.tuning.split(","))
         tune = dict(warps_per_cta=w, slots_per_warp=s, kc_floats=kc, ctas_per_sm=cps, unit_rows=ur)
-    for name in ("scan_mode", "planners", "batch_passes", "separate_select", "lazy_prune"):
+    for name in ("scan_mode", "planners", "batch_passes", "separate_select", "lazy_prune", "disable_fused_predicate"):
         if getattr(args, name):
             tune[name] = getattr(args, name)
     ctx.set_tuning(**tune)
@@ -665,6 +665,8 @@ def main():
     ap.add_argument("--planners", type=int, default=0, help="planner warps per CTA (planner front-end; 0 = auto)")
     ap.add_argument("--separate-select", dest="separate_select", type=int, default=0, help="1: K3 as its own kernel (A/B)")
     ap.add_argument("--lazy-prune", dest="lazy_prune", type=int, default=0, help="1: chunk pruning inside the scan kernel (A/B)")
+    ap.add_argument("--unfused-predicate", dest="disable_fused_predicate", type=int, default=0,
+                    help="1: row predicate in its own kernel (K0b row bitmask) instead of inside the scan (A/B)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"], help="N > 1: fused peer-memory exchange when available, or force NCCL")
     args = ap.parse_args()
     wl = Workload(args.workload, args.rows)

@@ -34,6 +34,8 @@ WORKLOADS: Dict[str, dict] = {
                desc="VecStore 1Mx768 fp32 Dot, batch of 1024 queries, top-100 (one merged list; tcgen05 tf32 selection + exact re-scoring)"),
     "c3": dict(rows=10_000_000, dim=128, chunk=1024, metric="Cosine", k=100, meta="pit",
                desc="MetaStore 10Mx128 Cosine top-100, chunk 1024, meta_filter price.gt & item.eq & ts.gte"),
+    "c3u": dict(rows=10_000_000, dim=128, chunk=0, metric="Cosine", k=100, meta=None,
+                desc="DIAGNOSTIC (not a BASELINE config): VecStore 10Mx128 Cosine top-100, C3's rows without its filter"),
     "c4": dict(rows=10_000_000, dim=768, chunk=0, metric="Euclidean", k=100, meta=None, desc="VecStore 10Mx768 fp32 L2 top-100"),
     "c5": dict(rows=5_000_000, dim=1536, chunk=1024, metric="Cosine", k=1000, meta="mixed", vec_filter=(0.8, CMP_GT), planted=5000,
                desc="MetaStore 5Mx1536 Cosine vec_filter(0.8,Gt) take(1000), chunk 1024, meta_filter qty.gte & (price.lt | item.eq) "

@@ -95,7 +95,8 @@ typedef struct {
     uint32_t kc_floats;    /* columns staged per slot (multiple of 8) */
     uint32_t ctas_per_sm;
     uint32_t unit_rows;    /* 32, 64 or 128 rows per dynamically scheduled work unit */
-    uint32_t disable_fused_predicate; /* 1: evaluate the row predicate in its own kernel instead of inside the scan */
+    uint32_t disable_fused_predicate; /* row predicate: 0 = automatic and 1 = its own kernel (K0b: surviving-row bitmask, then the
+                                         scan reads mask words), 2 = evaluated per work unit inside the scan kernel */
     uint32_t batch_mode;   /* query batches: 0 = automatic, 1 = always the tensor-core kernel (when k <= 1024), 2 = never */
     uint32_t batch_cta_group; /* tensor-core kernel: 0 = automatic (single CTAs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2) */
     uint32_t scan_mode;    /* K1 front-end: 0 = automatic, 1 = autonomous warps (scan.cu), 2 = planner + worker warps (scan_planner.cu) */

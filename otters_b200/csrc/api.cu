@@ -95,6 +95,7 @@ struct otters_ctx {
     bool own_stream = false;
     int sm_count = 148;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
     otters_scan_tuning tuning{};
     otters_last_work last{};
 
@@ -181,6 +182,7 @@ struct otters_ctx {
 
     // lanes: queries in flight (otters_query_submit / otters_query_wait).  lane[0] is this context itself, lane[1..] are
     // child contexts with their own stream and scratch, created on first use.
+    bool pipelined = false;             // the query being planned was submitted on a lane (otters_query_submit)
     otters_ctx* parent = nullptr;
     otters_ctx* lane[kMaxLanes] = {};
     uint32_t next_lane = 0;
@@ -488,7 +490,13 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     // planner warps per CTA: a filtered unit costs a planner one memory round trip (~2 µs under load); narrow rows are
     // consumed faster, so they need more planners to stay ahead of the workers
     if (planner) pl.planners = t.planners ? std::min<uint32_t>(t.planners, 4) : (filter_bytes ? (dim_pad <= 256 ? 4 : 2) : 1);
-    const size_t budget = c->smem_optin > 2048 ? c->smem_optin - 1024 : 0;
+    static const size_t margin = getenv("OTTERS_SMEM_MARGIN") ? (size_t)atoi(getenv("OTTERS_SMEM_MARGIN")) : 128;
+    // shared memory of one CTA: the opt-in maximum, or an equal share of the SM (minus the 1 KB the system reserves per
+    // CTA) when several CTAs are to be co-resident per SM (ctas_per_sm)
+    const uint32_t cps = t.ctas_per_sm ? std::min<uint32_t>(t.ctas_per_sm, 4) : 1;
+    size_t cta_smem = c->smem_optin;
+    if (cps > 1) cta_smem = std::min<size_t>(cta_smem, c->smem_per_sm / cps - 1024);
+    const size_t budget = cta_smem > 2048 ? cta_smem - margin : 0;  // (the kernels' static shared memory is < 64 bytes)
     if (pl.off_warps + 4096 > budget) return fail(OTTERS_ERR_UNSUPPORTED, "vector dimension too large for the scan kernel");
 
     uint32_t dim8 = (uint32_t)round_up(dim_pad, 8);
@@ -514,7 +522,7 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
         *o_inv = o;
         o += S * kTileRows * 4;
         *o_list = o;
-        o += kMaxUnitRows;
+        o += 2 * kMaxUnitRows;  // two row lists: the next unit's is built while the current one streams
         o = (uint32_t)round_up(o, 128);
         *o_slots = o;
         o += S * slot_bytes;
@@ -536,14 +544,16 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     pl.slots = S;
     pl.warp_bytes = warp_bytes_for(S, &pl.off_w_rows, &pl.off_w_info, &pl.off_w_inv, &pl.off_w_list, &pl.off_w_slots);
 
-    uint32_t ctas_per_sm = t.ctas_per_sm ? t.ctas_per_sm : 1;
+    uint32_t ctas_per_sm = cps;
     uint32_t grid = (uint32_t)c->sm_count * ctas_per_sm;
     uint32_t unit_rows = t.unit_rows ? t.unit_rows : kMaxUnitRows;
     if (unit_rows != 32 && unit_rows != 64 && unit_rows != 128) unit_rows = kMaxUnitRows;
     // small stores (e.g. one shard of a row-sharded search) need finer units, or the last units of the dynamic schedule
     // leave most warps idle: measured on a 1.25M x 768 shard, 32-row units scan in 0.293 ms against 0.330 ms for 128-row
     // units (profiles/r1_unit_rows_shard.log); large stores keep 128-row units (fewer unit boundaries)
-    if (!t.unit_rows) {
+    if (!t.unit_rows && !c->pipelined) {
+        // (queries submitted on the lanes keep the large units: the tail of one query's scan is filled by the head of the
+        // next one's, so fewer unit boundaries win — 1.25M x 768 shard: 3598 vs 3478 queries/s, profiles/r2_shard_units.txt)
         // planner front-end: a unit is spread over all warps of its CTA, so only the per-CTA unit count matters
         const uint64_t want = planner ? (uint64_t)grid * 16 : (uint64_t)grid * W * 16;
         while (unit_rows > 32 && n_rows / unit_rows < want) unit_rows >>= 1;
@@ -938,6 +948,12 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.cta_counts = c->d_cta_counts;
     sp.rows_scored = c->d_rows_scored;
     sp.g_tau = reinterpret_cast<unsigned long long*>(c->d_ctrl + 96);  // zeroed with the control block
+    {
+        static const int pred_seq = getenv("OTTERS_PRED_SEQ") ? atoi(getenv("OTTERS_PRED_SEQ")) : 1;
+        static const int no_prefetch = getenv("OTTERS_NO_PREFETCH") ? atoi(getenv("OTTERS_NO_PREFETCH")) : 0;
+        sp.pred_seq = pred_seq;
+        sp.no_prefetch = no_prefetch;
+    }
 
     uint32_t cur = 0;
     if (fused) {
@@ -1141,6 +1157,7 @@ static int ctx_create_impl(int device, void* cuda_stream, otters_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (cuda_stream) {
         c->stream = (cudaStream_t)cuda_stream;
     } else {
@@ -1811,6 +1828,10 @@ static int lower_filter(otters_metastore* ms, const otters_filter* f, std::vecto
         DevLeaf d{};
         d.col = in.col;
         d.op = in.op;
+        {   // Eq, Neq, Lt, Lte, Gt, Gte over the states {>, <, ==, unordered}
+            static const uint32_t kTruth[6] = {0x4u, 0xBu, 0x2u, 0x6u, 0x1u, 0x5u};
+            d.tt = kTruth[in.op];
+        }
         d.values = mc.d_values;
         d.null_words = mc.d_nulls;
         d.zmin = mc.d_zmin;
@@ -1988,8 +2009,12 @@ static int meta_enqueue(otters_ctx* c, otters_metastore* ms, const otters_vec_qu
     // the batched tensor-core kernel gates rows with a precomputed mask (K0b) instead of the fused predicate
     const bool batched = scan && !c->ex_active && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
     const uint32_t n_leaves = filter && filter->clause_offsets ? filter->clause_offsets[filter->n_clauses] : 0;
-    // the scan kernel evaluates the row predicate itself (fused K0b) unless the CNF is too large for its shared memory
-    const bool fuse = scan && filter && !batched && !c->tuning.disable_fused_predicate &&
+    // Row predicate: by default its own kernel (K0b writes the surviving-row bitmask at HBM bandwidth, the scan's producer then
+    // reads one mask word per 32 rows); the scan kernel can also evaluate the CNF itself per work unit (fused K0b:
+    // disable_fused_predicate == 2, or lazy_prune) — one launch less, but every unit then pays dependent metadata round trips
+    // inside the streaming warps: measured 3-6 % slower on every filtered workload (profiles/r2_predicate_ab.txt)
+    const bool want_fused = c->tuning.disable_fused_predicate == 2 || c->tuning.lazy_prune;
+    const bool fuse = scan && filter && !batched && want_fused &&
                       FusedFilter::smem_bytes_for(n_leaves, filter->n_clauses) <= kMaxFusedFilterBytes;
     // ... and can prune the chunks itself as well (lazy K0, opt-in: measured slower than the stand-alone kernel, whose 9-12 us
     // hide under the other lane's scan when two queries are in flight)
@@ -2395,7 +2420,9 @@ extern "C" int otters_query_submit(otters_vecstore* vs, otters_metastore* ms, co
     // a ticket of this lane that was never waited for is abandoned here: its result buffers are reused
     c->pend.active = false;
     Pending pd;
-    int rc = enqueue_any(c, vs, ms, q, filter, map_in, ex, seq, true, true, &pd);
+    c->pipelined = true;
+    int rc = enqueue_any(c, vs, ms, q, filter, map_in, ex, seq, true, false, &pd);
+    c->pipelined = false;
     if (rc) return rc;
     parent->next_lane += 1;
     parent->tickets += 1;

@@ -163,6 +163,7 @@ struct ScanParams {
     uint32_t emit_cap;
     // instrumentation
     unsigned long long* rows_scored;
+    uint32_t pred_seq, no_prefetch;  // experiment switches (OTTERS_PRED_SEQ / OTTERS_NO_PREFETCH)
     // fused selection: the last CTA to publish its list (ticket from done_counter) runs K3 itself — one launch per query
     uint32_t fuse_select;
     uint32_t* done_counter;
@@ -283,6 +284,9 @@ struct DevLeaf {         // one lowered leaf, self-contained: carries the device
     int32_t op;
     int32_t exec;        // LeafExec
     int32_t code_valid;  // LEAF_STR: literal present in the dictionary
+    uint32_t tt;         // 4-bit truth table of the operator over the compare states (predicate.cuh): bit 0 value > literal,
+                         // 1 value < literal, 2 equal, 3 unordered
+    uint32_t pad0;
     int64_t i64;
     double f64;
     float f32;

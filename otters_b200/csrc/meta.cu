@@ -122,9 +122,25 @@ __global__ void count_all_kernel(const __grid_constant__ MetaKernelParams p) {
     }
 }
 
-// K0b: one thread per row, one 32-bit mask word per warp.  The lowered filter is staged in shared memory
-// and every leaf of a surviving row is evaluated unconditionally, so the column loads of all leaves are
-// in flight together instead of forming a dependent chain.
+// K0b: the surviving-row bitmask.  A warp owns groups of 128 rows (four mask words); a lane owns row `lane` of each of the
+// four words, so every load is coalesced (32 consecutive values; warp-uniform null and chunk words), the four rows' loads of
+// a leaf are in flight together, and the type / operator dispatch is paid once per leaf (rows_pass_x4 + truth tables).
+// Round 1's form (one row per lane, a switch per row and leaf) was bound by instruction issue and by one dependent round trip
+// per 32 rows: 94 us for the 10M-row target.  The chunk bits of the NEXT group are loaded while the current one is evaluated.
+// Rows of pruned chunks are never read.
+__device__ __forceinline__ uint32_t chunk_live4(const MetaKernelParams& p, uint32_t r0, uint32_t lane) {
+    uint32_t live = 0;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u) {
+        const uint32_t row = r0 + 32u * u + lane;
+        if (row < p.n_rows) {
+            const uint32_t ch = row / p.chunk_size;
+            live |= ((__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u) << u;
+        }
+    }
+    return live;
+}
+
 __global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ MetaKernelParams p, uint32_t n_leaves, int use_smem) {
     extern __shared__ __align__(16) uint8_t fsm[];
     const DevLeaf* leaves = p.leaves;
@@ -141,18 +157,22 @@ __global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ Me
         clause_off = so;
     }
     const uint32_t n_words = (p.n_rows + 31) >> 5;
+    const uint32_t n_groups = (p.n_rows + 127) >> 7;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps_total) {
-        const uint32_t row = (w << 5) + lane;
-        bool keep = false;
-        if (row < p.n_rows) {
-            const uint32_t ch = row / p.chunk_size;
-            keep = (p.chunk_keep[ch >> 5] >> (ch & 31)) & 1u;
-            if (keep) keep = row_passes(leaves, clause_off, p.n_clauses, row);
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t live = g < n_groups ? chunk_live4(p, g << 7, lane) : 0;
+    for (; g < n_groups; g += warps_total) {
+        const uint32_t g_next = g + warps_total;
+        const uint32_t live_next = g_next < n_groups ? chunk_live4(p, g_next << 7, lane) : 0;  // in flight during the evaluation
+        const uint32_t pass = __any_sync(0xFFFFFFFFu, live != 0) ? rows_pass_x4(leaves, clause_off, p.n_clauses, g << 7, lane, live) : 0u;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (pass >> u) & 1u);
+            const uint32_t w = (g << 2) + u;
+            if (lane == 0 && w < n_words) p.row_mask[w] = m;
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-        if (lane == 0) p.row_mask[w] = m;
+        live = live_next;
     }
 }
 
@@ -170,8 +190,8 @@ int launch_prune(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s) {
 
 int launch_rowmask(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s) {
     if (p.n_rows == 0) return OTTERS_OK;
-    uint32_t n_words = (p.n_rows + 31) >> 5;
-    uint32_t blocks = (n_words + 7) / 8;  // 8 warps per block
+    uint32_t n_groups = (p.n_rows + 127) >> 7;
+    uint32_t blocks = (n_groups + 7) / 8;  // 8 warps per block, one 128-row group per warp and iteration
     if (blocks > 148 * 8) blocks = 148 * 8;
     size_t smem = (size_t)n_leaves * sizeof(DevLeaf) + ((size_t)p.n_clauses + 1) * 4;
     int use_smem = smem <= 40 * 1024;

@@ -9,8 +9,20 @@
 
 namespace otters {
 
+// A compare is reduced to one of four STATES of (value, literal) — 0: value > literal, 1: value < literal, 2: equal,
+// 3: unordered (a NaN on either side) — and the leaf carries a 4-bit truth table indexed by the state (DevLeaf::tt, set when
+// the filter is lowered: Eq 0100, Neq 1011, Lt 0010, Lte 0110, Gt 0001, Gte 0101).  That is a handful of straight-line
+// instructions per (row, leaf) where a switch over the operator cost ~60 with its branches: the predicate kernels were
+// bound by instruction issue, not by memory.  IEEE semantics are kept: NaN satisfies only Neq (src/type_utils.rs:306-444).
 template <typename T>
-__device__ __forceinline__ bool row_sat(int op, T v, T t) {
+__device__ __forceinline__ uint32_t cmp_state(T v, T t) {
+    const uint32_t lt = v < t ? 1u : 0u, eq = v == t ? 2u : 0u, gt = v > t ? 4u : 0u;
+    return (lt | eq | gt) ? (lt | eq) : 3u;  // integers are never unordered
+}
+__device__ __forceinline__ bool tt_sat(uint32_t tt, uint32_t state) { return ((tt >> state) & 1u) != 0; }
+
+template <typename T>
+__device__ __forceinline__ bool row_sat(int op, T v, T t) {  // reference form, kept for the chunk rules' documentation
     switch (op) {
     case OTTERS_OP_EQ: return v == t;
     case OTTERS_OP_NEQ: return v != t;
@@ -21,20 +33,23 @@ __device__ __forceinline__ bool row_sat(int op, T v, T t) {
     }
 }
 
+// state of the 64-bit raw value `raw` of a row under leaf lf (dictionary strings: code equality, src/meta_compute.rs:291-318)
+__device__ __forceinline__ uint32_t leaf_state_raw(const DevLeaf& lf, uint64_t raw) {
+    switch (lf.exec) {
+    case LEAF_I32: return cmp_state<int32_t>((int32_t)(uint32_t)raw, lf.i32);
+    case LEAF_I64: return cmp_state<int64_t>((int64_t)raw, lf.i64);
+    case LEAF_F32: return cmp_state<float>(__uint_as_float((uint32_t)raw), lf.f32);
+    case LEAF_F64: return cmp_state<double>(__longlong_as_double((long long)raw), lf.f64);
+    default: return (lf.code_valid && (uint32_t)raw == lf.code) ? 2u : 0u;
+    }
+}
+
 __device__ __forceinline__ bool row_leaf_sat(const DevLeaf& lf, uint32_t row) {
     const bool is_null = lf.null_words && ((lf.null_words[row >> 5] >> (row & 31)) & 1u);
-    bool sat;
-    switch (lf.exec) {
-    case LEAF_I32: sat = row_sat<int32_t>(lf.op, ((const int32_t*)lf.values)[row], lf.i32); break;
-    case LEAF_I64: sat = row_sat<int64_t>(lf.op, ((const int64_t*)lf.values)[row], lf.i64); break;
-    case LEAF_F32: sat = row_sat<float>(lf.op, ((const float*)lf.values)[row], lf.f32); break;
-    case LEAF_F64: sat = row_sat<double>(lf.op, ((const double*)lf.values)[row], lf.f64); break;
-    default: {  // dictionary-coded string equality (src/meta_compute.rs:291-318)
-        const bool eq = lf.code_valid && ((const uint32_t*)lf.values)[row] == lf.code;
-        sat = lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
-    }
-    }
-    return sat && !is_null;
+    const bool wide = lf.exec == LEAF_I64 || lf.exec == LEAF_F64;
+    const uint64_t raw = wide ? reinterpret_cast<const unsigned long long*>(lf.values)[row]
+                              : (uint64_t)reinterpret_cast<const uint32_t*>(lf.values)[row];
+    return tt_sat(lf.tt, leaf_state_raw(lf, raw)) && !is_null;
 }
 
 // CNF over one row: AND over clauses of OR over leaves; every leaf is evaluated so that its loads overlap
@@ -122,18 +137,7 @@ __device__ __forceinline__ bool chunk_passes(const DevLeaf* leaves, const uint32
 // a unit's metadata arrives in one memory round trip instead of one per leaf.  Same semantics as row_passes().
 constexpr uint32_t kMlpLeaves = 6;
 
-__device__ __forceinline__ bool leaf_sat_raw(const DevLeaf& lf, uint64_t raw) {
-    switch (lf.exec) {
-    case LEAF_I32: return row_sat<int32_t>(lf.op, (int32_t)(uint32_t)raw, lf.i32);
-    case LEAF_I64: return row_sat<int64_t>(lf.op, (int64_t)raw, lf.i64);
-    case LEAF_F32: return row_sat<float>(lf.op, __uint_as_float((uint32_t)raw), lf.f32);
-    case LEAF_F64: return row_sat<double>(lf.op, __longlong_as_double((long long)raw), lf.f64);
-    default: {
-        const bool eq = lf.code_valid && (uint32_t)raw == lf.code;
-        return lf.op == OTTERS_OP_EQ ? eq : (lf.op == OTTERS_OP_NEQ ? !eq : false);
-    }
-    }
-}
+__device__ __forceinline__ bool leaf_sat_raw(const DevLeaf& lf, uint64_t raw) { return tt_sat(lf.tt, leaf_state_raw(lf, raw)); }
 
 __device__ __forceinline__ uint32_t rows_pass_mlp(const DevLeaf* leaves, const uint32_t* clause_off, uint32_t n_clauses,
                                                   uint32_t n_leaves, uint32_t r, uint32_t bits, uint32_t rpl) {
@@ -183,6 +187,54 @@ __device__ __forceinline__ uint32_t rows_pass_mlp(const DevLeaf* leaves, const u
     }
     keep &= any;  // the clause the last leaf belongs to
     for (++ci; ci < n_clauses; ++ci) keep = 0;  // trailing clauses without leaves can never be satisfied
+    return keep;
+}
+
+
+// --- leaf-major form for the row-mask kernel (meta.cu) -------------------------------------------------------------
+// A lane owns row `lane` of four consecutive 32-row words starting at row `r0` (a multiple of 128): for every leaf the
+// four values are loaded together (coalesced: 32 lanes read 32 consecutive values; the null words are warp-uniform), the
+// type dispatch happens once per leaf, and the four rows' clause state advances side by side.  live = 4-bit mask of the
+// lane's rows that are still candidates (chunk kept, inside the store); returns the 4-bit mask of rows passing the CNF.
+__device__ __forceinline__ uint32_t rows_pass_x4(const DevLeaf* leaves, const uint32_t* clause_off, uint32_t n_clauses, uint32_t r0,
+                                                 uint32_t lane, uint32_t live) {
+    uint32_t keep = live;
+    for (uint32_t ci = 0; ci < n_clauses; ++ci) {
+        uint32_t any = 0;
+        for (uint32_t li = clause_off[ci]; li < clause_off[ci + 1]; ++li) {
+            const DevLeaf& lf = leaves[li];
+            const bool wide = lf.exec == LEAF_I64 || lf.exec == LEAF_F64;
+            uint64_t raw[4];
+            uint32_t nul[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t row = r0 + 32u * u + lane;
+                raw[u] = 0;
+                nul[u] = 0;
+                if ((live >> u) & 1u) {
+                    raw[u] = wide ? __ldg(reinterpret_cast<const unsigned long long*>(lf.values) + row)
+                                  : (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(lf.values) + row);
+                    if (lf.null_words) nul[u] = __ldg(lf.null_words + (row >> 5));
+                }
+            }
+            uint32_t m = 0;
+            switch (lf.exec) {  // one dispatch per leaf, four rows each
+#define OTTERS_X4(expr)                                                          \
+    _Pragma("unroll") for (uint32_t u = 0; u < 4; ++u) {                        \
+        const uint32_t st = (expr);                                              \
+        m |= (((lf.tt >> st) & 1u) & ~(nul[u] >> lane) & 1u) << u;               \
+    }
+            case LEAF_I32: OTTERS_X4(cmp_state<int32_t>((int32_t)(uint32_t)raw[u], lf.i32)) break;
+            case LEAF_I64: OTTERS_X4(cmp_state<int64_t>((int64_t)raw[u], lf.i64)) break;
+            case LEAF_F32: OTTERS_X4(cmp_state<float>(__uint_as_float((uint32_t)raw[u]), lf.f32)) break;
+            case LEAF_F64: OTTERS_X4(cmp_state<double>(__longlong_as_double((long long)raw[u]), lf.f64)) break;
+            default: OTTERS_X4((lf.code_valid && (uint32_t)raw[u] == lf.code) ? 2u : 0u) break;
+#undef OTTERS_X4
+            }
+            any |= m;
+        }
+        keep &= any;
+    }
     return keep;
 }
 

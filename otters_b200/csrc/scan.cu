@@ -88,103 +88,141 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     unsigned long long scored = 0;
     unsigned long long st_chunks = 0, st_vecs = 0;  // lazy pruning: chunks kept / rows of kept chunks x queries (per lane)
 
+    // The row list of the NEXT unit is built while a tile of the current unit is in flight: claiming the unit, reading its
+    // chunk bits and evaluating the row predicate cost two to three dependent memory round trips, which used to sit between
+    // the last tile of one unit and the first tile of the next with nothing in flight for this warp (32-row units of a small
+    // shard: ~15 % of the kernel; narrow filtered rows: ~35 %).  Two row-list buffers alternate.
+    uint32_t nlist_n = 0, nunit_row0 = 0, cur_buf = 0;
+    bool nvalid = false, claim_done = false;
+    auto prepare = [&]() {
+        uint8_t* nlist = rowlist + (cur_buf ^ 1u) * kMaxUnitRows;
+        while (!nvalid) {
+            uint32_t u = __shfl_sync(FULL, u_pref, 0);
+            if (u >= p.n_units) {
+                claim_done = true;
+                return;
+            }
+            if (lane == 0) {
+                // adopt what the other CTAs have found so far (value read one unit ago: no extra round trip)
+                if (!EMIT_ALL && g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
+                u_pref = atomicAdd(p.unit_counter, 1u);
+                if (!EMIT_ALL && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
+            }
+            // guided schedule: the first n_big units are unit_rows long, the rest (the tail of the store, claimed last)
+            // unit_small long, so that the warps run out of work within one SMALL unit of each other
+            const bool big = u < p.n_big;
+            const uint32_t urows = big ? p.unit_rows : p.unit_small;
+            uint32_t row0 = big ? u * p.unit_rows : p.n_big * p.unit_rows + (u - p.n_big) * p.unit_small;
+            const uint32_t rpl = urows >= 32 ? urows >> 5 : 1;  // rows per lane when building the row list (1, 2 or 4)
+            uint32_t r = row0 + rpl * lane;  // this lane's first row; its rpl rows share one mask word
+            uint32_t bits = (1u << rpl) - 1u;
+            if (rpl * lane >= urows) bits = 0;  // 16-row units: the upper half of the warp has no row
+            if (p.row_mask) {
+                uint32_t w = (r >> 5) < p.row_mask_words ? __ldg(p.row_mask + (r >> 5)) : 0xFFFFFFFFu;
+                bits &= w >> (r & 31);
+            }
+            if (r >= p.n_rows) bits = 0;
+            else if (p.n_rows - r < rpl) bits &= (1u << (p.n_rows - r)) - 1u;
+            if (p.flt_leaves && r < p.n_rows) {
+                uint32_t out = 0;
+                if (p.chunk_keep) {
+                    // fused K0b: chunk bits from the prune kernel, then the CNF over the rows' metadata with EVERY value and
+                    // null-word load of the lane's (up to 4) rows in flight together (rows_pass_mlp): evaluated row after row,
+                    // the four rows cost four dependent HBM round trips per unit — a third of the kernel on narrow rows
+                    uint32_t km = 0, ch_prev = 0xFFFFFFFFu, kp = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        if (j < rpl && r + j < p.n_rows) {
+                            const uint32_t ch = (r + j) / p.chunk_size;
+                            if (ch != ch_prev) {
+                                kp = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
+                                ch_prev = ch;
+                            }
+                            km |= kp << j;
+                        }
+                    }
+                    if (p.pred_seq) {
+                        const uint32_t live = bits & km;
+                        for (uint32_t j = 0; j < rpl; ++j)
+                            if (((live >> j) & 1u) && row_passes(f_leaves, f_off, p.flt_n_clauses, r + j)) out |= 1u << j;
+                    } else {
+                        out = rows_pass_mlp(f_leaves, f_off, p.flt_n_clauses, p.flt_n_leaves, r, bits & km, rpl);
+                    }
+                } else if (rpl * lane < urows) {
+                    // fused K0 + K0b (lazy pruning): the zonemap / Bloom rules of the chunk(s) this lane's rows fall into are
+                    // evaluated right here (uniform addresses across the warp for the usual chunk >= unit case: broadcast
+                    // loads that hit L2), and the lane holding a chunk's FIRST row accounts the chunk in the statistics —
+                    // every row of the store belongs to exactly one lane of one unit, so every chunk is counted once
+                    // (src/meta.rs:666-669, src/meta_compute.rs:166)
+                    uint32_t km = 0, ch_prev = 0xFFFFFFFFu;
+                    bool kp = false;
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        if (j < rpl && r + j < p.n_rows) {
+                            const uint32_t row = r + j;
+                            const uint32_t ch = row / p.chunk_size;
+                            if (ch != ch_prev) {
+                                kp = chunk_passes(f_leaves, f_off, p.flt_n_clauses, ch);
+                                ch_prev = ch;
+                            }
+                            if (kp) {
+                                km |= 1u << j;
+                                if ((uint64_t)row == (uint64_t)ch * p.chunk_size) {  // first row of its chunk
+                                    const uint64_t ch_end = (uint64_t)(ch + 1) * p.chunk_size;
+                                    st_chunks += 1ull;
+                                    st_vecs += (unsigned long long)(ch_end <= p.n_rows ? p.chunk_size : p.n_rows - row) * p.nq_stats;
+                                }
+                            }
+                        }
+                    }
+                    out = rows_pass_mlp(f_leaves, f_off, p.flt_n_clauses, p.flt_n_leaves, r, bits & km, rpl);
+                }
+                bits = out;
+            }
+            uint32_t c = __popc(bits);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            uint32_t pos = incl - c;
+            __syncwarp();
+            while (bits) {
+                int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                nlist[pos++] = (uint8_t)(rpl * lane + b);
+            }
+            const uint32_t n_keep = __shfl_sync(FULL, incl, 31);
+            __syncwarp();
+            if (n_keep) {
+                nlist_n = n_keep;
+                nunit_row0 = row0;
+                nvalid = true;
+            }
+        }
+    };
+
     auto issue = [&]() {
         if (prod_done) return;
         if (kc_i == 0) {
-            while (list_pos >= list_n) {
-                uint32_t u = __shfl_sync(FULL, u_pref, 0);
-                if (u >= p.n_units) {
+            if (list_pos >= list_n) {
+                if (!nvalid && !claim_done) prepare();  // nothing prefetched yet (kernel start, or only empty units so far)
+                if (!nvalid) {
                     prod_done = true;
                     return;
                 }
-                if (lane == 0) {
-                    // adopt what the other CTAs have found so far (value read one unit ago: no extra round trip)
-                    if (!EMIT_ALL && g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
-                    u_pref = atomicAdd(p.unit_counter, 1u);
-                    if (!EMIT_ALL && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
-                }
-                // guided schedule: the first n_big units are unit_rows long, the rest (the tail of the store, claimed last)
-                // unit_small long, so that the warps run out of work within one SMALL unit of each other
-                const bool big = u < p.n_big;
-                const uint32_t urows = big ? p.unit_rows : p.unit_small;
-                uint32_t row0 = big ? u * p.unit_rows : p.n_big * p.unit_rows + (u - p.n_big) * p.unit_small;
-                const uint32_t rpl = urows >= 32 ? urows >> 5 : 1;  // rows per lane when building the row list (1, 2 or 4)
-                uint32_t r = row0 + rpl * lane;  // this lane's first row; its rpl rows share one mask word
-                uint32_t bits = (1u << rpl) - 1u;
-                if (rpl * lane >= urows) bits = 0;  // 16-row units: the upper half of the warp has no row
-                if (p.row_mask) {
-                    uint32_t w = (r >> 5) < p.row_mask_words ? __ldg(p.row_mask + (r >> 5)) : 0xFFFFFFFFu;
-                    bits &= w >> (r & 31);
-                }
-                if (r >= p.n_rows) bits = 0;
-                else if (p.n_rows - r < rpl) bits &= (1u << (p.n_rows - r)) - 1u;
-                if (p.flt_leaves && r < p.n_rows) {
-                    uint32_t out = 0;
-                    if (p.chunk_keep) {
-                        // fused K0b: chunk bit from the prune kernel, then the CNF over the row's metadata
-                        uint32_t ch = r / p.chunk_size;
-                        uint64_t ch_end = (uint64_t)(ch + 1) * p.chunk_size;  // first row of the next chunk
-                        uint32_t keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
-                        for (uint32_t j = 0; j < rpl; ++j) {
-                            const uint32_t row = r + j;
-                            if (row >= p.n_rows) break;
-                            if ((uint64_t)row >= ch_end) {  // crossed into the next chunk
-                                ch = row / p.chunk_size;
-                                ch_end = (uint64_t)(ch + 1) * p.chunk_size;
-                                keep_ch = (__ldg(p.chunk_keep + (ch >> 5)) >> (ch & 31)) & 1u;
-                            }
-                            if (((bits >> j) & 1u) && keep_ch && row_passes(f_leaves, f_off, p.flt_n_clauses, row)) out |= 1u << j;
-                        }
-                    } else if (rpl * lane < urows) {
-                        // fused K0 + K0b (lazy pruning): the zonemap / Bloom rules of the chunk(s) this lane's rows fall into are
-                        // evaluated right here (uniform addresses across the warp for the usual chunk >= unit case: broadcast
-                        // loads that hit L2), and the lane holding a chunk's FIRST row accounts the chunk in the statistics —
-                        // every row of the store belongs to exactly one lane of one unit, so every chunk is counted once
-                        // (src/meta.rs:666-669, src/meta_compute.rs:166)
-                        uint32_t ch = 0;
-                        uint64_t ch_end = 0;
-                        bool keep_ch = false;
-                        for (uint32_t j = 0; j < rpl; ++j) {
-                            const uint32_t row = r + j;
-                            if (row >= p.n_rows) break;
-                            if ((uint64_t)row >= ch_end) {
-                                ch = row / p.chunk_size;
-                                ch_end = (uint64_t)(ch + 1) * p.chunk_size;
-                                keep_ch = chunk_passes(f_leaves, f_off, p.flt_n_clauses, ch);
-                            }
-                            if (keep_ch && (uint64_t)row + p.chunk_size == ch_end) {  // first row of its chunk
-                                st_chunks += 1ull;
-                                st_vecs += (unsigned long long)(ch_end <= p.n_rows ? p.chunk_size : p.n_rows - row) * p.nq_stats;
-                            }
-                            if (((bits >> j) & 1u) && keep_ch && row_passes(f_leaves, f_off, p.flt_n_clauses, row)) out |= 1u << j;
-                        }
-                    }
-                    bits = out;
-                }
-                uint32_t c = __popc(bits);
-                uint32_t incl = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t t = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                uint32_t pos = incl - c;
-                __syncwarp();
-                while (bits) {
-                    int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    rowlist[pos++] = (uint8_t)(rpl * lane + b);
-                }
-                list_n = __shfl_sync(FULL, incl, 31);
+                cur_buf ^= 1u;
+                list_n = nlist_n;
                 list_pos = 0;
-                unit_row0 = row0;
-                __syncwarp();
+                unit_row0 = nunit_row0;
+                nvalid = false;
             }
             tile_cnt = list_n - list_pos < kTileRows ? list_n - list_pos : kTileRows;
         }
         const uint32_t slot = prod_step % p.slots;
         uint32_t row = 0xFFFFFFFFu;
-        if (lane < (int)tile_cnt) row = unit_row0 + rowlist[list_pos + lane];
+        if (lane < (int)tile_cnt) row = unit_row0 + rowlist[cur_buf * kMaxUnitRows + list_pos + lane];
         if (lane < (int)kTileRows) slot_rows[slot * kTileRows + lane] = row;
         const uint32_t c0 = kc_i * p.kc;
         const uint32_t ncols = p.dim_pad - c0 < p.kc ? p.dim_pad - c0 : p.kc;
@@ -216,6 +254,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     float rinv = 0.f;
 
     for (uint32_t s = 0; s < p.slots; ++s) issue();
+    if (!p.no_prefetch && !nvalid && !claim_done) prepare();
 
     while (cons_step < prod_step) {
         const uint32_t slot = cons_step % p.slots;
@@ -308,6 +347,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         __syncwarp();
         ++cons_step;
         issue();
+        if (!p.no_prefetch && !nvalid && !claim_done) prepare();  // overlaps the copy that was just issued
     }
 
     if (p.rows_scored) {

@@ -34,13 +34,13 @@ def test_fused_prune_and_select_match_standalone_kernels(cs, ctx):
             fp = ora.FilterPack.from_compiled(expr.compile(store.schema()), store.column_index()) if expr is not None else None
             for k in (1, 100, 1024):
                 oi, os_, _, ostats = ost.query(q, ob.Metric.Cosine, ob.TakeType.Max, k, None, fp, ora.CANONICAL)
-                for sel, lazy, mode in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 1, 2), (1, 0, 2)):
-                    ctx.set_tuning(separate_select=sel, lazy_prune=lazy, scan_mode=mode)
+                for sel, lazy, mode, fused in ((0, 0, 0, 0), (1, 0, 0, 0), (0, 1, 0, 0), (1, 1, 0, 0), (0, 1, 2, 0), (1, 0, 2, 0), (0, 0, 1, 2), (0, 0, 2, 2)):
+                    ctx.set_tuning(separate_select=sel, lazy_prune=lazy, scan_mode=mode, disable_fused_predicate=fused)
                     plan = store.query(q[0], ob.Metric.Cosine)
                     if expr is not None:
                         plan = plan.meta_filter(expr)
                     res = plan.take(k).collect()
-                    what = f"cs={cs} filter={fi} k={k} separate_select={sel} lazy_prune={lazy} scan_mode={mode}"
+                    what = f"cs={cs} filter={fi} k={k} separate_select={sel} lazy_prune={lazy} scan_mode={mode} fused={fused}"
                     assert_same_results((res.indices, res.scores), (oi, os_), what)
                     st = store.last_query_stats()
                     for key in STAT_KEYS:
@@ -50,7 +50,8 @@ def test_fused_prune_and_select_match_standalone_kernels(cs, ctx):
 
 
 def test_one_launch_per_query(ctx):
-    """Single queries with k <= 1024: prune kernel + ONE scan kernel (predicate + scan + select); lazy_prune folds the first in."""
+    """Single queries with k <= 1024: prune kernel + row-mask kernel + ONE scan kernel (scan + select); the row predicate
+    (disable_fused_predicate=2) and the chunk pruning (lazy_prune) can be folded into the scan kernel, down to one launch."""
     n, dim, cs = 20000, 64, 256
     vectors = ora.synth_fill(0, n, dim, 84)
     cols = meta_columns(n, cs, 85)
@@ -58,8 +59,8 @@ def test_one_launch_per_query(ctx):
     q = ora.synth_fill(0, 1, dim, 86)[0]
     expr = FILTERS[0]()
     try:
-        for sel, lazy, want in ((0, 1, 1), (1, 1, 2), (0, 0, 2), (1, 0, 3)):
-            ctx.set_tuning(separate_select=sel, lazy_prune=lazy)
+        for sel, lazy, fused, want in ((0, 1, 0, 1), (1, 1, 0, 2), (0, 0, 2, 2), (1, 0, 2, 3), (0, 0, 0, 3), (1, 0, 0, 4)):
+            ctx.set_tuning(separate_select=sel, lazy_prune=lazy, disable_fused_predicate=fused)
             store.query(q, ob.Metric.Cosine).meta_filter(expr).take(10).collect()
             assert ctx.last_work()["kernel_launches"] == want
         ctx.set_tuning()

@@ -336,15 +336,15 @@ def test_meta_empty_store(ctx):
 
 
 def test_fused_and_unfused_predicate_paths_agree(meta_pair):
-    """The scan kernel normally evaluates the row predicate itself (fused K0b); the stand-alone row-mask kernel
-    must give the same answer."""
+    """The row predicate normally runs as its own kernel (K0b row bitmask); evaluated per work unit inside the scan kernel
+    (fused K0b) it must give the same answer."""
     store, ost, _, _ = meta_pair
     q = ora.synth_fill(0, 1, 64, 66)
     try:
         for fi in range(len(FILTERS)):
             expr = FILTERS[fi]()
             got = []
-            for disable in (0, 1):
+            for disable in (1, 2):
                 store.ctx.set_tuning(disable_fused_predicate=disable)
                 res = store.query(q[0], ob.Metric.Cosine).meta_filter(expr).take(40).collect()
                 got.append((res.indices, res.scores))
