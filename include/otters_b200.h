@@ -268,10 +268,27 @@ typedef struct {
 /* MetaQueryPlan::collect (src/meta.rs:632-721): zonemap/Bloom chunk pruning (:407-544), per-row CNF
  * predicate (src/meta_compute.rs:194-318), scoring, top-k, stats.  `q->row_mask_words` must be NULL.
  * `filter` may be NULL (no meta_filter).  Result-column gathering (src/meta.rs:723-828) stays on
- * the host side of the boundary. */
+ * the host side of the boundary or, on the device, otters_metastore_gather. */
 OTTERS_API int otters_metastore_query(otters_metastore *ms, const otters_vec_query *q, const otters_filter *filter,
                            uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap, uint64_t *out_len,
                            otters_query_stats *stats /* nullable */);
+/* Per-query top-k for a batch — an extension: the reference merges a batch into ONE list (src/vec.rs:217-219), which
+ * otters_vecstore_query / otters_metastore_query reproduce.  Here every query i of q (nq queries) gets its own list:
+ * out_idx / out_score hold nq rows of q->k entries, out_len[i] results are valid in row i, and row i is exactly what the
+ * single-query call returns for query i (bit-identical).  The queries are pipelined over the context's two lanes.  Stats
+ * follow the reference's batch convention (chunks counted once, vectors_compared = sum over chunks of len * nq). */
+OTTERS_API int otters_vecstore_query_batch(otters_vecstore *vs, const otters_vec_query *q, uint64_t *out_idx, float *out_score,
+                                uint64_t *out_len /* [nq] */);
+OTTERS_API int otters_metastore_query_batch(otters_metastore *ms, const otters_vec_query *q, const otters_filter *filter,
+                                 uint64_t *out_idx, float *out_score, uint64_t *out_len /* [nq] */,
+                                 otters_query_stats *stats /* nullable */);
+/* MetaQueryResults.data (src/meta.rs:723-821): gathers column `col` at the n result rows on the device.  out_values is
+ * typed like the column (int32 / int64 / float / double / DateTime millis); for String columns it receives uint32
+ * dictionary codes, which otters_metastore_dict_entry maps back to bytes (valid while the store lives).  out_nulls[i] = 1
+ * marks a NULL row (its value slot holds the column's sentinel / an undefined code). */
+OTTERS_API int otters_metastore_gather(otters_metastore *ms, uint32_t col, const uint64_t *rows, uint64_t n, void *out_values,
+                            uint8_t *out_nulls);
+OTTERS_API int otters_metastore_dict_entry(const otters_metastore *ms, uint32_t col, uint32_t code, const uint8_t **bytes, uint64_t *len);
 /* MetaStore::last_query_stats (src/meta.rs:395-397); returns OTTERS_ERR_INVALID if no query ran yet */
 OTTERS_API int otters_metastore_last_stats(const otters_metastore *ms, otters_query_stats *out);
 

@@ -229,6 +229,12 @@ otters_metastore_query = _sig(
     c_u64p,
     C.POINTER(QueryStats),
 )
+otters_vecstore_query_batch = _sig("otters_vecstore_query_batch", C.c_int, _p, C.POINTER(VecQuery), c_u64p, c_f32p, c_u64p)
+otters_metastore_query_batch = _sig(
+    "otters_metastore_query_batch", C.c_int, _p, C.POINTER(VecQuery), C.POINTER(Filter), c_u64p, c_f32p, c_u64p, C.POINTER(QueryStats)
+)
+otters_metastore_gather = _sig("otters_metastore_gather", C.c_int, _p, C.c_uint32, c_u64p, C.c_uint64, _p, c_u8p)
+otters_metastore_dict_entry = _sig("otters_metastore_dict_entry", C.c_int, _p, C.c_uint32, C.c_uint32, C.POINTER(c_u8p), c_u64p)
 otters_metastore_last_stats = _sig("otters_metastore_last_stats", C.c_int, _p, C.POINTER(QueryStats))
 otters_metastore_chunk_mask = _sig("otters_metastore_chunk_mask", C.c_int, _p, C.POINTER(Filter), c_u8p)
 otters_metastore_row_mask = _sig("otters_metastore_row_mask", C.c_int, _p, C.POINTER(Filter), c_u8p)

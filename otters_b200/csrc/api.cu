@@ -176,6 +176,8 @@ struct otters_ctx {
     // that runs it, so two lanes can search the same store at the same time)
     uint32_t* d_chunk_keep = nullptr;   // stand-alone prune kernel: one bit per chunk
     size_t chunk_keep_words = 0;
+    uint8_t* d_gather = nullptr;        // result-column gather staging
+    size_t d_gather_bytes = 0;
     uint32_t* d_meta_mask = nullptr;    // stand-alone row-mask kernel: one bit per row
     size_t meta_mask_words = 0;
     FusedFilter cur_filter;             // where the last lowered filter lives on the device
@@ -409,6 +411,19 @@ struct VecStorage {
         if (n + cnt >= 0xFFFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "a store shard is limited to 2^32-16 rows");
         int rc = reserve(n + cnt);
         if (rc) return rc;
+        // large host inputs are pinned in place for the duration of the copy (cudaHostRegister): the H2D copy then runs at
+        // PCIe rate instead of being staged through the driver's bounce buffers; silently skipped when the range cannot be pinned
+        struct Pin {
+            void* p = nullptr;
+            ~Pin() {
+                if (p) cudaHostUnregister(p);
+            }
+        } pin;
+        const size_t in_bytes = (size_t)cnt * dim * sizeof(float);
+        if (kind == cudaMemcpyHostToDevice && in_bytes >= ((size_t)64 << 20) && !getenv("OTTERS_NO_PIN")) {
+            if (cudaHostRegister((void*)rows, in_bytes, cudaHostRegisterDefault) == cudaSuccess) pin.p = (void*)rows;
+            else cudaGetLastError();
+        }
         if (pitch == dim) {
             OTTERS_CUDA(cudaMemcpyAsync(d_rows + n * pitch, rows, cnt * dim * sizeof(float), kind, ctx->stream));
         } else {
@@ -1204,6 +1219,7 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_chunk_keep);
     cudaFree(c->d_meta_mask);
+    cudaFree(c->d_gather);
     cudaFree(c->d_io);
     for (auto& e : c->ev_io)
         if (e) cudaEventDestroy(e);
@@ -1434,6 +1450,7 @@ struct MetaColumn {
     std::vector<uint32_t> non_null;
     // string dictionary
     std::unordered_map<std::string, uint32_t> dict;
+    std::vector<std::string> dict_strings;  // code -> bytes (result-column gather)
     size_t value_bytes = 0;
 };
 
@@ -1661,7 +1678,10 @@ static int build_column(otters_metastore* ms, const otters_column& in, const ott
             }
             std::string sv((const char*)in.str_bytes + in.str_offsets[i], in.str_offsets[i + 1] - in.str_offsets[i]);
             auto it = mc->dict.find(sv);
-            if (it == mc->dict.end()) it = mc->dict.emplace(std::move(sv), (uint32_t)mc->dict.size()).first;
+            if (it == mc->dict.end()) {
+                mc->dict_strings.push_back(sv);
+                it = mc->dict.emplace(std::move(sv), (uint32_t)mc->dict.size()).first;
+            }
             codes[i] = it->second;
         }
         // per-chunk Bloom filters sized for the chunk length (src/meta_compute.rs:99-116)
@@ -1704,6 +1724,165 @@ static int build_column(otters_metastore* ms, const otters_column& in, const ott
     default: return fail(OTTERS_ERR_INVALID, "unknown column dtype");
     }
     if ((rc = upload(&mc->d_non_null, mc->non_null.data(), nc * 4))) return rc;
+    return OTTERS_OK;
+}
+
+// ---- device-side column build (build.cu): same tables as build_column above, computed by kernels over the uploaded column ----
+struct DevTmp {  // frees temporary device buffers on scope exit
+    std::vector<void*> ptrs;
+    template <typename T>
+    int alloc(T** p, size_t bytes) {
+        *p = nullptr;
+        if (cudaMalloc((void**)p, std::max<size_t>(bytes, 16)) != cudaSuccess) return fail(OTTERS_ERR_NOMEM, "device allocation for the store build failed");
+        ptrs.push_back(*p);
+        return OTTERS_OK;
+    }
+    ~DevTmp() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+template <typename T>
+static int dev_alloc(T** dptr, size_t bytes) {
+    *dptr = nullptr;
+    if (cudaMalloc((void**)dptr, std::max<size_t>(bytes, 16)) != cudaSuccess) return fail(OTTERS_ERR_NOMEM, "device allocation for metadata failed");
+    return OTTERS_OK;
+}
+
+// returns OTTERS_OK with *used = false when the column must take the host path (hash collision in the dictionary)
+static int build_column_device(otters_metastore* ms, const otters_column& in, const otters_build_params* p, double bloom_fpr,
+                               uint64_t bloom_bits, MetaColumn* mc, bool* used) {
+    *used = true;
+    const uint64_t n = p->n_rows, cs = ms->chunk_size, nc = ms->n_chunks;
+    cudaStream_t s = ms->ctx->stream;
+    mc->name = in.name ? in.name : "";
+    mc->dtype = in.dtype;
+    mc->non_null.assign(nc, 0);
+    int rc;
+    if (in.null_words) {
+        if ((rc = upload(&mc->d_nulls, in.null_words, (n + 63) / 64 * 8))) return rc;
+    }
+    if ((rc = dev_alloc(&mc->d_non_null, nc * 4))) return rc;
+    if (in.dtype != OTTERS_DTYPE_STRING) {
+        const size_t w = (in.dtype == OTTERS_DTYPE_INT32 || in.dtype == OTTERS_DTYPE_FLOAT32) ? 4 : 8;
+        if (in.dtype < 0 || in.dtype > OTTERS_DTYPE_DATETIME) return fail(OTTERS_ERR_INVALID, "unknown column dtype");
+        if (n && !in.values) return fail(OTTERS_ERR_INVALID, "column values are missing");
+        if ((rc = upload(&mc->d_values, in.values, n * w))) return rc;
+        if ((rc = dev_alloc(&mc->d_zmin, nc * w))) return rc;
+        if ((rc = dev_alloc(&mc->d_zmax, nc * w))) return rc;
+        if ((rc = launch_zonemap(in.dtype, mc->d_values, mc->d_nulls, n, cs, nc, mc->d_zmin, mc->d_zmax, mc->d_non_null, s))) return rc;
+        mc->value_bytes = w;
+        // host copies of the (small) tables for the parity exports
+        std::vector<uint8_t> hmin(nc * w), hmax(nc * w);
+        OTTERS_CUDA(cudaMemcpyAsync(hmin.data(), mc->d_zmin, nc * w, cudaMemcpyDeviceToHost, s));
+        OTTERS_CUDA(cudaMemcpyAsync(hmax.data(), mc->d_zmax, nc * w, cudaMemcpyDeviceToHost, s));
+        OTTERS_CUDA(cudaMemcpyAsync(mc->non_null.data(), mc->d_non_null, nc * 4, cudaMemcpyDeviceToHost, s));
+        OTTERS_CUDA(cudaStreamSynchronize(s));
+        const bool is_f = in.dtype == OTTERS_DTYPE_FLOAT32 || in.dtype == OTTERS_DTYPE_FLOAT64;
+        if (is_f) {
+            mc->zmin_f.resize(nc);
+            mc->zmax_f.resize(nc);
+        } else {
+            mc->zmin_i.resize(nc);
+            mc->zmax_i.resize(nc);
+        }
+        for (uint64_t ch = 0; ch < nc; ++ch) {
+            switch (in.dtype) {
+            case OTTERS_DTYPE_INT32: mc->zmin_i[ch] = ((int32_t*)hmin.data())[ch]; mc->zmax_i[ch] = ((int32_t*)hmax.data())[ch]; break;
+            case OTTERS_DTYPE_FLOAT32: mc->zmin_f[ch] = ((float*)hmin.data())[ch]; mc->zmax_f[ch] = ((float*)hmax.data())[ch]; break;
+            case OTTERS_DTYPE_FLOAT64: mc->zmin_f[ch] = ((double*)hmin.data())[ch]; mc->zmax_f[ch] = ((double*)hmax.data())[ch]; break;
+            default: mc->zmin_i[ch] = ((int64_t*)hmin.data())[ch]; mc->zmax_i[ch] = ((int64_t*)hmax.data())[ch]; break;
+            }
+        }
+        return OTTERS_OK;
+    }
+    // ---- String: hashes -> Bloom filters + dictionary codes -------------------------------------------------------------
+    if (n && (!in.str_offsets || (!in.str_bytes && in.str_offsets[n] != 0))) return fail(OTTERS_ERR_INVALID, "expected String column");
+    if (n >= 0xFFFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "a store shard is limited to 2^32-16 rows");
+    DevTmp tmp;
+    uint8_t* d_bytes = nullptr;
+    uint64_t *d_offs = nullptr, *d_hash = nullptr;
+    const uint64_t n_bytes = n ? in.str_offsets[n] : 0;
+    if ((rc = tmp.alloc(&d_bytes, n_bytes))) return rc;
+    if ((rc = tmp.alloc(&d_offs, (n + 1) * 8))) return rc;
+    if ((rc = tmp.alloc(&d_hash, n * 8))) return rc;
+    if (n_bytes) OTTERS_CUDA(cudaMemcpyAsync(d_bytes, in.str_bytes, n_bytes, cudaMemcpyHostToDevice, s));
+    if (n) OTTERS_CUDA(cudaMemcpyAsync(d_offs, in.str_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_string_hash(d_bytes, d_offs, mc->d_nulls, n, d_hash, s))) return rc;
+    // Bloom geometry per chunk (host: one entry per chunk), filters built on the device
+    uint64_t m0;
+    uint32_t k0;
+    bloom_params(std::min<uint64_t>(cs, std::max<uint64_t>(n, 1)), p->bloom_mode, bloom_fpr, bloom_bits, &m0, &k0);
+    mc->bloom_stride = m0 / 64;
+    mc->bloom_k0 = k0;
+    std::vector<uint64_t> mbits(std::max<uint64_t>(nc, 1), 64);
+    std::vector<uint32_t> kh(std::max<uint64_t>(nc, 1), 1);
+    for (uint64_t ch = 0; ch < nc; ++ch) {
+        const uint64_t cs0 = ch * cs, ce = std::min<uint64_t>(cs0 + cs, n);
+        bloom_params(ce - cs0, p->bloom_mode, bloom_fpr, bloom_bits, &mbits[ch], &kh[ch]);
+    }
+    const size_t n_words = std::max<uint64_t>(nc, 1) * mc->bloom_stride;
+    if ((rc = dev_alloc(&mc->d_bloom, n_words * 8))) return rc;
+    OTTERS_CUDA(cudaMemsetAsync(mc->d_bloom, 0, std::max<size_t>(n_words * 8, 16), s));
+    if ((rc = upload(&mc->d_bloom_mbits, mbits.data(), mbits.size() * 8))) return rc;
+    if ((rc = upload(&mc->d_bloom_k, kh.data(), kh.size() * 4))) return rc;
+    if ((rc = launch_bloom_build(d_hash, mc->d_nulls, n, cs, nc, mc->d_bloom_mbits, mc->d_bloom_k, mc->bloom_stride, mc->d_bloom, mc->d_non_null, s)))
+        return rc;
+    // dictionary: distinct hashes claim table slots; the host numbers them in order of first occurrence
+    const uint64_t T = std::max<uint64_t>(pow2_at_least(2 * std::max<uint64_t>(n, 1)), 1024);
+    uint64_t* d_keys = nullptr;
+    uint32_t *d_rep = nullptr, *d_slot_code = nullptr, *d_list_slot = nullptr, *d_list_rep = nullptr, *d_flags = nullptr;
+    const uint32_t list_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(n, 1), 0xFFFFFFF0ull);
+    if ((rc = tmp.alloc(&d_keys, T * 8))) return rc;
+    if ((rc = tmp.alloc(&d_rep, T * 4))) return rc;
+    if ((rc = tmp.alloc(&d_slot_code, T * 4))) return rc;
+    if ((rc = tmp.alloc(&d_list_slot, (size_t)list_cap * 4))) return rc;
+    if ((rc = tmp.alloc(&d_list_rep, (size_t)list_cap * 4))) return rc;
+    if ((rc = tmp.alloc(&d_flags, 16))) return rc;
+    OTTERS_CUDA(cudaMemsetAsync(d_keys, 0xFF, T * 8, s));
+    OTTERS_CUDA(cudaMemsetAsync(d_rep, 0xFF, T * 4, s));
+    OTTERS_CUDA(cudaMemsetAsync(d_flags, 0, 16, s));
+    if ((rc = launch_dict_insert(d_hash, mc->d_nulls, n, d_keys, d_rep, T, s))) return rc;
+    if ((rc = launch_dict_collect(d_keys, d_rep, T, d_list_slot, d_list_rep, d_flags, list_cap, s))) return rc;
+    uint32_t n_distinct = 0;
+    OTTERS_CUDA(cudaMemcpyAsync(&n_distinct, d_flags, 4, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaStreamSynchronize(s));
+    if (n_distinct > list_cap) return fail(OTTERS_ERR_UNSUPPORTED, "dictionary build: inconsistent distinct count");
+    std::vector<uint32_t> l_slot(n_distinct), l_rep(n_distinct), order(n_distinct), l_code(n_distinct);
+    if (n_distinct) {
+        OTTERS_CUDA(cudaMemcpy(l_slot.data(), d_list_slot, (size_t)n_distinct * 4, cudaMemcpyDeviceToHost));
+        OTTERS_CUDA(cudaMemcpy(l_rep.data(), d_list_rep, (size_t)n_distinct * 4, cudaMemcpyDeviceToHost));
+    }
+    for (uint32_t i = 0; i < n_distinct; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return l_rep[a] < l_rep[b]; });
+    mc->dict.clear();
+    mc->dict_strings.clear();
+    mc->dict_strings.reserve(n_distinct);
+    bool collision = false;
+    for (uint32_t code = 0; code < n_distinct; ++code) {
+        const uint32_t i = order[code], r = l_rep[i];
+        l_code[i] = code;
+        std::string sv((const char*)in.str_bytes + in.str_offsets[r], in.str_offsets[r + 1] - in.str_offsets[r]);
+        if (!mc->dict.emplace(sv, code).second) collision = true;  // (two slots, one string: impossible — same hash, same slot)
+        mc->dict_strings.push_back(std::move(sv));
+    }
+    uint32_t* d_list_code = nullptr;
+    if ((rc = tmp.alloc(&d_list_code, (size_t)std::max<uint32_t>(n_distinct, 1) * 4))) return rc;
+    if (n_distinct) OTTERS_CUDA(cudaMemcpyAsync(d_list_code, l_code.data(), (size_t)n_distinct * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = dev_alloc((uint32_t**)&mc->d_values, n * 4))) return rc;
+    if ((rc = launch_dict_encode(d_list_slot, d_list_code, n_distinct, d_slot_code, d_hash, mc->d_nulls, d_bytes, d_offs, n, d_keys, d_rep, T,
+                                 (uint32_t*)mc->d_values, d_flags + 1, s)))
+        return rc;
+    uint32_t mismatch = 0;
+    OTTERS_CUDA(cudaMemcpyAsync(&mismatch, d_flags + 1, 4, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaMemcpyAsync(mc->non_null.data(), mc->d_non_null, nc * 4, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaStreamSynchronize(s));
+    mc->value_bytes = 4;
+    if (mismatch || collision) {  // two different strings share a 64-bit hash: let the host build this column
+        *used = false;
+        cudaFree(mc->d_values); cudaFree(mc->d_nulls); cudaFree(mc->d_non_null); cudaFree(mc->d_bloom); cudaFree(mc->d_bloom_mbits); cudaFree(mc->d_bloom_k);
+        *mc = MetaColumn{};
+    }
     return OTTERS_OK;
 }
 
@@ -1766,7 +1945,15 @@ extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* 
     ms->cols.resize(p->n_columns);
     std::vector<DevColumn> dcols(std::max<uint32_t>(p->n_columns, 1));
     for (uint32_t i = 0; i < p->n_columns; ++i) {
-        rc = build_column(ms.get(), p->columns[i], p, fpr, bits, &ms->cols[i]);
+        // tables are built by kernels over the uploaded column (build.cu); OTTERS_BUILD_HOST=1 keeps the host loops
+        // (the two are bit-identical: tests/test_gpu_build.py)
+        const char* host_env = getenv("OTTERS_BUILD_HOST");
+        bool on_device = !(host_env && atoi(host_env) != 0);
+        if (on_device) {
+            rc = build_column_device(ms.get(), p->columns[i], p, fpr, bits, &ms->cols[i], &on_device);
+            if (rc) return cleanup(rc);
+        }
+        if (!on_device) rc = build_column(ms.get(), p->columns[i], p, fpr, bits, &ms->cols[i]);
         if (rc) return cleanup(rc);
         const MetaColumn& mc = ms->cols[i];
         DevColumn& d = dcols[i];
@@ -2429,6 +2616,130 @@ extern "C" int otters_query_submit(otters_vecstore* vs, otters_metastore* ms, co
     pd.ticket = (parent->tickets << 8) | li;
     c->pend = pd;
     *ticket = pd.ticket;
+    return OTTERS_OK;
+}
+
+namespace otters {
+// ---- per-query top-k for a batch (extension beyond src/vec.rs:217-219's merged list) ------------------------------------
+// Every query of the batch gets its own list — exactly what the single-query call returns for it (bit-identical by
+// construction: each list comes from one streaming scan in the reference's arithmetic).  The queries are pipelined over the
+// context's two lanes, so the launch, the input copy and the selection of query i+1 overlap the scan of query i.
+static int query_batch_impl(otters_vecstore* vs, otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                            uint64_t* out_idx, float* out_score, uint64_t* out_len, otters_query_stats* stats) {
+    otters_ctx* parent = vs ? vs->st.ctx : ms->ctx;
+    DeviceGuard g(parent->device);
+    if (!q) return fail(OTTERS_ERR_INVALID, "Query vectors or their norms are not set");
+    if (!out_len || ((!out_idx || !out_score) && q->nq && q->k)) return fail(OTTERS_ERR_INVALID, "null output buffers");
+    const uint32_t store_dim = vs ? vs->st.dim : ms->st.dim;
+    if (vs) {
+        int rc = validate_query(q, store_dim, false);
+        if (rc) return rc;
+    } else if (q->nq == 0 || q->dim != store_dim || !q->queries) {
+        // MetaStore swallows per-chunk errors (src/meta_compute.rs:182): no rows, statistics only — same as the merged call
+        uint64_t n = 0;
+        return meta_query_impl(parent, ms, q, filter, nullptr, ShardMap{}, nullptr, nullptr, nullptr, 0, &n, stats);
+    }
+    Pending pd[kMaxLanes];
+    otters_query_stats st_first{};
+    otters_last_work total{};
+    int rc = OTTERS_OK;
+    for (uint32_t i = 0; i <= q->nq && rc == OTTERS_OK; ++i) {
+        if (i < q->nq) {
+            otters_ctx* c = get_lane(parent, i % kMaxLanes);
+            if (!c) return OTTERS_ERR_CUDA;
+            c->pend.active = false;
+            otters_vec_query one = *q;
+            one.queries = q->queries + (size_t)i * q->dim;
+            one.nq = 1;
+            c->pipelined = true;
+            rc = enqueue_any(c, vs, ms, &one, filter, nullptr, nullptr, 0, true, false, &pd[i % kMaxLanes]);
+            c->pipelined = false;
+            if (rc) break;
+        }
+        if (i >= 1) {
+            const uint32_t j = i - 1;
+            otters_ctx* c = get_lane(parent, j % kMaxLanes);
+            uint64_t n = 0;
+            otters_query_stats st{};
+            rc = ms ? meta_finish(c, &pd[j % kMaxLanes], true, out_idx + (size_t)j * q->k, out_score + (size_t)j * q->k, nullptr, q->k, &n, &st)
+                    : vec_finish(c, &pd[j % kMaxLanes], true, out_idx + (size_t)j * q->k, out_score + (size_t)j * q->k, nullptr, q->k, &n);
+            out_len[j] = std::min<uint64_t>(n, q->k);
+            if (j == 0) st_first = st;
+            total.kernel_launches += c->last.kernel_launches;
+            total.rows_scored += c->last.rows_scored;
+            total.scan_bytes += c->last.scan_bytes;
+            total.h2d_bytes += c->last.h2d_bytes;
+            total.d2h_bytes += c->last.d2h_bytes;
+        }
+    }
+    if (rc) {
+        otters_ctx_synchronize(parent);
+        return rc;
+    }
+    parent->last = total;
+    if (ms) {
+        // statistics of the batch as the reference reports them: chunks once, vectors_compared = sum over chunks of len * Q
+        st_first.vectors_compared *= q->nq;
+        ms->last = st_first;
+        ms->has_stats = true;
+        if (stats) *stats = st_first;
+    }
+    return OTTERS_OK;
+}
+
+}  // namespace otters
+
+extern "C" int otters_vecstore_query_batch(otters_vecstore* vs, const otters_vec_query* q, uint64_t* out_idx, float* out_score,
+                                           uint64_t* out_len) {
+    if (!vs) return fail(OTTERS_ERR_INVALID, "null store");
+    return query_batch_impl(vs, nullptr, q, nullptr, out_idx, out_score, out_len, nullptr);
+}
+
+extern "C" int otters_metastore_query_batch(otters_metastore* ms, const otters_vec_query* q, const otters_filter* filter,
+                                            uint64_t* out_idx, float* out_score, uint64_t* out_len, otters_query_stats* stats) {
+    if (!ms) return fail(OTTERS_ERR_INVALID, "null store");
+    if (q && q->row_mask_words) return fail(OTTERS_ERR_INVALID, "row masks are not part of MetaQueryPlan");
+    return query_batch_impl(nullptr, ms, q, filter, out_idx, out_score, out_len, stats);
+}
+
+// MetaQueryResults.data (src/meta.rs:723-821): the metadata of the result rows, gathered on the device
+extern "C" int otters_metastore_gather(otters_metastore* ms, uint32_t col, const uint64_t* rows, uint64_t n, void* out_values,
+                                       uint8_t* out_nulls) {
+    if (!ms || col >= ms->cols.size()) return fail(OTTERS_ERR_INVALID, "unknown column");
+    if (n == 0) return OTTERS_OK;
+    if (!rows || !out_values || !out_nulls) return fail(OTTERS_ERR_INVALID, "null argument");
+    otters_ctx* c = ms->ctx;
+    DeviceGuard g(c->device);
+    const MetaColumn& mc = ms->cols[col];
+    const size_t w = mc.value_bytes;
+    for (uint64_t i = 0; i < n; ++i)
+        if (rows[i] >= ms->st.n) return fail(OTTERS_ERR_INVALID, "row index out of bounds");
+    // staging: [rows u32 | values | nulls] in one pinned buffer and one device buffer
+    const size_t off_v = round_up(n * 4, 16), off_n = off_v + round_up(n * w, 16), total = off_n + round_up(n, 16);
+    int rc = ensure_stage(c, total);
+    if (rc) return rc;
+    rc = ensure_dev(&c->d_gather, &c->d_gather_bytes, total, c->stream);
+    if (rc) return rc;
+    uint32_t* h_rows = reinterpret_cast<uint32_t*>(c->h_stage);
+    for (uint64_t i = 0; i < n; ++i) h_rows[i] = (uint32_t)rows[i];
+    cudaStream_t s = c->stream;
+    OTTERS_CUDA(cudaMemcpyAsync(c->d_gather, h_rows, n * 4, cudaMemcpyHostToDevice, s));
+    rc = launch_gather(mc.d_values, mc.d_nulls, (uint32_t)w, reinterpret_cast<const uint32_t*>(c->d_gather), (uint32_t)n, c->d_gather + off_v,
+                       c->d_gather + off_n, s);
+    if (rc) return rc;
+    OTTERS_CUDA(cudaMemcpyAsync(c->h_stage + off_v, c->d_gather + off_v, total - off_v, cudaMemcpyDeviceToHost, s));
+    OTTERS_CUDA(cudaStreamSynchronize(s));
+    memcpy(out_values, c->h_stage + off_v, n * w);
+    memcpy(out_nulls, c->h_stage + off_n, n);
+    return OTTERS_OK;
+}
+
+extern "C" int otters_metastore_dict_entry(const otters_metastore* ms, uint32_t col, uint32_t code, const uint8_t** bytes, uint64_t* len) {
+    if (!ms || col >= ms->cols.size() || !bytes || !len) return fail(OTTERS_ERR_INVALID, "unknown column");
+    const MetaColumn& mc = ms->cols[col];
+    if (mc.dtype != OTTERS_DTYPE_STRING || code >= mc.dict_strings.size()) return fail(OTTERS_ERR_INVALID, "not a dictionary code of this column");
+    *bytes = reinterpret_cast<const uint8_t*>(mc.dict_strings[code].data());
+    *len = mc.dict_strings[code].size();
     return OTTERS_OK;
 }
 

@@ -262,6 +262,20 @@ int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t
 int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, ShardMap gen_map, uint64_t n,
                       uint64_t seed, cudaStream_t s);
 
+// ---- device-side MetaStore build: build.cu ---------------------------------------------------------------------------
+int launch_zonemap(int dtype, const void* values, const uint32_t* null_words, uint64_t n_rows, uint64_t chunk_size, uint64_t n_chunks,
+                   void* zmin, void* zmax, uint32_t* non_null, cudaStream_t s);
+int launch_string_hash(const uint8_t* bytes, const uint64_t* offsets, const uint32_t* null_words, uint64_t n_rows, uint64_t* hashes, cudaStream_t s);
+int launch_bloom_build(const uint64_t* hashes, const uint32_t* null_words, uint64_t n_rows, uint64_t chunk_size, uint64_t n_chunks,
+                       const uint64_t* mbits, const uint32_t* khash, uint64_t stride_words, uint64_t* words, uint32_t* non_null, cudaStream_t s);
+int launch_dict_insert(const uint64_t* hashes, const uint32_t* null_words, uint64_t n_rows, uint64_t* keys, uint32_t* rep, uint64_t table_size,
+                       cudaStream_t s);
+int launch_dict_collect(const uint64_t* keys, const uint32_t* rep, uint64_t table_size, uint32_t* list_slot, uint32_t* list_rep, uint32_t* count,
+                        uint32_t cap, cudaStream_t s);
+int launch_dict_encode(const uint32_t* list_slot, const uint32_t* list_code, uint32_t n_distinct, uint32_t* slot_code, const uint64_t* hashes,
+                       const uint32_t* null_words, const uint8_t* bytes, const uint64_t* offsets, uint64_t n_rows, const uint64_t* keys,
+                       const uint32_t* rep, uint64_t table_size, uint32_t* codes, uint32_t* mismatch, cudaStream_t s);
+
 // ---- metadata kernels -------------------------------------------------------------------------
 struct DevColumn {
     int32_t dtype;
@@ -328,5 +342,7 @@ struct MetaKernelParams {
 int launch_prune(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s);
 int launch_rowmask(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s);
 int launch_count_all_chunks(const MetaKernelParams& p, cudaStream_t s);
+int launch_gather(const void* values, const uint32_t* null_words, uint32_t width, const uint32_t* rows, uint32_t n, void* out_values,
+                  uint8_t* out_nulls, cudaStream_t s);
 
 }  // namespace otters

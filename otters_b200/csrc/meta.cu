@@ -176,7 +176,30 @@ __global__ void __launch_bounds__(256) rowmask_kernel(const __grid_constant__ Me
     }
 }
 
+// Result-column gather (MetaQueryPlan::collect's `data`, reference src/meta.rs:723-821): values and NULL flags of the result
+// rows of one column.  W = value width in bytes (4: Int32 / Float32 / dictionary codes, 8: Int64 / Float64 / DateTime).
+template <typename T>
+__global__ void gather_kernel(const T* values, const uint32_t* null_words, const uint32_t* rows, uint32_t n, T* out_values, uint8_t* out_nulls) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t row = rows[i];
+    out_values[i] = values[row];
+    out_nulls[i] = null_words ? (uint8_t)((null_words[row >> 5] >> (row & 31)) & 1u) : (uint8_t)0;
+}
+
 }  // namespace
+
+int launch_gather(const void* values, const uint32_t* null_words, uint32_t width, const uint32_t* rows, uint32_t n, void* out_values,
+                  uint8_t* out_nulls, cudaStream_t s) {
+    if (n == 0) return OTTERS_OK;
+    const unsigned blocks = (n + 255) / 256;
+    if (width == 8)
+        gather_kernel<uint64_t><<<blocks, 256, 0, s>>>((const uint64_t*)values, null_words, rows, n, (uint64_t*)out_values, out_nulls);
+    else
+        gather_kernel<uint32_t><<<blocks, 256, 0, s>>>((const uint32_t*)values, null_words, rows, n, (uint32_t*)out_values, out_nulls);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
 
 int launch_prune(const MetaKernelParams& p, uint32_t n_leaves, cudaStream_t s) {
     if (p.n_chunks == 0) return OTTERS_OK;

@@ -373,7 +373,9 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         __syncthreads();
         if (warp == 0) {
             const uint32_t cnt = hdr->count;  // every push has completed: cnt <= cap and written == cnt
-            warp_sort(cbuf, cnt, p.cap, lane);
+            uint32_t sort_n = 32;  // only as much of the buffer as holds candidates (k = 1000: 2048 slots, usually a few dozen used)
+            while (sort_n < cnt) sort_n <<= 1;
+            warp_sort(cbuf, cnt, sort_n, lane);
             const uint32_t n = cnt < p.k ? cnt : p.k;
             for (uint32_t i = lane; i < n; i += 32) p.cta_keys[(size_t)blockIdx.x * p.k + i] = cbuf[i];
             if (lane == 0) p.cta_counts[blockIdx.x] = n;

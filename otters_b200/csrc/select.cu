@@ -51,7 +51,7 @@ merge_records_kernel(const otters_topk_record* recs, uint32_t n, uint32_t k, uin
     }
     if (loc) atomicAdd(&s_valid, loc);
     __syncthreads();
-    if (n <= kRankSelectElems) {
+    if (n <= kRankMergeElems) {
         // few records (world * k): every thread counts the records ordered before its own — no sorting network.
         // When the input is a concatenation of ordered lists of list_len records (what otters_query_local_device writes,
         // one list per rank) the count is a binary search per list; the ordering is verified first.

@@ -60,7 +60,10 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
 // so position order == qid order among equal keys); lists 1.. are this query's per-CTA lists.
 // tag = list << 11 | position  (position < 2048 because k <= 1024 in the fused path)
 constexpr uint32_t kPosBits = 11;
-constexpr uint32_t kRankSelectElems = 2048;  // largest working set served by the rank-counting fast paths
+constexpr uint32_t kRankSelectElems = 4096;  // largest working set served by the rank-counting fast path of the local selection
+                                             // (keys in s_keys[0, 4096), compacted candidates in s_keys[4096, 8192), the ranked
+                                             // result in the source-tag area, which the single-query path does not use)
+constexpr uint32_t kRankMergeElems = 2048;   // stand-alone record merge (select.cu): all-pairs count below this size
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -133,7 +136,7 @@ __device__ __forceinline__ void select_body(const SelectParams& p, uint8_t* sm) 
         // Fast path of the single-query case (all keys distinct): every thread loads one element of the union of
         // prefixes and finds its final position by counting the better elements — no sorting network, two barriers.
         const uint32_t nel_max = p.n_lists * L;
-        uint64_t* ranked = s_keys + kSelectSmemElems / 2;
+        uint64_t* ranked = reinterpret_cast<uint64_t*>(s_src);  // [kSelectSmemElems / 2]
         if (threadIdx.x == 0) {
             s_nel = 0;
             s_retry = 0;
@@ -314,7 +317,10 @@ __device__ __forceinline__ void select_body(const SelectParams& p, uint8_t* sm) 
         if (threadIdx.x == 0) s_nel = 0;
         __syncthreads();
         uint32_t loc = 0;
-        uint32_t P2 = n_in <= kRankSelectElems ? n_in : next_pow2(n_in);
+        // every rank's k records arrive ordered, so a record's final position is a binary search per rank: this serves any
+        // world * k that fits the working set (8 x 1024 records: ~20 us; the bitonic network it replaces took ~400 us with
+        // the few hundred threads of a scan CTA)
+        uint32_t P2 = n_in <= kSelectSmemElems ? n_in : next_pow2(n_in);
         for (uint32_t e = threadIdx.x; e < P2; e += blockDim.x) {
             uint64_t key = 0ull;
             uint32_t tag = 0xFFFFFFFFu;
@@ -332,7 +338,7 @@ __device__ __forceinline__ void select_body(const SelectParams& p, uint8_t* sm) 
         if (loc) atomicAdd(&s_nel, loc);
         __syncthreads();
         n_out = s_nel < p.ex_k ? s_nel : p.ex_k;
-        if (n_in <= kRankSelectElems) {
+        if (n_in <= kSelectSmemElems) {
             for (uint32_t e = threadIdx.x; e < n_in; e += blockDim.x) {
                 const uint64_t key = s_keys[e];
                 if (key == 0ull) continue;

@@ -289,6 +289,33 @@ class MetaStore:
     def n_chunks(self) -> int:
         return int(_ffi.otters_metastore_n_chunks(self._h))
 
+    def gather(self, name: str, indices) -> Column:
+        """Column ``name`` at the result rows ``indices``, gathered on the DEVICE (``otters_metastore_gather``;
+        MetaQueryResults.data of the reference, src/meta.rs:723-821).  NULLs are preserved; strings come back through the
+        store's dictionary."""
+        col = self._col_index[name]
+        dt = self._schema[name]
+        rows = np.ascontiguousarray(indices, dtype=np.uint64)
+        n = len(rows)
+        np_t = {DataType.Int32: np.int32, DataType.Int64: np.int64, DataType.Float32: np.float32, DataType.Float64: np.float64,
+                DataType.DateTime: np.int64, DataType.String: np.uint32}[dt]
+        vals = np.zeros(max(n, 1), np_t)
+        nulls = np.zeros(max(n, 1), np.uint8)
+        check(_ffi.otters_metastore_gather(self._h, col, rows.ctypes.data_as(_ffi.c_u64p), n, C.c_void_p(vals.ctypes.data),
+                                           nulls.ctypes.data_as(_ffi.c_u8p)))
+        vals, nulls = vals[:n], nulls[:n].astype(bool)
+        if dt != DataType.String:
+            return Column.from_numpy(name, dt, vals, nulls)
+        vocab: Dict[int, str] = {}
+        for code in np.unique(vals[~nulls]):
+            p, ln = _ffi.c_u8p(), C.c_uint64(0)
+            check(_ffi.otters_metastore_dict_entry(self._h, col, int(code), C.byref(p), C.byref(ln)))
+            vocab[int(code)] = C.string_at(p, ln.value).decode("utf-8")
+        out = Column(name, DataType.String)
+        for v, isnull in zip(vals, nulls):
+            out.push(None if isnull else vocab[int(v)])
+        return out
+
     def chunk_size(self) -> int:
         return self._chunk_size
 
@@ -460,8 +487,25 @@ class MetaQueryPlan:
         )
         indices = [int(i) for i in idx[:m]]
         names = sorted(store.schema().keys())  # src/meta.rs:723-724
-        data = {n: store.columns()[n].gather(indices) for n in names}
+        data = {n: store.gather(n, indices) for n in names}  # gathered on the device
         return MetaQueryResults(names, data, indices, [float(s) for s in score[:m]], [int(x) for x in qid[:m]])
+
+    def collect_per_query(self) -> List[MetaQueryResults]:
+        """Extension (``otters_metastore_query_batch``): one result per query of the batch instead of the reference's single
+        merged list; entry i is exactly what ``store.query(queries[i], metric)...collect()`` returns."""
+        if self._meta_error is not None:
+            raise OttersError(self._meta_error)
+        store = self._store
+        vq, fp, q, k, nq = self.build_query()
+        k_cap = max(min(k, store.len()), 1)
+        vq.k = k_cap if k > 0 else 0
+        idx = np.zeros((max(nq, 1), k_cap), np.uint64)
+        score = np.zeros((max(nq, 1), k_cap), np.float32)
+        lens = np.zeros(max(nq, 1), np.uint64)
+        st = _ffi.QueryStats()
+        check(_ffi.otters_metastore_query_batch(store.handle, C.byref(vq), fp.byref() if fp else None, idx.ctypes.data_as(_ffi.c_u64p),
+                                                score.ctypes.data_as(_ffi.c_f32p), lens.ctypes.data_as(_ffi.c_u64p), C.byref(st)))
+        return [self._results(idx[i], score[i], np.full(k_cap, i, np.uint32), int(lens[i]), st) for i in range(nq)]
 
     def submit(self) -> "PendingMetaQuery":
         """Non-blocking form of collect() (``otters_query_submit``): the query is enqueued on one of the context's two lanes and

@@ -272,6 +272,21 @@ class VecQueryPlan:
         m = min(out_len.value, cap)
         return idx[:m], score[:m], qid[:m]
 
+    def collect_per_query(self):
+        """Extension (``otters_vecstore_query_batch``): a list with one (indices, scores) pair per query of the batch instead
+        of the reference's single merged list; entry i is exactly what the single-query plan returns for query i."""
+        vq, keep, cap = self._build_query()
+        nq = len(self._queries)
+        k_cap = max(min(vq.k, self._store.len()), 1)
+        if vq.k > 0:
+            vq.k = k_cap
+        idx = np.zeros((nq, k_cap), np.uint64)
+        score = np.zeros((nq, k_cap), np.float32)
+        lens = np.zeros(nq, np.uint64)
+        check(_ffi.otters_vecstore_query_batch(self._store._handle(), C.byref(vq), idx.ctypes.data_as(_ffi.c_u64p),
+                                               score.ctypes.data_as(_ffi.c_f32p), lens.ctypes.data_as(_ffi.c_u64p)))
+        return [(idx[i, : int(lens[i])].copy(), score[i, : int(lens[i])].copy()) for i in range(nq)]
+
     def submit(self) -> "PendingVecQuery":
         """Non-blocking form of collect_arrays() (``otters_query_submit``); at most two outstanding per context."""
         vq, keep, cap = self._build_query()

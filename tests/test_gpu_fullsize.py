@@ -91,12 +91,13 @@ def test_fullsize_vecstore_properties(metric, big_vecstore, ctx):
 
 def test_fullsize_metastore_target(ctx):
     """North-star target: MetaStore 10M x 768 Cosine top-100 with price.gt & item.eq & ts.gte (bench.py's generators)."""
-    import bench
+    import bench_workloads as bw
 
     n, dim, chunk, k = 10_000_000, 768, 1024, 100
-    cols = bench.meta_columns(ob, np.arange(n), chunk)
+    wl = bw.Workload("target")
+    cols = [c.to_ob(ob) for c in wl.columns(np.arange(n))]
     store = ob.MetaStore.from_columns(cols).with_synthetic_vectors(n, dim, SEED).with_chunk_size(chunk).with_context(ctx).build()
-    expr, _ = bench.meta_expr(ob, n)
+    expr = wl.expr(ob)
     q = ora.synth_fill(123_456, 1, dim, SEED)[0] + np.float32(0.25) * ora.synth_fill(0, 1, dim, 99)[0]
     res = store.query(q, ob.Metric.Cosine).meta_filter(expr).take(k).collect()
     st = store.last_query_stats()
@@ -121,6 +122,92 @@ def test_fullsize_metastore_target(ctx):
     kept = np.nonzero(keep_rows)[0]
     sample = np.setdiff1d(rng.choice(kept, 400, replace=False), idx)
     assert np.all(oracle_rows(sample, dim, q, ob.Metric.Cosine) <= score[-1])
+    del store
+    gc.collect()
+
+
+def _fullsize_meta_workload(ctx, name):
+    """Builds bench.py's full-size MetaStore workload `name` on the device; returns (workload, store, host columns, oracle filter)."""
+    import bench_workloads as bw
+
+    wl = bw.Workload(name)
+    spec = wl.columns(np.arange(wl.rows))
+    store = (ob.MetaStore.from_columns([c.to_ob(ob) for c in spec]).with_synthetic_vectors(wl.rows, wl.dim, SEED)
+             .with_chunk_size(wl.chunk).with_context(ctx).build())
+    prow, pvec = wl.planted()
+    if len(prow):
+        store.set_rows(prow, pvec)
+    idx = {c.name(): i for i, c in enumerate(spec)}
+    fp = ora.FilterPack([[(idx[n], op, kind, val) for n, op, kind, val in cl] for cl in wl.clauses()])
+    return wl, store, spec, fp, (prow, pvec)
+
+
+def _check_stats_and_mask(ctx, wl, store, spec, fp, idx):
+    """Chunk statistics equal the oracle's on the same metadata; returned rows pass the predicate; rows scored == rows kept."""
+    st = store.last_query_stats()
+    stand_in = np.ones((wl.rows, 1), np.float32)  # pruning and row masks do not depend on the vectors
+    ost = ora.MetaStore(stand_in, spec, wl.chunk)
+    keep_rows = ost.row_mask(fp)
+    assert keep_rows[idx].all(), "a returned row fails the metadata filter"
+    assert np.array_equal(keep_rows.astype(bool), wl.row_mask(spec)), "NumPy restatement of the CNF disagrees with the oracle"
+    _, _, _, ostats = ost.query(np.ones((1, 1), np.float32), ob.Metric.DotProduct, ob.TakeType.Max, 1, None, fp, ora.CANONICAL)
+    assert (st.total_chunks, st.pruned_chunks, st.evaluated_chunks, st.vectors_compared) == (
+        ostats["total_chunks"], ostats["pruned_chunks"], ostats["evaluated_chunks"], ostats["vectors_compared"])
+    assert 0 < st.evaluated_chunks < st.total_chunks
+    assert ctx.last_work()["rows_scored"] == int(keep_rows.sum())
+    return keep_rows
+
+
+def test_fullsize_metastore_c3(ctx):
+    """BASELINE config 3: MetaStore 10M x 128 Cosine, chunk 1024, price.gt & item.eq & ts.gte (zonemap + Bloom prune), top-100."""
+    wl, store, spec, fp, _ = _fullsize_meta_workload(ctx, "c3")
+    dim, k = wl.dim, wl.k
+    q = ora.synth_fill(4_321_987, 1, dim, SEED)[0] + np.float32(0.25) * ora.synth_fill(0, 1, dim, 98)[0]
+    res = store.query(q, ob.Metric.Cosine).meta_filter(wl.expr(ob)).take(k).collect()
+    idx, score = np.array(res.indices, np.int64), np.array(res.scores, np.float32)
+    assert len(idx) == k and np.all(score[:-1] >= score[1:])
+    check_against_row_oracle((idx, score), dim, q, ob.Metric.Cosine)
+    keep_rows = _check_stats_and_mask(ctx, wl, store, spec, fp, idx)
+    assert store.last_query_stats().total_chunks == 9766
+    # a sample of kept rows outside the result cannot beat its last entry
+    rng = np.random.default_rng(9)
+    sample = np.setdiff1d(rng.choice(np.nonzero(keep_rows)[0], 2000, replace=False), idx)
+    assert np.all(oracle_rows(sample, dim, q, ob.Metric.Cosine) <= score[-1])
+    # the non-blocking API, both predicate placements and both front-ends return the same bytes
+    again = store.query(q, ob.Metric.Cosine).meta_filter(wl.expr(ob)).take(k).submit().wait()
+    assert_same_results((again.indices, again.scores), (idx, score), "submit/wait")
+    for tune in (dict(disable_fused_predicate=2), dict(disable_fused_predicate=2, lazy_prune=1), dict(scan_mode=2), dict(scan_mode=1)):
+        ctx.set_tuning(**tune)
+        r2 = store.query(q, ob.Metric.Cosine).meta_filter(wl.expr(ob)).take(k).collect()
+        assert_same_results((r2.indices, r2.scores), (idx, score), str(tune))
+    ctx.set_tuning()
+    del store
+    gc.collect()
+
+
+def test_fullsize_metastore_c5(ctx):
+    """BASELINE config 5 as specified: MetaStore 5M x 1536 Cosine, Int32 / Float64 / String predicates
+    qty.gte & (price.lt | item.eq) & brand.neq, ~5,000 planted near-duplicates of the query, vec_filter(0.8, Gt), take(1000).
+    The answer is known by construction: the best 1000 planted rows that pass the metadata filter, all with cosine > 0.8."""
+    wl, store, spec, fp, (prow, pvec) = _fullsize_meta_workload(ctx, "c5")
+    dim, k = wl.dim, wl.k
+    q = wl.queries()[0, 0]
+    res = store.query(q, ob.Metric.Cosine).meta_filter(wl.expr(ob)).vec_filter(0.8, ob.Cmp.Gt).take(k).collect()
+    idx, score = np.array(res.indices, np.int64), np.array(res.scores, np.float32)
+    assert len(idx) == k and np.all(score[:-1] >= score[1:]) and np.all(score > np.float32(0.8))
+    keep_rows = _check_stats_and_mask(ctx, wl, store, spec, fp, idx)
+    # expected: oracle scores of the planted rows alone, filtered by the predicate and the threshold, best 1000
+    pidx, psc, _ = ora.vecstore_query(pvec, q[None, :], ob.Metric.Cosine, ob.TakeType.Max, len(prow), (0.8, ob.Cmp.Gt), None, ora.CANONICAL)
+    pidx = np.asarray(pidx, np.int64)
+    ok = keep_rows[prow[pidx]].astype(bool)
+    assert ok.sum() > k, "the workload must plant more passing near-duplicates than it asks for"
+    assert_same_results((idx, score), (prow[pidx][ok][:k], np.asarray(psc)[ok][:k]), "planted set's top-1000")
+    # without the threshold the same 1000 rows lead the list (nothing else comes near 0.8); take(k) > 1024 takes the sort path
+    res2 = store.query(q, ob.Metric.Cosine).meta_filter(wl.expr(ob)).take(1500).collect()
+    assert_same_results((res2.indices[:k], res2.scores[:k]), (idx, score), "no vec_filter, sort path")
+    n_ok = int(ok.sum())
+    assert n_ok >= 1500 or (res2.scores[n_ok] < 0.8 <= res2.scores[n_ok - 1])
+    assert np.isin(np.array(res2.indices[: min(n_ok, 1500)], np.int64), prow).all()
     del store
     gc.collect()
 
