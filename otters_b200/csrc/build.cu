@@ -1,7 +1,7 @@
 // build.cu — device-side MetaStore build (MetaStoreBuilder::build, reference src/meta.rs:151-305): per-chunk zonemaps
 // (min / max / non-null, src/meta_compute.rs:32-132), per-chunk string Bloom filters (:99-116) and the dictionary encoding
 // of string columns, as kernels over the uploaded columns.  Every table is bit-identical to what the host path (api.cu:
-// build_column) and the oracle build: min / max / counts and bit-set unions do not depend on the order of evaluation.
+// build_column) builds: min / max / counts and bit-set unions do not depend on the order of evaluation.
 #include "internal.h"
 
 namespace otters {
