@@ -566,11 +566,14 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     // small stores (e.g. one shard of a row-sharded search) need finer units, or the last units of the dynamic schedule
     // leave most warps idle: measured on a 1.25M x 768 shard, 32-row units scan in 0.293 ms against 0.330 ms for 128-row
     // units (profiles/r1_unit_rows_shard.log); large stores keep 128-row units (fewer unit boundaries)
-    if (!t.unit_rows && !c->pipelined) {
-        // (queries submitted on the lanes keep the large units: the tail of one query's scan is filled by the head of the
-        // next one's, so fewer unit boundaries win — 1.25M x 768 shard: 3598 vs 3478 queries/s, profiles/r2_shard_units.txt)
-        // planner front-end: a unit is spread over all warps of its CTA, so only the per-CTA unit count matters
-        const uint64_t want = planner ? (uint64_t)grid * 16 : (uint64_t)grid * W * 16;
+    if (!t.unit_rows) {
+        // planner front-end: a unit is spread over all warps of its CTA, so only the per-CTA unit count matters.
+        // Blocking calls want ~16 units per warp so that the tail of the dynamic schedule stays short; queries submitted on
+        // the lanes keep larger units — the tail of one query's scan is filled by the head of the next one's, so fewer unit
+        // boundaries win (1.25M x 768 shard: 3598 vs 3478 queries/s) — as long as every warp still gets a couple of units
+        // (a 100k-row store cut into 128-row units would leave two thirds of the warps without work).
+        const uint64_t per = c->pipelined ? 2 : 16;
+        const uint64_t want = planner ? (uint64_t)grid * per : (uint64_t)grid * W * per;
         while (unit_rows > 32 && n_rows / unit_rows < want) unit_rows >>= 1;
     }
     pl.unit_rows = unit_rows;

@@ -1,9 +1,43 @@
-//! Hand-written declarations of include/otters_b200.h (bindgen is not needed: the ABI is small and stable).
+//! Raw FFI declarations of libotters_b200.so — GENERATED from include/otters_b200.h by scripts/gen_rust_sys.py; do not edit.
 //! Every item mirrors the C header one to one; see the header for the reference lines each entry point replaces.
+//! tests/test_rust_sys.py keeps this file in step with the header and checks every repr(C) layout.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
 pub const OTTERS_OK: c_int = 0;
+pub const OTTERS_ERR_INVALID: c_int = 1;
+pub const OTTERS_ERR_CUDA: c_int = 2;
+pub const OTTERS_ERR_NOMEM: c_int = 3;
+pub const OTTERS_ERR_UNSUPPORTED: c_int = 4;
+pub const OTTERS_METRIC_COSINE: c_int = 0;
+pub const OTTERS_METRIC_EUCLIDEAN: c_int = 1;
+pub const OTTERS_METRIC_DOT: c_int = 2;
+pub const OTTERS_TAKE_MIN: c_int = 0;
+pub const OTTERS_TAKE_MAX: c_int = 1;
+pub const OTTERS_CMP_LT: c_int = 0;
+pub const OTTERS_CMP_GT: c_int = 1;
+pub const OTTERS_CMP_LTE: c_int = 2;
+pub const OTTERS_CMP_GTE: c_int = 3;
+pub const OTTERS_CMP_EQ: c_int = 4;
+pub const OTTERS_OP_EQ: c_int = 0;
+pub const OTTERS_OP_NEQ: c_int = 1;
+pub const OTTERS_OP_LT: c_int = 2;
+pub const OTTERS_OP_LTE: c_int = 3;
+pub const OTTERS_OP_GT: c_int = 4;
+pub const OTTERS_OP_GTE: c_int = 5;
+pub const OTTERS_DTYPE_INT32: c_int = 0;
+pub const OTTERS_DTYPE_INT64: c_int = 1;
+pub const OTTERS_DTYPE_FLOAT32: c_int = 2;
+pub const OTTERS_DTYPE_FLOAT64: c_int = 3;
+pub const OTTERS_DTYPE_STRING: c_int = 4;
+pub const OTTERS_DTYPE_DATETIME: c_int = 5;
+pub const OTTERS_LIT_I64: c_int = 0;
+pub const OTTERS_LIT_F64: c_int = 1;
+pub const OTTERS_LIT_STR: c_int = 2;
+pub const OTTERS_VECTORS_HOST: c_int = 0;
+pub const OTTERS_VECTORS_DEVICE: c_int = 1;
+pub const OTTERS_VECTORS_SYNTHETIC: c_int = 2;
+pub const OTTERS_EXCHANGE_SLOTS: c_int = 4;
 
 #[repr(C)]
 pub struct otters_ctx { _private: [u8; 0] }
@@ -13,25 +47,67 @@ pub struct otters_vecstore { _private: [u8; 0] }
 pub struct otters_metastore { _private: [u8; 0] }
 
 #[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct otters_scan_tuning {
+    pub warps_per_cta: u32,
+    pub slots_per_warp: u32,
+    pub kc_floats: u32,
+    pub ctas_per_sm: u32,
+    pub unit_rows: u32,
+    pub disable_fused_predicate: u32,
+    pub batch_mode: u32,
+    pub batch_cta_group: u32,
+    pub scan_mode: u32,
+    pub planners: u32,
+    pub timing: u32,
+    pub batch_passes: u32,
+    pub separate_select: u32,
+    pub lazy_prune: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct otters_last_work {
+    pub kernel_launches: u64,
+    pub rows_scored: u64,
+    pub scan_bytes: u64,
+    pub meta_bytes: u64,
+    pub scan_ms: f32,
+    pub prune_ms: f32,
+    pub rowmask_ms: f32,
+    pub select_ms: f32,
+    pub batch_used: u32,
+    pub batch_fallback: u32,
+    pub batch_candidates: u64,
+    pub batch_max_err: f32,
+    pub batch_delta: f32,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+    pub batch_passes: u32,
+    pub batch_attempts: u32,
+}
+
+#[repr(C)]
 #[derive(Clone, Copy)]
 pub struct otters_vec_query {
     pub queries: *const f32,
     pub nq: u32,
     pub dim: u32,
-    pub metric: i32,     // 0 Cosine, 1 Euclidean, 2 DotProduct  (src/vec.rs:11-16)
-    pub take_type: i32,  // 0 Min, 1 Max                          (src/vec.rs:18-22)
+    pub metric: i32,
+    pub take_type: i32,
     pub k: u64,
     pub has_filter: i32,
     pub thr: f32,
-    pub cmp: i32,        // 0 Lt, 1 Gt, 2 Lte, 3 Gte, 4 Eq         (src/vec.rs:24-31)
+    pub cmp: i32,
     pub row_mask_words: *const u64,
     pub row_mask_bits: u64,
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
 pub struct otters_column {
     pub name: *const c_char,
-    pub dtype: i32,      // 0 Int32, 1 Int64, 2 Float32, 3 Float64, 4 String, 5 DateTime (src/type_utils.rs:11-19)
+    pub dtype: i32,
     pub values: *const c_void,
     pub null_words: *const u64,
     pub str_offsets: *const u64,
@@ -39,6 +115,7 @@ pub struct otters_column {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
 pub struct otters_build_params {
     pub n_rows: u64,
     pub dim: u32,
@@ -56,7 +133,7 @@ pub struct otters_build_params {
 }
 
 #[repr(C)]
-#[derive(Default, Clone, Copy)]
+#[derive(Clone, Copy, Default)]
 pub struct otters_build_stats {
     pub n_rows: u64,
     pub dim: u64,
@@ -67,7 +144,7 @@ pub struct otters_build_stats {
 }
 
 #[repr(C)]
-#[derive(Default, Clone, Copy)]
+#[derive(Clone, Copy, Default)]
 pub struct otters_query_stats {
     pub total_chunks: u64,
     pub pruned_chunks: u64,
@@ -80,10 +157,11 @@ pub struct otters_query_stats {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
 pub struct otters_leaf {
     pub col: u32,
-    pub op: i32,     // 0 Eq, 1 Neq, 2 Lt, 3 Lte, 4 Gt, 5 Gte (src/expr.rs:83-91)
-    pub kind: i32,   // 0 I64, 1 F64, 2 Str
+    pub op: i32,
+    pub kind: i32,
     pub i: i64,
     pub f: f64,
     pub s: *const u8,
@@ -91,15 +169,23 @@ pub struct otters_leaf {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy)]
 pub struct otters_filter {
     pub n_clauses: u32,
     pub clause_offsets: *const u32,
     pub leaves: *const otters_leaf,
 }
 
-/// otters_shard_map: how local rows of a shard map to global row ids (contiguous or block-cyclic).
 #[repr(C)]
-#[derive(Default, Clone, Copy)]
+#[derive(Clone, Copy, Default)]
+pub struct otters_topk_record {
+    pub row: u64,
+    pub score: f32,
+    pub qid: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
 pub struct otters_shard_map {
     pub row_base: u64,
     pub world: u32,
@@ -107,17 +193,8 @@ pub struct otters_shard_map {
     pub block_rows: u64,
 }
 
-/// otters_topk_record: one entry of a shard's local top-k as it travels between GPUs.
 #[repr(C)]
 #[derive(Clone, Copy)]
-pub struct otters_topk_record {
-    pub row: u64,   // global row id; u64::MAX = empty slot
-    pub score: f32,
-    pub qid: u32,
-}
-
-/// otters_peer_exchange: record / flag areas of every rank as mapped into this process (CUDA IPC / VMM).
-#[repr(C)]
 pub struct otters_peer_exchange {
     pub world: u32,
     pub rank: u32,
@@ -126,56 +203,47 @@ pub struct otters_peer_exchange {
     pub peer_flags: *const *mut u32,
 }
 
-/// otters_scan_tuning: profiling knobs (0 = automatic everywhere); results never depend on them.
-#[repr(C)]
-#[derive(Default, Clone, Copy)]
-pub struct otters_scan_tuning {
-    pub warps_per_cta: u32,
-    pub slots_per_warp: u32,
-    pub kc_floats: u32,
-    pub ctas_per_sm: u32,
-    pub unit_rows: u32,
-    pub disable_fused_predicate: u32,
-    pub batch_mode: u32,       // 0 auto, 1 always the tcgen05 kernel for batches, 2 never
-    pub batch_cta_group: u32,  // 0 auto (CTA pairs), 1 single CTAs, 2 pairs
-    pub scan_mode: u32,        // K1 front-end: 0 auto, 1 autonomous warps, 2 planner + worker warps
-    pub planners: u32,         // planner warps per CTA (0 auto)
-    pub timing: u32,           // 0 auto, 1 always record phase events, 2 never
-    pub batch_passes: u32,     // 0 auto (single-pass tf32 selection, then 3xTF32), 1 single pass only, 3 3xTF32 only
-}
-
 extern "C" {
-    pub fn otters_ctx_set_tuning(ctx: *mut otters_ctx, t: *const otters_scan_tuning) -> c_int;
-    /// Row-sharded search, NCCL flavour: the local top-k stays in HBM as k records ...
-    pub fn otters_query_local_device(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query,
-                                     filter: *const otters_filter, map: *const otters_shard_map, d_records: *mut c_void,
-                                     stats: *mut otters_query_stats) -> c_int;
-    /// ... and after the all-gather every rank merges world * k records.
-    pub fn otters_topk_merge_device(ctx: *mut otters_ctx, d_records: *const c_void, n_records: u64, k: u64, take_type: i32,
-                                    out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64) -> c_int;
-    /// Row-sharded search with the exchange fused into the selection kernel (peer stores over NVLink, no NCCL call).
-    pub fn otters_query_exchange(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query,
-                                 filter: *const otters_filter, map: *const otters_shard_map, ex: *const otters_peer_exchange,
-                                 seq: u64, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64,
-                                 out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
-
     pub fn otters_ctx_create(device: c_int, cuda_stream: *mut c_void, out: *mut *mut otters_ctx) -> c_int;
     pub fn otters_ctx_destroy(ctx: *mut otters_ctx) -> c_int;
+    pub fn otters_ctx_synchronize(ctx: *mut otters_ctx) -> c_int;
+    pub fn otters_ctx_join(ctx: *mut otters_ctx) -> c_int;
     pub fn otters_last_error() -> *const c_char;
-
+    pub fn otters_version() -> *const c_char;
+    pub fn otters_ctx_set_tuning(ctx: *mut otters_ctx, t: *const otters_scan_tuning) -> c_int;
+    pub fn otters_ctx_last_work(ctx: *mut otters_ctx, out: *mut otters_last_work) -> c_int;
     pub fn otters_vecstore_create(ctx: *mut otters_ctx, dim: u32, out: *mut *mut otters_vecstore) -> c_int;
     pub fn otters_vecstore_destroy(vs: *mut otters_vecstore) -> c_int;
+    pub fn otters_vecstore_reserve(vs: *mut otters_vecstore, n_rows: u64) -> c_int;
     pub fn otters_vecstore_add(vs: *mut otters_vecstore, rows: *const f32, n: u64) -> c_int;
+    pub fn otters_vecstore_add_device(vs: *mut otters_vecstore, d_rows: *const f32, n: u64) -> c_int;
+    pub fn otters_vecstore_add_synthetic(vs: *mut otters_vecstore, first_row: u64, n: u64, seed: u64) -> c_int;
+    pub fn otters_vecstore_set_rows(vs: *mut otters_vecstore, rows: *const u64, data: *const f32, n: u64) -> c_int;
     pub fn otters_vecstore_len(vs: *const otters_vecstore) -> u64;
-    pub fn otters_vecstore_query(vs: *mut otters_vecstore, q: *const otters_vec_query, out_idx: *mut u64, out_score: *mut f32,
-                                 out_qid: *mut u32, cap: u64, out_len: *mut u64) -> c_int;
-
-    pub fn otters_metastore_build(ctx: *mut otters_ctx, p: *const otters_build_params, out: *mut *mut otters_metastore,
-                                  stats: *mut otters_build_stats) -> c_int;
+    pub fn otters_vecstore_dim(vs: *const otters_vecstore) -> u32;
+    pub fn otters_vecstore_inv_norms(vs: *const otters_vecstore, first: u64, n: u64, out: *mut f32) -> c_int;
+    pub fn otters_vecstore_query(vs: *mut otters_vecstore, q: *const otters_vec_query, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64) -> c_int;
+    pub fn otters_metastore_build(ctx: *mut otters_ctx, p: *const otters_build_params, out: *mut *mut otters_metastore, stats: *mut otters_build_stats) -> c_int;
     pub fn otters_metastore_destroy(ms: *mut otters_metastore) -> c_int;
+    pub fn otters_metastore_set_rows(ms: *mut otters_metastore, rows: *const u64, data: *const f32, n: u64) -> c_int;
     pub fn otters_metastore_n_chunks(ms: *const otters_metastore) -> u64;
-    pub fn otters_metastore_query(ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter,
-                                  out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64,
-                                  stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_metastore_chunk_size(ms: *const otters_metastore) -> u64;
+    pub fn otters_metastore_len(ms: *const otters_metastore) -> u64;
+    pub fn otters_metastore_query(ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_vecstore_query_batch(vs: *mut otters_vecstore, q: *const otters_vec_query, out_idx: *mut u64, out_score: *mut f32, out_len: *mut u64) -> c_int;
+    pub fn otters_metastore_query_batch(ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, out_idx: *mut u64, out_score: *mut f32, out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_metastore_gather(ms: *mut otters_metastore, col: u32, rows: *const u64, n: u64, out_values: *mut c_void, out_nulls: *mut u8) -> c_int;
+    pub fn otters_metastore_dict_entry(ms: *const otters_metastore, col: u32, code: u32, bytes: *mut *const u8, len: *mut u64) -> c_int;
     pub fn otters_metastore_last_stats(ms: *const otters_metastore, out: *mut otters_query_stats) -> c_int;
+    pub fn otters_metastore_chunk_mask(ms: *mut otters_metastore, filter: *const otters_filter, keep: *mut u8) -> c_int;
+    pub fn otters_metastore_row_mask(ms: *mut otters_metastore, filter: *const otters_filter, keep: *mut u8) -> c_int;
+    pub fn otters_metastore_zonemap_i64(ms: *const otters_metastore, col: u32, mn: *mut i64, mx: *mut i64, non_null: *mut u64) -> c_int;
+    pub fn otters_metastore_zonemap_f64(ms: *const otters_metastore, col: u32, mn: *mut f64, mx: *mut f64, non_null: *mut u64) -> c_int;
+    pub fn otters_metastore_inv_norms(ms: *const otters_metastore, first: u64, n: u64, out: *mut f32) -> c_int;
+    pub fn otters_query_local_device(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, map: *const otters_shard_map, d_records: *mut c_void, stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_query_exchange(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, map: *const otters_shard_map, ex: *const otters_peer_exchange, seq: u64, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_query_submit(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, map: *const otters_shard_map, ex: *const otters_peer_exchange, seq: u64, ticket: *mut u64) -> c_int;
+    pub fn otters_query_wait(ctx: *mut otters_ctx, ticket: u64, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_vecstore_add_synthetic_sharded(vs: *mut otters_vecstore, map: *const otters_shard_map, n_local: u64, seed: u64) -> c_int;
+    pub fn otters_topk_merge_device(ctx: *mut otters_ctx, d_records: *const c_void, n_records: u64, k: u64, take_type: i32, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64) -> c_int;
 }
