@@ -715,9 +715,12 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     rc = launch_batch_delta(q->metric, st->dim, passes, d_qmax2, st->d_minv_bits, d_delta, s);
     if (rc) return rc;
 
-    // single CTAs by default: with the raw-hi operand split they measured faster than CTA pairs (6.04 vs 6.33 ms on
-    // 1M x 768 x 1024 queries, profiles/r1_batch_experiments.log); tcgen05 cta_group::2 pairs stay selectable
-    const uint32_t cg = (c->tuning.batch_cta_group == 2 && c->sm_count >= 2) ? 2 : 1;
+    // the single-pass rung runs as CTA pairs (tcgen05 cta_group::2: each CTA stages half of the query tile, both CTAs' TMA loads
+    // credit the leader's barrier directly, three k-blocks per stage): 2.59 vs 3.03 ms on 1M x 768 x 1024 queries, same box
+    // (profiles/r2_k2_variants.log); the 3xTF32 rung stays on single CTAs (5.74 vs 5.99 ms, round 1)
+    const uint32_t cg_auto = passes == 1 ? 2u : 1u;
+    const uint32_t cg_want = c->tuning.batch_cta_group == 0 ? cg_auto : c->tuning.batch_cta_group;
+    const uint32_t cg = (cg_want == 2 && c->sm_count >= 2) ? 2 : 1;
     const uint32_t tile_rows = kBatchRows * cg;
     const uint32_t n_rowtiles = (uint32_t)((st->n + tile_rows - 1) / tile_rows);
     const uint64_t n_tiles = (uint64_t)n_rowtiles * (nq_pad / kBatchQueries);
@@ -754,6 +757,12 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bp.cta_qids = c->d_cta_qids;
     bp.cta_counts = c->d_cta_counts;
     bp.passes = passes;
+    {
+        static const int kps = getenv("OTTERS_K2_KPS") ? atoi(getenv("OTTERS_K2_KPS")) : 3;  // clamped in the kernel to leave two stages
+        static const int direct = getenv("OTTERS_K2_DIRECT") ? atoi(getenv("OTTERS_K2_DIRECT")) : 1;
+        bp.kps = (uint32_t)kps;
+        bp.pair_direct = (uint32_t)direct;
+    }
 #ifdef OTTERS_K2_EXPERIMENTS
     // timing experiments only (role-by-role timing of K2, scripts/dbg_passes_roles.py): results are garbage, so the hooks are
     // compiled out of the shipped library and a run with them on is never accepted (see below)

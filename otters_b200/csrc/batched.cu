@@ -55,6 +55,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// CTA pairs: the same load, but its transaction bytes are credited to the barrier at this shared-memory offset in the
+// pair's LEADER (bit 24 of a shared::cluster address is the CTA's rank inside the pair; clearing it addresses rank 0)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -367,8 +375,13 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     constexpr uint32_t MAX_STAGES = RING_BYTES / (A_BYTES + B_BYTES);  // single-pass stages hold V | Qhi only
     // the ring is cut at run time: 3xTF32 stages are Vhi | Vlo | Qhi | Qlo, single-pass stages V | Qhi (twice as many)
     const bool single = p.passes == 1;  // one tf32 MMA per product (selection with a wider error bound) instead of the 3xTF32 split
-    const uint32_t STAGE_BYTES = single ? A_BYTES + B_BYTES : G::STAGE_BYTES;
-    const uint32_t STAGES = single ? MAX_STAGES : G::STAGES;
+    // single pass only: KPS k-blocks share one stage = one barrier round trip and one tcgen05.commit;
+    // DIRECT (pairs): both CTAs' loads credit the leader's barrier themselves instead of going through the relay warp
+    const uint32_t KPS = !single ? 1u : (p.kps < 1u ? 1u : (p.kps > MAX_STAGES / 2u ? MAX_STAGES / 2u : p.kps));  // at least two stages
+    const bool direct = CG == 2 && single && p.pair_direct != 0u;
+    const uint32_t KB_BYTES = A_BYTES + B_BYTES;  // one single-pass k-block: V | Qhi
+    const uint32_t STAGE_BYTES = single ? KPS * KB_BYTES : G::STAGE_BYTES;
+    const uint32_t STAGES = single ? MAX_STAGES / KPS : G::STAGES;
     const uint32_t Q_OFF = single ? A_BYTES : 2 * A_BYTES;  // Qhi inside a stage
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x;
@@ -403,7 +416,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_cast[s], CG);  // one elected arrival per CTA of the pair
             mbar_init(&bar_empty[s], 1);
-            mbar_init(&bar_full2[s], CG);
+            mbar_init(&bar_full2[s], direct ? 1 : CG);  // direct: the leader's producer arrives once and expects both CTAs' bytes
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(&bar_tfull[b], 1);
@@ -430,6 +443,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     const uint32_t n_rowtiles = (p.n_rows + G::TILE_ROWS - 1) / G::TILE_ROWS;
     const uint32_t n_tiles = n_rowtiles * p.n_qtiles;
     const uint32_t nkb = p.nkb;
+    const uint32_t nst = (nkb + KPS - 1) / KPS;  // stage fills per tile
 
     if (warp == 0) {
         // ===== TMA producer (every CTA stages its own rows and its share of the query tile) =====
@@ -438,19 +452,40 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
             for (uint32_t t = unit; t < n_tiles; t += n_units) {
                 const uint32_t rt = t / p.n_qtiles, qt = t % p.n_qtiles;
                 if (!tile_live<CG>(p, rt)) continue;
-                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                for (uint32_t ks = 0; ks < nst; ++ks, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&bar_empty[s], ph ^ 1u);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     if (p.dbg & 1u) {  // timing experiment: no loads
-                        mbar_arrive_expect_tx(&bar_full[s], 0);
+                        if (!direct) mbar_arrive_expect_tx(&bar_full[s], 0);
+                        else if (rank == 0) mbar_arrive_expect_tx(&bar_full2[s], 0);
                         continue;
                     }
-                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + (single ? 1u : 2u) * B_BYTES);
+                    if (single) {
+                        const uint32_t nk = nkb - ks * KPS < KPS ? nkb - ks * KPS : KPS;  // k-blocks in this fill
+                        if (direct) {
+                            if (rank == 0) mbar_arrive_expect_tx(&bar_full2[s], 2u * nk * KB_BYTES);
+                        } else {
+                            mbar_arrive_expect_tx(&bar_full[s], nk * KB_BYTES);
+                        }
+                        for (uint32_t j = 0; j < nk; ++j) {
+                            const uint32_t kb = ks * KPS + j;
+                            uint8_t* blk = st + j * KB_BYTES;
+                            if (direct) {
+                                tma_load_2d_pair(blk, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full2[s]);
+                                tma_load_2d_pair(blk + A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full2[s]);
+                            } else {
+                                tma_load_2d(blk, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full[s]);
+                                tma_load_2d(blk + A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
+                            }
+                        }
+                        continue;
+                    }
+                    const uint32_t kb = ks;
+                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + 2u * B_BYTES);
                     tma_load_2d(st, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full[s]);
                     tma_load_2d(st + Q_OFF, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
-                    if (!single)
-                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tm_ql, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
                 }
             }
         }
@@ -466,7 +501,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 else mbar_wait(&bar_tempty[buf], bph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                for (uint32_t kb = 0; kb < nst; ++kb, ++it) {  // kb counts stage fills (= k-blocks unless KPS > 1)
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t d_vh = umma_desc_sw128(sa), d_vl = umma_desc_sw128(sa + A_BYTES);
@@ -476,10 +511,14 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                         if constexpr (CG == 2) mbar_wait_cluster(&bar_full2[s], ph);
                         else mbar_wait(&bar_full[s], ph);
                         tc_fence_after();
+                        const uint32_t nk = nkb - kb * KPS < KPS ? nkb - kb * KPS : KPS;
+                        for (uint32_t j = 0; j < nk; ++j) {
+                            const uint64_t blk = (uint64_t)((j * KB_BYTES) >> 4);  // descriptor start addresses count 16-byte units
 #pragma unroll
-                        for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
-                            const uint64_t adv = (uint64_t)((kk * UK * 4) >> 4);
-                            umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, (kb | kk) != 0 ? 1u : 0u);
+                            for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
+                                const uint64_t adv = blk + (uint64_t)((kk * UK * 4) >> 4);
+                                umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, (kb | j | kk) != 0 ? 1u : 0u);
+                            }
                         }
                     } else if (raw_hi) {
                         // the landed fp32 tile itself is the hi operand (the tensor core reads its upper 19 bits), so two
@@ -522,12 +561,12 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         }
     } else if (warp == 3) {
         // ===== relay (CTA pairs with raw hi operands): tells rank 0 that this CTA's loads of a stage have landed =====
-        if (CG == 2 && raw_hi && lane == 0) {
+        if (CG == 2 && raw_hi && !direct && lane == 0) {
             uint32_t it = 0;
             for (uint32_t t = unit; t < n_tiles; t += n_units) {
                 const uint32_t rt = t / p.n_qtiles;
                 if (!tile_live<CG>(p, rt)) continue;
-                for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+                for (uint32_t kb = 0; kb < nst; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                     mbar_wait(&bar_full[s], ph);
                     if (rank != 0) mbar_arrive_remote(&bar_full2[s], 0);

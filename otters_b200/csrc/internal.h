@@ -216,6 +216,8 @@ struct BatchParams {
     uint32_t* cta_qids;          // [grid][k]
     uint32_t* cta_counts;        // [grid]
     uint32_t passes;             // tf32 MMAs per product: 3 (3xTF32 split, fp32-faithful) or 1 (selection only, wider error bound)
+    uint32_t kps;                // single pass: k-blocks per pipeline stage (1 or 2: one barrier round trip and one commit for two)
+    uint32_t pair_direct;        // CTA pairs, single pass: both CTAs' TMA loads credit the leader's barrier themselves (no relay warp)
     uint32_t dbg;                // timing experiments only (OTTERS_BATCH_DBG): 1 no loads, 2 no split, 4 no epilogue, 8 no MMAs
 };
 struct BatchLaunch {
