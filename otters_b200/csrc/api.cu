@@ -976,6 +976,12 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     sp.rows_scored = c->d_rows_scored;
     sp.g_tau = reinterpret_cast<unsigned long long*>(c->d_ctrl + 96);  // zeroed with the control block
     {
+        // unit ids claimed ahead per claiming warp: two (same-box A/B, profiles/r2_claim_depth.txt: 10M x 128 filtered 2054 -> 2111
+        // q/s, 100k x 128 44.6k -> 47.5k; four ids are no better and starve late warps on small stores)
+        static const int depth_env = getenv("OTTERS_CLAIM_DEPTH") ? atoi(getenv("OTTERS_CLAIM_DEPTH")) : 0;
+        sp.claim_depth = depth_env ? (uint32_t)std::min(std::max(depth_env, 1), 4) : 2u;
+    }
+    {
         static const int pred_seq = getenv("OTTERS_PRED_SEQ") ? atoi(getenv("OTTERS_PRED_SEQ")) : 1;
         static const int no_prefetch = getenv("OTTERS_NO_PREFETCH") ? atoi(getenv("OTTERS_NO_PREFETCH")) : 0;
         sp.pred_seq = pred_seq;

@@ -163,6 +163,7 @@ struct ScanParams {
     uint32_t emit_cap;
     // instrumentation
     unsigned long long* rows_scored;
+    uint32_t claim_depth;       // unit ids every claiming warp keeps in flight (1..4)
     uint32_t pred_seq, no_prefetch;  // experiment switches (OTTERS_PRED_SEQ / OTTERS_NO_PREFETCH)
     // fused selection: the last CTA to publish its list (ticket from done_counter) runs K3 itself — one launch per query
     uint32_t fuse_select;

@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     const uint64_t l2pol = policy_evict_first();
 
     // ---- producer state ----
-    uint32_t u_pref = 0;  // lane 0: prefetched unit id
+    UnitClaims claims;  // lane 0: the next unit ids, claimed ahead of time (scan_shared.cuh)
     unsigned long long g_pref = 0;  // lane 0: grid-wide threshold read together with the unit id
-    if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
+    claims.prime(p.unit_counter, p.claim_depth, lane);
     uint32_t list_n = 0, list_pos = 0, unit_row0 = 0, kc_i = 0, tile_cnt = 0;
     bool prod_done = false;
     uint32_t prod_step = 0, cons_step = 0;
@@ -97,17 +97,18 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     auto prepare = [&]() {
         uint8_t* nlist = rowlist + (cur_buf ^ 1u) * kMaxUnitRows;
         while (!nvalid) {
-            uint32_t u = __shfl_sync(FULL, u_pref, 0);
+            uint32_t u = claims.front();
             if (u >= p.n_units) {
                 claim_done = true;
                 return;
             }
             if (lane == 0) {
-                // adopt what the other CTAs have found so far (value read one unit ago: no extra round trip)
-                if (!EMIT_ALL && g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
-                u_pref = atomicAdd(p.unit_counter, 1u);
-                if (!EMIT_ALL && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
+                // adopt what the other CTAs have found so far (once per round of claims; the value was read a round ago)
+                if (!EMIT_ALL && !claims.phase && g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
+                claims.refill(p.unit_counter);
+                if (!EMIT_ALL && !claims.phase && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
             }
+            claims.advance(p.claim_depth);
             // guided schedule: the first n_big units are unit_rows long, the rest (the tail of the store, claimed last)
             // unit_small long, so that the warps run out of work within one SMALL unit of each other
             const bool big = u < p.n_big;

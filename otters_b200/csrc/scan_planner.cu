@@ -94,19 +94,20 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
     unsigned long long scored = 0;
     if (warp < (int)np) {
         // =============================== planner ===============================
-        uint32_t u_pref = 0;
+        UnitClaims claims;  // lane 0: the next unit ids, claimed ahead of time (scan_shared.cuh)
         unsigned long long g_pref = 0;  // grid-wide threshold, read together with the unit id
         unsigned long long st_chunks = 0, st_vecs = 0;  // lazy pruning: chunks kept / rows of kept chunks x queries (per lane)
-        if (lane == 0) u_pref = atomicAdd(p.unit_counter, 1u);
+        claims.prime(p.unit_counter, p.claim_depth, lane);
         for (;;) {
-            const uint32_t u = __shfl_sync(FULL, u_pref, 0);
+            const uint32_t u = claims.front();
             if (u >= p.n_units) break;
             if (lane == 0) {
-                // adopt what the other CTAs have found so far (value read one unit ago: no extra round trip)
-                if (g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
-                u_pref = atomicAdd(p.unit_counter, 1u);
-                if (p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
+                // adopt what the other CTAs have found so far (once per round of claims; the value was read a round ago)
+                if (!claims.phase && g_pref > ld_volatile_u64(&hdr->tau)) atomicMax(&hdr->tau, g_pref);
+                claims.refill(p.unit_counter);
+                if (!claims.phase && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
             }
+            claims.advance(p.claim_depth);
             // guided schedule (see scan.cu): big units first, small units for the tail of the store
             const bool big = u < p.n_big;
             const uint32_t urows = big ? p.unit_rows : p.unit_small;

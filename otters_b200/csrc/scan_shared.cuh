@@ -105,5 +105,40 @@ __device__ inline void warp_push(CtaHdr* hdr, uint64_t* buf, uint32_t cap, uint3
 }
 
 
+// Unit ids claimed ahead of time.  The atomic on the (single, hot) unit counter takes 1-3 us under load, and a run of dead
+// units is worked off faster than one claim returns: with a single id in flight the shuffle that broadcasts it was ~10 % of
+// the stall samples on the filtered 10M x 128 workload (profiles/r2_scan_c3_hot_sass.txt).  Up to four ids are kept in flight
+// in four registers used round-robin (a uniform switch: no instruction touches a register whose atomic is still pending);
+// the depth is chosen on the host so that small stores do not starve late warps (ScanParams::claim_depth).
+struct UnitClaims {
+    uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0, phase = 0;
+    __device__ __forceinline__ void prime(uint32_t* counter, uint32_t depth, int lane) {
+        if (lane != 0) return;
+        u0 = atomicAdd(counter, 1u);
+        if (depth > 1) u1 = atomicAdd(counter, 1u);
+        if (depth > 2) u2 = atomicAdd(counter, 1u);
+        if (depth > 3) u3 = atomicAdd(counter, 1u);
+    }
+    // the oldest claimed id, broadcast to the warp
+    __device__ __forceinline__ uint32_t front() const {
+        switch (phase) {
+        case 0: return __shfl_sync(FULL, u0, 0);
+        case 1: return __shfl_sync(FULL, u1, 0);
+        case 2: return __shfl_sync(FULL, u2, 0);
+        default: return __shfl_sync(FULL, u3, 0);
+        }
+    }
+    // lane 0: replace the id just taken by a new claim
+    __device__ __forceinline__ void refill(uint32_t* counter) {
+        switch (phase) {
+        case 0: u0 = atomicAdd(counter, 1u); break;
+        case 1: u1 = atomicAdd(counter, 1u); break;
+        case 2: u2 = atomicAdd(counter, 1u); break;
+        default: u3 = atomicAdd(counter, 1u); break;
+        }
+    }
+    __device__ __forceinline__ void advance(uint32_t depth) { phase = phase + 1u >= depth ? 0u : phase + 1u; }
+};
+
 }  // namespace scan_detail
 }  // namespace otters
