@@ -190,6 +190,10 @@ struct otters_ctx {
     uint32_t next_lane = 0;
     uint64_t tickets = 0;
     Pending pend;
+    // what otters_ctx_last_work reports after otters_query_wait: the waited query's counters (lane 0 shares `last` with the
+    // query it has in flight, so the report is kept apart); a blocking call on this context switches back to `last`
+    otters_last_work reported{};
+    bool report_waited = false;
 };
 
 namespace otters {
@@ -288,6 +292,7 @@ static int begin_query(otters_ctx* c) {
     c->timed_single = c->timed_meta = c->timed_rowmask = false;
     c->timing = c->tuning.timing == 1;
     c->want_host_result = false;
+    if (!c->pipelined) c->report_waited = false;  // a blocking call: otters_ctx_last_work reports it
     return OTTERS_OK;
 }
 
@@ -1299,7 +1304,7 @@ extern "C" int otters_ctx_set_tuning(otters_ctx* c, const otters_scan_tuning* t)
 
 extern "C" int otters_ctx_last_work(otters_ctx* c, otters_last_work* out) {
     if (!c || !out) return fail(OTTERS_ERR_INVALID, "null argument");
-    *out = c->last;
+    *out = c->report_waited ? c->reported : c->last;
     return OTTERS_OK;
 }
 
@@ -2695,6 +2700,7 @@ static int query_batch_impl(otters_vecstore* vs, otters_metastore* ms, const ott
         return rc;
     }
     parent->last = total;
+    parent->report_waited = false;
     if (ms) {
         // statistics of the batch as the reference reports them: chunks once, vectors_compared = sum over chunks of len * Q
         st_first.vectors_compared *= q->nq;
@@ -2772,7 +2778,8 @@ extern "C" int otters_query_wait(otters_ctx* parent, uint64_t ticket, uint64_t* 
     DeviceGuard g(c->device);
     int rc = c->pend.meta ? meta_finish(c, &c->pend, true, out_idx, out_score, out_qid, cap, out_len, stats)
                           : vec_finish(c, &c->pend, true, out_idx, out_score, out_qid, cap, out_len);
-    if (c != parent) parent->last = c->last;
+    parent->reported = c->last;
+    parent->report_waited = true;
     return rc;
 }
 
