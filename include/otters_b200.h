@@ -103,9 +103,11 @@ typedef struct {
     uint32_t planners;     /* planner front-end: planner warps per CTA (0 = automatic: 2 for filtered stores up to 256-d, else 1) */
     uint32_t timing;       /* per-phase CUDA events (otters_last_work *_ms, otters_query_stats durations): 0 = automatic (only
                               for blocking MetaStore queries that ask for stats), 1 = always, 2 = never */
-    uint32_t batch_passes; /* tensor-core kernel: 0 = automatic (single-pass tf32 selection first, 3xTF32 when its certificate
-                              fails), 1 = single pass only, 3 = 3xTF32 only.  Results never change: every returned score is
-                              re-computed in the reference's arithmetic and the selection is certified or redone */
+    uint32_t batch_passes; /* tensor-core kernel, arithmetic rung of the SELECTION: 0 = automatic (bf16 operands from a bf16 shadow
+                              of the rows when device memory allows, then single-pass tf32, then 3xTF32, each tried when the
+                              certificate of the one before fails), 1 = single-pass tf32 only, 2 = bf16 only, 3 = 3xTF32 only.
+                              Results never change: every returned score is re-computed in the reference's arithmetic from the
+                              fp32 rows and the selection is certified or redone */
     uint32_t separate_select; /* 1: run the final selection (K3) as its own kernel instead of in the last CTA of the scan kernel */
     uint32_t lazy_prune;      /* 1: evaluate the zonemap / Bloom chunk rules lazily inside the scan kernel (per work unit) instead
                                  of running K0 first: one launch per query, but measured slower — every unit pays a dependent
@@ -130,7 +132,7 @@ typedef struct {
     float batch_delta;          /* the error bound the selection assumed (must exceed batch_max_err) */
     uint64_t h2d_bytes;         /* host-to-device bytes of the last query (input image: control block + filter + queries; row mask) */
     uint64_t d2h_bytes;         /* device-to-host bytes of the last query (result header + candidates / stats) */
-    uint32_t batch_passes;      /* tf32 MMAs per product of the accepted tensor-core run: 1 or 3 (0: K2 not used) */
+    uint32_t batch_passes;      /* rung of the accepted tensor-core run: 2 = bf16, 1 = single-pass tf32, 3 = 3xTF32 (0: K2 not used) */
     uint32_t batch_attempts;    /* tensor-core runs made for the last query (a failed certificate costs one) */
 } otters_last_work;
 OTTERS_API int otters_ctx_last_work(otters_ctx *ctx, otters_last_work *out);

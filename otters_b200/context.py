@@ -44,7 +44,8 @@ class Context:
         batch_cta_group: 0 = automatic (single CTAs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2).
         scan_mode: K1 front-end, 0 = automatic, 1 = autonomous warps, 2 = planner + worker warps; planners: planner warps per CTA.
         timing: per-phase CUDA events; 0 = only for blocking MetaStore queries with stats, 1 = always, 2 = never.
-        batch_passes: tensor-core kernel, 0 = single-pass tf32 selection first and 3xTF32 if its certificate fails, 1 / 3 = only that.
+        batch_passes: tensor-core kernel, 0 = bf16 selection first (bf16 shadow rows), then single-pass tf32, then 3xTF32, each when the
+        certificate of the one before fails; 1 (tf32 single pass) / 2 (bf16) / 3 (3xTF32) = only that rung.
         separate_select: 1 = run the final selection (K3) as its own kernel instead of in the last CTA of the scan kernel.
         lazy_prune: 1 = evaluate the chunk rules (K0) per work unit inside the scan kernel instead of as their own kernel."""
         t = _ffi.ScanTuning(warps_per_cta, slots_per_warp, kc_floats, ctas_per_sm, unit_rows, disable_fused_predicate, batch_mode,

@@ -129,6 +129,8 @@ struct otters_ctx {
     float* d_qh = nullptr;              // hi / lo tf32 split of the staged queries, padded to 256-query tiles
     float* d_ql = nullptr;
     size_t d_qh_floats = 0, d_ql_floats = 0;
+    uint16_t* d_qb = nullptr;           // bf16 copy of the staged queries (bf16 rung), padded to 256-query tiles
+    size_t d_qb_elems = 0;
     float* d_qscal = nullptr;           // per-query scalar: 1/|q| (cosine) or |q|^2 (euclidean)
     size_t d_qscal_floats = 0;
     uint32_t* d_cta_qids = nullptr;     // [grid_max][kMaxFusedK]
@@ -387,6 +389,12 @@ struct VecStorage {
     float* d_inv = nullptr;
     uint32_t* d_minv_bits = nullptr;  // smallest positive inverse row norm (float bits), for the batched path's error bound
     bool minv_valid = false;
+    // bf16 SHADOW of the rows for K2's bf16 rung: selection only (scores are always re-computed from the fp32 rows), built on
+    // the first query batch that wants it when memory allows (ensure_bf16_shadow), dropped whenever the rows change
+    uint16_t* d_rows_h = nullptr;
+    uint64_t pitch_h = 0, h_cap_rows = 0, h_declined_n = 0;
+    bool h_valid = false;
+    uint32_t bf16_backoff = 0;         // batches left that skip the bf16 rung (its certificate failed on this store)
 
     int reserve(uint64_t want) {
         if (want <= cap) return OTTERS_OK;
@@ -441,6 +449,7 @@ struct VecStorage {
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be reused after return
         n += cnt;
         minv_valid = false;
+        h_valid = false;
         return OTTERS_OK;
     }
     int add_synth(ShardMap gen_map, uint64_t cnt, uint64_t seed) {
@@ -455,6 +464,7 @@ struct VecStorage {
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
         n += cnt;
         minv_valid = false;
+        h_valid = false;
         return OTTERS_OK;
     }
     // overwrites individual rows (host data, dim floats each) and recomputes their inverse norms
@@ -469,15 +479,20 @@ struct VecStorage {
         }
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
         minv_valid = false;
+        h_valid = false;
         return OTTERS_OK;
     }
     void release() {
         cudaFree(d_rows);
         cudaFree(d_inv);
         cudaFree(d_minv_bits);
+        cudaFree(d_rows_h);
         d_rows = d_inv = nullptr;
         d_minv_bits = nullptr;
+        d_rows_h = nullptr;
+        h_cap_rows = h_declined_n = 0;
         minv_valid = false;
+        h_valid = false;
         n = cap = 0;
     }
 };
@@ -670,6 +685,48 @@ static int store_min_inv_norm(otters_ctx* c, VecStorage* st) {
     return OTTERS_OK;
 }
 
+// The bf16 shadow costs half of the store again; in automatic mode it is built only when that leaves the device half empty.
+static int ensure_bf16_shadow(otters_ctx* c, VecStorage* st, bool force, bool* ok) {
+    *ok = false;
+    if (st->h_valid) {
+        *ok = true;
+        return OTTERS_OK;
+    }
+    const uint64_t pitch_h = round_up(st->dim, 8);
+    const size_t bytes = (size_t)st->n * pitch_h * 2;
+    if (st->d_rows_h && (st->h_cap_rows < st->n || st->pitch_h != pitch_h)) {
+        OTTERS_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(st->d_rows_h);
+        st->d_rows_h = nullptr;
+        st->h_cap_rows = 0;
+    }
+    if (!st->d_rows_h) {
+        if (!force) {
+            if (st->h_declined_n == st->n) return OTTERS_OK;
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr < 2 * bytes + ((size_t)1 << 30) || fr - bytes < tot / 2) {
+                cudaGetLastError();
+                st->h_declined_n = st->n;
+                return OTTERS_OK;
+            }
+        }
+        if (cudaMalloc((void**)&st->d_rows_h, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+            cudaGetLastError();
+            st->d_rows_h = nullptr;
+            st->h_declined_n = st->n;
+            return OTTERS_OK;
+        }
+        st->h_cap_rows = st->n;
+        st->pitch_h = pitch_h;
+    }
+    int rc = launch_convert_bf16(st->d_rows, st->pitch, st->n, st->dim, st->d_rows_h, pitch_h, st->n, c->stream);
+    if (rc) return rc;
+    OTTERS_CUDA(cudaStreamSynchronize(c->stream));  // other contexts / lanes may use the shadow from their own streams
+    st->h_valid = true;
+    *ok = true;
+    return OTTERS_OK;
+}
+
 static bool batch_eligible(const otters_ctx* c, const otters_vec_query* q, uint64_t n_rows, uint64_t k_eff) {
     const uint32_t mode = c->tuning.batch_mode;
     if (mode == 2 || q->nq < 2 || k_eff == 0 || k_eff > kMaxFusedK || n_rows == 0) return false;
@@ -719,11 +776,19 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (rc) return rc;
     rc = launch_batch_delta(q->metric, st->dim, passes, d_qmax2, st->d_minv_bits, d_delta, s);
     if (rc) return rc;
+    const uint32_t q_pitch_h = (uint32_t)round_up(st->dim, 8);
+    if (passes == 2) {
+        if (!st->h_valid) return fail(OTTERS_ERR_INVALID, "the bf16 rung was requested without its shadow rows");
+        rc = ensure_dev(&c->d_qb, &c->d_qb_elems, (size_t)nq_pad * q_pitch_h, s);
+        if (rc) return rc;
+        rc = launch_convert_bf16(c->d_query, dim_pad, q->nq, st->dim, c->d_qb, q_pitch_h, nq_pad, s);
+        if (rc) return rc;
+    }
 
     // the single-pass rung runs as CTA pairs (tcgen05 cta_group::2: each CTA stages half of the query tile, both CTAs' TMA loads
     // credit the leader's barrier directly, three k-blocks per stage): 2.59 vs 3.03 ms on 1M x 768 x 1024 queries, same box
     // (profiles/r2_k2_variants.log); the 3xTF32 rung stays on single CTAs (5.74 vs 5.99 ms, round 1)
-    const uint32_t cg_auto = passes == 1 ? 2u : 1u;
+    const uint32_t cg_auto = passes != 3 ? 2u : 1u;
     const uint32_t cg_want = c->tuning.batch_cta_group == 0 ? cg_auto : c->tuning.batch_cta_group;
     const uint32_t cg = (cg_want == 2 && c->sm_count >= 2) ? 2 : 1;
     const uint32_t tile_rows = kBatchRows * cg;
@@ -737,6 +802,10 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bl.dim_pad = dim_pad;
     bl.q_hi = c->d_qh;
     bl.q_lo = c->d_ql;
+    bl.v_half = st->d_rows_h;
+    bl.pitch_h = st->pitch_h;
+    bl.q_half = c->d_qb;
+    bl.q_pitch_h = q_pitch_h;
     bl.nq_pad = nq_pad;
     bl.cta_group = cg;
     bl.grid = (uint32_t)std::min<uint64_t>((uint64_t)(c->sm_count / cg), n_tiles) * cg;
@@ -827,7 +896,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         if (rc) return rc;
     }
     rec_event(c, 5);
-    c->last.kernel_launches += 8 + (d_records_out ? 1 : 0);
+    c->last.kernel_launches += 8 + (d_records_out ? 1 : 0) + (passes == 2 ? 1 : 0);
 
     // fetch header + candidates and verify the selection
     const size_t bytes = sizeof(ResultHeader) + (size_t)k_eff * sizeof(Cand);
@@ -897,10 +966,29 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         // selection runs single-pass tf32 first (a third of the MMAs and of the operand traffic; error bound 2^-9 |q||v|);
         // when its certificate fails the batch is redone with the 3xTF32 split (2^-15), and only then query by query.
         // A store whose single-pass certificate failed goes straight to 3xTF32 for its next kSinglePassBackoff batches.
+        // The bf16 rung (a bf16 shadow of the rows, half the operand bytes and twice the MMA rate, bound 2^-7 |q||v|) goes first
+        // when the shadow exists or can be built; every rung is selection only and carries the same kind of certificate.
         const uint32_t want = c->tuning.batch_passes;
+        bool accepted = false;
+        if (want == 2 || (want == 0 && st->bf16_backoff == 0)) {
+            bool have = false;
+            rc = ensure_bf16_shadow(c, st, want == 2, &have);
+            if (rc) return rc;
+            if (want == 2 && !have) return fail(OTTERS_ERR_NOMEM, "device allocation for the bf16 shadow rows failed");
+            if (have) {
+                rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, 2, &accepted);
+                if (rc) return rc;
+                if (accepted) return OTTERS_OK;
+                if (want == 0) st->bf16_backoff = kSinglePassBackoff;
+                rc = reset_scan_state(c);
+                if (rc) return rc;
+                c->last.batch_fallback = want == 2 ? 1 : 0;
+            }
+        } else if (want == 0 && st->bf16_backoff) {
+            st->bf16_backoff -= 1;
+        }
         const bool try_single = want == 1 || (want == 0 && st->single_pass_backoff == 0);
         if (want == 0 && st->single_pass_backoff) st->single_pass_backoff -= 1;
-        bool accepted = false;
         if (try_single) {
             rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, 1, &accepted);
             if (rc) return rc;
@@ -909,7 +997,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
             rc = reset_scan_state(c);
             if (rc) return rc;
         }
-        if (want != 1) {
+        if (want != 1 && want != 2) {
             c->last.batch_fallback = 0;
             rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, 3, &accepted);
             if (rc) return rc;
@@ -1258,6 +1346,7 @@ extern "C" int otters_ctx_destroy(otters_ctx* c) {
     cudaFree(c->d_emit);
     cudaFree(c->d_qh);
     cudaFree(c->d_ql);
+    cudaFree(c->d_qb);
     cudaFree(c->d_qscal);
     cudaFree(c->d_cta_qids);
     if (c->h_stage) cudaFreeHost(c->h_stage);

@@ -21,6 +21,10 @@
 //   reference's exact arithmetic order (same code shape as K1), applies the exact vec_filter, and the
 //   final order comes from the exact keys.  The host verifies that no excluded pair can reach the
 //   result (approximate cut + error bound < exact k-th score) and otherwise falls back to K1 per query.
+//   Rungs (BatchParams::passes): 2 = one kind::f16 MMA per k-step on a bf16 SHADOW of the store rows and bf16 queries
+//   (half the operand bytes, twice the MMA rate; bound 2^-7 |q||v|), 1 = one kind::tf32 MMA on the fp32 rows (2^-9),
+//   3 = the 3xTF32 split (2^-15).  A k-block is one 128-byte swizzle atom in every rung: 32 fp32 or 64 bf16 columns,
+//   so stages, barriers and descriptors are byte-identical between rungs 1 and 2.
 #include <cuda.h>  // CUtensorMap types only; the encoder is resolved through cudaGetDriverEntryPoint
 #include <float.h>
 
@@ -273,6 +277,8 @@ struct Geo {
     static constexpr uint32_t STAGES = (192u * 1024u) / STAGE_BYTES;  // 2 / 3 at 128-byte k-blocks, 4 / 6 at 64-byte ones
     static constexpr uint32_t TILE_ROWS = BM * CG;
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
+    // kind::f16: same fields, A / B format = 1 (bf16), fp32 accumulate
+    static constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((TILE_ROWS >> 4) << 24);
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -320,6 +326,25 @@ __device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t adesc, ui
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// the bf16 rung: kind::f16 with bf16 operands (K = 16 per instruction = the same 32 bytes per row as 8 tf32 columns)
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     }
@@ -374,7 +399,9 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
     constexpr uint32_t RING_BYTES = G::STAGES * G::STAGE_BYTES;
     constexpr uint32_t MAX_STAGES = RING_BYTES / (A_BYTES + B_BYTES);  // single-pass stages hold V | Qhi only
     // the ring is cut at run time: 3xTF32 stages are Vhi | Vlo | Qhi | Qlo, single-pass stages V | Qhi (twice as many)
-    const bool single = p.passes == 1;  // one tf32 MMA per product (selection with a wider error bound) instead of the 3xTF32 split
+    const bool single = p.passes != 3;  // one MMA per product (selection with a wider error bound) instead of the 3xTF32 split
+    const bool half = p.passes == 2;    // ... on bf16 operands (tm_v / tm_qh then describe the bf16 shadow arrays)
+    const uint32_t kcols = half ? 2u * BK : BK;  // columns of one k-block: one swizzle atom of bf16 or of fp32
     // single pass only: KPS k-blocks share one stage = one barrier round trip and one tcgen05.commit;
     // DIRECT (pairs): both CTAs' loads credit the leader's barrier themselves instead of going through the relay warp
     const uint32_t KPS = !single ? 1u : (p.kps < 1u ? 1u : (p.kps > MAX_STAGES / 2u ? MAX_STAGES / 2u : p.kps));  // at least two stages
@@ -472,11 +499,11 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                             const uint32_t kb = ks * KPS + j;
                             uint8_t* blk = st + j * KB_BYTES;
                             if (direct) {
-                                tma_load_2d_pair(blk, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full2[s]);
-                                tma_load_2d_pair(blk + A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full2[s]);
+                                tma_load_2d_pair(blk, &tm_v, (int)(kb * kcols), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full2[s]);
+                                tma_load_2d_pair(blk + A_BYTES, &tm_qh, (int)(kb * kcols), (int)(qt * BN + rank * G::BN_LOAD), &bar_full2[s]);
                             } else {
-                                tma_load_2d(blk, &tm_v, (int)(kb * BK), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full[s]);
-                                tma_load_2d(blk + A_BYTES, &tm_qh, (int)(kb * BK), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
+                                tma_load_2d(blk, &tm_v, (int)(kb * kcols), (int)(rt * G::TILE_ROWS + rank * BM), &bar_full[s]);
+                                tma_load_2d(blk + A_BYTES, &tm_qh, (int)(kb * kcols), (int)(qt * BN + rank * G::BN_LOAD), &bar_full[s]);
                             }
                         }
                         continue;
@@ -507,7 +534,8 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                     const uint64_t d_vh = umma_desc_sw128(sa), d_vl = umma_desc_sw128(sa + A_BYTES);
                     const uint64_t d_qh = umma_desc_sw128(sa + Q_OFF), d_ql = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
                     if (single) {
-                        // single-pass selection: one tf32 MMA per k-step on the landed tiles (V read at 19 bits, Q rounded)
+                        // single-pass selection: one MMA per k-step on the landed tiles (tf32: V read at 19 bits, Q rounded;
+                        // bf16: both operands were rounded when their shadow arrays were written)
                         if constexpr (CG == 2) mbar_wait_cluster(&bar_full2[s], ph);
                         else mbar_wait(&bar_full[s], ph);
                         tc_fence_after();
@@ -516,8 +544,9 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                             const uint64_t blk = (uint64_t)((j * KB_BYTES) >> 4);  // descriptor start addresses count 16-byte units
 #pragma unroll
                             for (uint32_t kk = 0; kk < ((p.dbg & 8u) ? 0u : BK / UK); ++kk) {
-                                const uint64_t adv = blk + (uint64_t)((kk * UK * 4) >> 4);
-                                umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, (kb | j | kk) != 0 ? 1u : 0u);
+                                const uint64_t adv = blk + (uint64_t)((kk * UK * 4) >> 4);  // 32 bytes per k-step in both formats
+                                if (half) umma_bf16_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC_BF16, (kb | j | kk) != 0 ? 1u : 0u);
+                                else umma_tf32_cg<CG>(d_tmem, d_vh + adv, d_qh + adv, G::IDESC, (kb | j | kk) != 0 ? 1u : 0u);
                             }
                         }
                     } else if (raw_hi) {
@@ -810,7 +839,13 @@ __global__ void batch_delta_kernel(int metric, uint32_t dim, uint32_t passes, co
     // tensor core's internal alignment, not something the runtime check can see for the EXCLUDED pairs.  The measured error
     // is 20-90x below the bound, so doubling it (single pass) / quadrupling it (3xTF32, whose margin was only ~5 %) costs
     // almost no extra fallbacks.
-    const double kappa = passes == 1 ? 2.0 * ldexp(1.0, -9) * fmax(1.0, (double)dim / 1024.0) : 4.0 * ldexp(1.0, -15) * fmax(1.0, (double)dim / 640.0);
+    // bf16 rung: both operands were rounded to nearest-even at 8 significant bits by convert_bf16_kernel — an error this library
+    //   produces itself, (1 + 2^-8)^2 - 1 = 2^-7 + 2^-16 relative to sum |q_i v_i| <= |q||v| — and the products are exact in
+    //   the fp32 accumulator up to (dim/16 + 1) truncating additions: 1.01 * 2^-7 + 4 * (dim/16 + 1) * 2^-23 (safety factor 4
+    //   on the accumulator model only; the operand term is exact arithmetic, re-derived by tests/test_tf32_bound.py).
+    const double kappa = passes == 2   ? 1.01 * ldexp(1.0, -7) + ((double)dim / 16.0 + 1.0) * ldexp(1.0, -21)
+                         : passes == 1 ? 2.0 * ldexp(1.0, -9) * fmax(1.0, (double)dim / 1024.0)
+                                       : 4.0 * ldexp(1.0, -15) * fmax(1.0, (double)dim / 640.0);
     double d;
     if (metric == OTTERS_METRIC_COSINE) {
         d = kappa;
@@ -931,6 +966,40 @@ __global__ void min_inv_norm_kernel(const float* inv, uint64_t n, uint32_t* out_
     if ((threadIdx.x & 31) == 0) atomicMin(out_bits, __float_as_uint(m));  // positive floats order like uints
 }
 
+// ---- bf16 shadow arrays for the bf16 rung: dst[r][c] = bf16_rn(src[r][c]) for r < n_src, c < dim; everything else 0 ------
+// One thread converts 8 columns (two 16-byte loads, one 16-byte store); pitches are multiples of 4 floats / 8 bf16.
+__global__ void convert_bf16_kernel(const float* __restrict__ src, uint64_t src_pitch, uint64_t n_src, uint32_t dim,
+                                    uint16_t* __restrict__ dst, uint64_t dst_pitch, uint64_t n_dst) {
+    const uint64_t groups = dst_pitch >> 3;
+    const uint64_t total = n_dst * groups;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / groups;
+        const uint32_t c0 = (uint32_t)(i - r * groups) << 3;
+        float x[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) x[j] = 0.f;
+        if (r < n_src) {
+            const float* sp = src + r * src_pitch + c0;
+            if (c0 + 8 <= dim) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), b = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+                x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+            } else {
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j)
+                    if (c0 + j < dim) x[j] = __ldg(sp + j);
+            }
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            // round to nearest even; NaN stays NaN and |x| >= 2^128 (1 - 2^-9) becomes inf (the kernel then flags the batch)
+            // (the first source operand lands in the upper half of the pair)
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(x[2 * j + 1]), "f"(x[2 * j]));
+        }
+        *reinterpret_cast<uint4*>(dst + r * dst_pitch + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -950,14 +1019,15 @@ EncodeTiledFn tensor_map_encoder() {
 
 // 2D fp32 tensor [rows][cols] with a row pitch of pitch_floats, boxes of box_rows x 32 columns, 128B swizzle;
 // out-of-bounds elements are filled with zeros
-int make_tensor_map(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_floats, uint32_t box_rows) {
+// (half: a bf16 tensor with a row pitch of pitch_elems bf16 and boxes of box_rows x 64 columns — the same 128 bytes per box row)
+int make_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems, uint32_t box_rows, bool half = false) {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return fail(OTTERS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {pitch_floats * sizeof(float)};
-    cuuint32_t box[2] = {BK, box_rows};
+    cuuint64_t strides[1] = {pitch_elems * (half ? 2 : sizeof(float))};
+    cuuint32_t box[2] = {half ? 2 * BK : BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+    CUresult r = enc(out, half ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, kSwizzleBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1028,14 +1098,25 @@ int launch_batch_delta(int metric, uint32_t dim, uint32_t passes, const uint32_t
 int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s) {
     const uint32_t cg = l.cta_group == 2 ? 2 : 1;
     CUtensorMap tv, tqh, tql;
-    int rc = make_tensor_map(&tv, l.vectors, l.n_rows, l.dim, l.pitch_g, BM);
-    if (rc) return rc;
-    rc = make_tensor_map(&tqh, l.q_hi, l.nq_pad, l.dim, l.dim_pad, BN / cg);
-    if (rc) return rc;
-    rc = make_tensor_map(&tql, l.q_lo, l.nq_pad, l.dim, l.dim_pad, BN / cg);
-    if (rc) return rc;
+    int rc;
+    if (p.passes == 2) {
+        if (!l.v_half || !l.q_half) return fail(OTTERS_ERR_INVALID, "the bf16 rung needs the bf16 shadow arrays");
+        rc = make_tensor_map(&tv, l.v_half, l.n_rows, l.dim, l.pitch_h, BM, true);
+        if (rc) return rc;
+        rc = make_tensor_map(&tqh, l.q_half, l.nq_pad, l.dim, l.q_pitch_h, BN / cg, true);
+        if (rc) return rc;
+        tql = tqh;  // unused by single-pass rungs
+    } else {
+        rc = make_tensor_map(&tv, l.vectors, l.n_rows, l.dim, l.pitch_g, BM);
+        if (rc) return rc;
+        rc = make_tensor_map(&tqh, l.q_hi, l.nq_pad, l.dim, l.dim_pad, BN / cg);
+        if (rc) return rc;
+        rc = make_tensor_map(&tql, l.q_lo, l.nq_pad, l.dim, l.dim_pad, BN / cg);
+        if (rc) return rc;
+    }
     p.n_qtiles = l.nq_pad / BN;
-    p.nkb = (l.dim + BK - 1) / BK;
+    const uint32_t kcols = p.passes == 2 ? 2 * BK : BK;
+    p.nkb = (l.dim + kcols - 1) / kcols;
     const uint32_t smem = batch_smem_bytes(p.cap);
     if (cg == 2) return launch_batch_cg<2>(tv, tqh, tql, p, l.grid, smem, metric, smem_configured, s);
     return launch_batch_cg<1>(tv, tqh, tql, p, l.grid, smem, metric, smem_configured, s);
@@ -1052,6 +1133,17 @@ int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStre
         }
     }
     if (n_sort > total) pad_cands_kernel<<<64, 256, 0, s>>>(p.out, total, n_sort);
+    OTTERS_CUDA(cudaGetLastError());
+    return OTTERS_OK;
+}
+
+int launch_convert_bf16(const float* src, uint64_t src_pitch, uint64_t n_src, uint32_t dim, uint16_t* dst, uint64_t dst_pitch, uint64_t n_dst,
+                        cudaStream_t s) {
+    if (dst_pitch & 7u) return fail(OTTERS_ERR_INVALID, "bf16 row pitch must be a multiple of 8");
+    const uint64_t total = n_dst * (dst_pitch >> 3);
+    if (!total) return OTTERS_OK;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 16);
+    convert_bf16_kernel<<<blocks, 256, 0, s>>>(src, src_pitch, n_src, dim, dst, dst_pitch, n_dst);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
 }

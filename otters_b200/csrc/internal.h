@@ -216,7 +216,8 @@ struct BatchParams {
     uint64_t* cta_keys;          // [grid][k] approximate keys, best first
     uint32_t* cta_qids;          // [grid][k]
     uint32_t* cta_counts;        // [grid]
-    uint32_t passes;             // tf32 MMAs per product: 3 (3xTF32 split, fp32-faithful) or 1 (selection only, wider error bound)
+    uint32_t passes;             // arithmetic rung: 3 (3xTF32 split, fp32-faithful), 1 (one tf32 MMA per product: selection only, wider
+                                 // error bound) or 2 (one bf16 MMA per product on the bf16 shadow arrays: widest bound, fastest)
     uint32_t kps;                // single pass: k-blocks per pipeline stage (1 or 2: one barrier round trip and one commit for two)
     uint32_t pair_direct;        // CTA pairs, single pass: both CTAs' TMA loads credit the leader's barrier themselves (no relay warp)
     uint32_t dbg;                // timing experiments only (OTTERS_BATCH_DBG): 1 no loads, 2 no split, 4 no epilogue, 8 no MMAs
@@ -228,6 +229,10 @@ struct BatchLaunch {
     const float* q_hi;
     const float* q_lo;
     uint32_t nq_pad;             // multiple of kBatchQueries
+    const uint16_t* v_half;      // bf16 rung: bf16 shadow of the store rows [n_rows][pitch_h] ...
+    const uint16_t* q_half;      // ... and of the (zero padded) queries [nq_pad][q_pitch_h]
+    uint64_t pitch_h;
+    uint32_t q_pitch_h;
     uint32_t grid;               // CTAs (a multiple of cta_group)
     uint32_t cta_group;          // 1: one CTA per 128-row tile; 2: CTA pairs (tcgen05 cta_group::2) on 256-row tiles
 };
@@ -258,6 +263,8 @@ int launch_batch_delta(int metric, uint32_t dim, uint32_t passes, const uint32_t
 int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem_configured, cudaStream_t s);
 int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s);
 int launch_min_inv_norm(const float* inv, uint64_t n, uint32_t* out_bits, cudaStream_t s);
+int launch_convert_bf16(const float* src, uint64_t src_pitch, uint64_t n_src, uint32_t dim, uint16_t* dst, uint64_t dst_pitch, uint64_t n_dst,
+                        cudaStream_t s);
 
 // ---- store kernels ----------------------------------------------------------------------------
 int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t first, uint64_t n, float* out,

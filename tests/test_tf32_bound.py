@@ -7,6 +7,8 @@ emulating the operand formats of tcgen05.mma.kind::tf32 with numpy:
                                                                     bound 2^-15 max(1, dim/640) |q||v|
 Products and sums are taken in float64 here; the accumulator's own fp32 truncation (at most dim/8 additions of
 2^-23 relative each) is accounted for separately and must fit into the headroom the test measures.
+The bf16 rung (kind::f16 on operands this library rounds itself, nearest even at 8 bits) is derived the same way at the end:
+                                                                    bound 1.01 * 2^-7 |q||v| + accumulation.
 No GPU and no oracle involved: this is arithmetic about the formats only."""
 import numpy as np
 import pytest
@@ -78,3 +80,52 @@ def test_single_pass_bound_is_not_vacuous():
     exact, s1, _ = emulate(v, q)
     rel = abs(s1 - exact) / float(np.linalg.norm(v.astype(np.float64)) * np.linalg.norm(q.astype(np.float64)))
     assert 0.7 * 2.0 ** -9 < rel < 2.0 ** -9
+
+
+# ---- bf16 rung: both operands rounded to nearest even at 8 significant bits (convert_bf16_kernel) ------------------------
+def rne_bf16(x):
+    b = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    r = b + 0x7FFF + ((b >> 16) & 1)
+    return (r & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def adversarial_bf16(dim, rng, kind):
+    if kind == "aligned_worst":
+        # both operands just below a rounding midpoint: each loses almost 2^-8 relative, all errors with the same sign
+        mant = rng.integers(0, 1 << 7, dim).astype(np.uint32) << 16 | np.uint32(0x7FFF)
+        exp = np.uint32(127) << 23
+        return (exp | mant).view(np.float32), (exp | mant).view(np.float32)
+    if kind == "aligned_small_mantissa":
+        v = (np.full(dim, 0x3F800000, np.uint32) | np.uint32(0x7FFF)).view(np.float32)
+        return v, v.copy()
+    if kind == "rounds_up":
+        v = (np.full(dim, 0x3F800000, np.uint32) | np.uint32(0x8001)).view(np.float32)
+        return v, v.copy()
+    return adversarial(dim, rng, kind)
+
+
+@pytest.mark.parametrize("kind", ["aligned_worst", "aligned_small_mantissa", "rounds_up", "mixed_exponents", "random"])
+@pytest.mark.parametrize("dim", [8, 33, 640, 768, 1024, 1536, 4096])
+def test_bf16_selection_error_bound(kind, dim):
+    rng = np.random.default_rng(dim * 11 + len(kind))
+    worst = 0.0
+    for _ in range(20):
+        v, q = adversarial_bf16(dim, rng, kind)
+        vb, qb = rne_bf16(v), rne_bf16(q)
+        exact = float(np.dot(v.astype(np.float64), q.astype(np.float64)))
+        approx = float(np.dot(vb.astype(np.float64), qb.astype(np.float64)))
+        scale = float(np.linalg.norm(v.astype(np.float64)) * np.linalg.norm(q.astype(np.float64)))
+        worst = max(worst, abs(approx - exact) / scale)
+    acc = (dim / 16 + 1) * 2.0 ** -23                           # truncating fp32 additions in the tensor core, K = 16 per step
+    kappa = 1.01 * 2.0 ** -7 + (dim / 16 + 1) * 2.0 ** -21      # batch_delta_kernel's constant (4x the accumulation model)
+    assert worst <= 2.0 ** -7 + 2.0 ** -16, f"operand rounding error {worst:.3e} exceeds the format bound"
+    assert worst + 4 * acc <= kappa
+
+
+def test_bf16_bound_is_not_vacuous():
+    v, q = adversarial_bf16(768, np.random.default_rng(1), "aligned_small_mantissa")
+    vb, qb = rne_bf16(v), rne_bf16(q)
+    exact = float(np.dot(v.astype(np.float64), q.astype(np.float64)))
+    approx = float(np.dot(vb.astype(np.float64), qb.astype(np.float64)))
+    rel = abs(approx - exact) / float(np.linalg.norm(v.astype(np.float64)) * np.linalg.norm(q.astype(np.float64)))
+    assert 0.95 * 2.0 ** -7 < rel < 2.0 ** -7
