@@ -355,12 +355,13 @@ class VecQueryPlan {
 
 class VecStore {
     size_t dim_;
+    int32_t vector_format_ = OTTERS_VECTORS_FMT_F32;
     mutable otters_vecstore* h_ = nullptr;
     mutable std::vector<float> pending_;
     size_t n_ = 0;
     friend class VecQueryPlan;
     otters_vecstore* handle() const {
-        if (!h_ && otters_vecstore_create(default_ctx(), (uint32_t)dim_, &h_) != OTTERS_OK) throw std::runtime_error(otters_last_error());
+        if (!h_ && otters_vecstore_create_fmt(default_ctx(), (uint32_t)dim_, vector_format_, &h_) != OTTERS_OK) throw std::runtime_error(otters_last_error());
         if (!pending_.empty()) {
             if (otters_vecstore_add(h_, pending_.data(), pending_.size() / dim_) != OTTERS_OK) throw std::runtime_error(otters_last_error());
             pending_.clear();
@@ -369,7 +370,7 @@ class VecStore {
     }
 
   public:
-    explicit VecStore(size_t dim) : dim_(dim) {}
+    explicit VecStore(size_t dim, int32_t vector_format = OTTERS_VECTORS_FMT_F32) : dim_(dim), vector_format_(vector_format) {}
     VecStore(const VecStore&) = delete;
     ~VecStore() { if (h_) otters_vecstore_destroy(h_); }
     Result<bool> add_vector(const std::vector<float>& v) {  // src/vec.rs:357-371
@@ -470,6 +471,7 @@ class MetaStoreBuilder {
     int bloom_mode_ = 0;
     double bloom_fpr_ = 0.01;
     uint64_t bloom_bits_ = 0;
+    int32_t vector_format_ = OTTERS_VECTORS_FMT_F32;
 
   public:
     explicit MetaStoreBuilder(std::vector<Column> cols) : cols_(std::move(cols)) { for (auto& c : cols_) schema_[c.name()] = c.dtype(); }
@@ -477,6 +479,8 @@ class MetaStoreBuilder {
     MetaStoreBuilder with_chunk_size(size_t c) && { chunk_size_ = std::max<size_t>(c, 1); return std::move(*this); }
     MetaStoreBuilder with_bloom_fpr(double f) && { bloom_mode_ = 0; bloom_fpr_ = std::isfinite(f) ? std::min(std::max(f, 1e-2), 0.5) : 0.01; return std::move(*this); }
     MetaStoreBuilder with_bloom_bits(size_t b) && { bloom_mode_ = 1; bloom_bits_ = std::max<size_t>(b, 64); return std::move(*this); }
+    /* extension: OTTERS_VECTORS_FMT_BF16 keeps the rows as bf16 (see otters_vecstore_create_fmt in otters_b200.h) */
+    MetaStoreBuilder with_vector_format(int32_t f) && { vector_format_ = f; return std::move(*this); }
     Result<std::unique_ptr<MetaStore>> build() &&;
 };
 
@@ -529,6 +533,7 @@ inline Result<std::unique_ptr<MetaStore>> MetaStoreBuilder::build() && {  // src
     bp.bloom_mode = bloom_mode_; bp.bloom_fpr = bloom_fpr_; bp.bloom_bits = bloom_bits_;
     bp.vectors_kind = OTTERS_VECTORS_HOST; bp.vectors = flat.data();
     bp.columns = cc.data(); bp.n_columns = (uint32_t)cc.size();
+    bp.vector_format = vector_format_;
     auto ms = std::make_unique<MetaStore>();
     otters_build_stats bs{};
     if (otters_metastore_build(default_ctx(), &bp, &ms->h_, &bs) != OTTERS_OK) return R::Err(otters_last_error());

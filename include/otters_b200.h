@@ -143,6 +143,16 @@ OTTERS_API int otters_ctx_last_work(otters_ctx *ctx, otters_last_work *out);
  * 1/sqrt, 0.0 for a zero row; src/vec.rs:357-371).
  * ------------------------------------------------------------------------------------------- */
 OTTERS_API int otters_vecstore_create(otters_ctx *ctx, uint32_t dim, otters_vecstore **out); /* VecStore::new */
+/* Reduced-precision rows (the reference's roadmap item "Quantization for vectors", README.md:208).
+ * OTTERS_VECTORS_FMT_BF16: every element is rounded to bf16 (nearest even) when it is added and the store keeps 2 bytes per
+ * element — half the bytes of a scan that runs at the HBM limit.  The parity contract is the reference's arithmetic applied
+ * to the ROUNDED rows: scores, inverse norms and results are bit-identical to the CPU path run on f32(bf16(x)) (queries
+ * stay fp32; widening a bf16 value to fp32 is exact).  Rows are still passed in as fp32.  Query batches on a bf16 store are
+ * answered query by query on the streaming kernel. */
+#define OTTERS_VECTORS_FMT_F32 0
+#define OTTERS_VECTORS_FMT_BF16 1
+OTTERS_API int otters_vecstore_create_fmt(otters_ctx *ctx, uint32_t dim, int32_t vector_format, otters_vecstore **out);
+OTTERS_API int32_t otters_vecstore_format(const otters_vecstore *vs);
 OTTERS_API int otters_vecstore_destroy(otters_vecstore *vs);
 OTTERS_API int otters_vecstore_reserve(otters_vecstore *vs, uint64_t n_rows);
 /* VecStore::add_vectors with contiguous row-major host rows (n * dim floats). */
@@ -215,6 +225,7 @@ typedef struct {
     const void *synthetic_map;      /* optional otters_shard_map*: global row ids of the generated rows */
     const otters_column *columns;
     uint32_t n_columns;
+    int32_t vector_format;          /* OTTERS_VECTORS_FMT_* (0 = fp32 rows; see otters_vecstore_create_fmt) */
 } otters_build_params;
 
 /* src/meta.rs:844-852 (durations in seconds) */

@@ -6,7 +6,7 @@ Public surface mirrors the reference's prelude (src/prelude.rs:7-23):
 selection runs in hand-written CUDA behind the C ABI in ``include/otters_b200.h``
 (``otters_b200/libotters_b200.so``); importing this package without that library fails.
 """
-from .types import Cmp, CmpOp, DataType, Metric, OttersError, TakeType  # noqa: F401
+from .types import Cmp, CmpOp, DataType, Metric, OttersError, TakeType, VectorFormat, round_to_bf16  # noqa: F401
 from .column import Column, ColumnError, parse_datetime_millis  # noqa: F401
 from .expr import (  # noqa: F401
     ColumnFilter,

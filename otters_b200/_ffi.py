@@ -109,6 +109,7 @@ class BuildParams(C.Structure):
         ("synthetic_map", C.c_void_p),
         ("columns", C.POINTER(Column)),
         ("n_columns", C.c_uint32),
+        ("vector_format", C.c_int32),
     ]
 
 
@@ -196,6 +197,8 @@ otters_version = _sig("otters_version", C.c_char_p)
 otters_ctx_set_tuning = _sig("otters_ctx_set_tuning", C.c_int, _p, C.POINTER(ScanTuning))
 otters_ctx_last_work = _sig("otters_ctx_last_work", C.c_int, _p, C.POINTER(LastWork))
 otters_vecstore_create = _sig("otters_vecstore_create", C.c_int, _p, C.c_uint32, C.POINTER(_p))
+otters_vecstore_create_fmt = _sig("otters_vecstore_create_fmt", C.c_int, _p, C.c_uint32, C.c_int32, C.POINTER(_p))
+otters_vecstore_format = _sig("otters_vecstore_format", C.c_int32, _p)
 otters_vecstore_destroy = _sig("otters_vecstore_destroy", C.c_int, _p)
 otters_vecstore_reserve = _sig("otters_vecstore_reserve", C.c_int, _p, C.c_uint64)
 otters_vecstore_add = _sig("otters_vecstore_add", C.c_int, _p, c_f32p, C.c_uint64)

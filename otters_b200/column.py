@@ -269,7 +269,9 @@ class Column:
         out = Column(self._name, self._dtype)
         nulls = self.null_mask()
         idx = np.asarray(indices, dtype=np.int64)
-        if self._dtype == DataType.String:
+        if isinstance(self._vals, _CatSeq):
+            out._vals = _CatSeq(self._vals.vocab, self._vals.codes[idx] if len(idx) else np.zeros(0, np.int64))
+        elif self._dtype == DataType.String:
             out._vals = [self._vals[i] for i in idx]
         else:
             out._vals = self.numpy()[idx] if len(idx) else np.zeros(0, dtype=_NP[self._dtype])

@@ -172,6 +172,7 @@ struct otters_ctx {
     bool timed_meta = false;      // ev[0]/ev[1] bracket the prune kernel of the last query
     bool timed_rowmask = false;   // ev[1]/ev[6] bracket the stand-alone row-mask kernel of the last query
     uint32_t last_dim = 0;        // of the last scan (for the algorithmic-bytes figure)
+    uint32_t last_esz = 4;        // bytes per stored element of the last scan (4, or 2 for a bf16 store)
     int32_t last_metric = 0;
 
     // per-query MetaStore scratch (stores are immutable after build: everything a query writes lives in the context
@@ -396,19 +397,28 @@ struct VecStorage {
     bool h_valid = false;
     uint32_t bf16_backoff = 0;         // batches left that skip the bf16 rung (its certificate failed on this store)
 
+    bool half = false;  // rows are bf16 (OTTERS_VECTORS_FMT_BF16): d_rows then points at uint16_t elements, pitch counts bf16
+    size_t esz() const { return half ? 2 : 4; }
+    void set_format(uint32_t d, bool h) {
+        dim = d;
+        half = h;
+        pitch = (uint32_t)round_up(std::max<uint32_t>(d, 1), h ? 8 : 4);  // 16-byte rows for the bulk copies
+    }
+    uint8_t* row_ptr(uint64_t row) const { return reinterpret_cast<uint8_t*>(d_rows) + row * pitch * esz(); }
+
     int reserve(uint64_t want) {
         if (want <= cap) return OTTERS_OK;
         uint64_t ncap = std::max<uint64_t>(want, cap ? cap + cap / 2 : 0);
         if (ncap == want && cap != 0 && want < cap * 2) ncap = want;
         float *nr = nullptr, *ni = nullptr;
-        if (cudaMalloc((void**)&nr, std::max<uint64_t>(ncap * pitch, 4) * sizeof(float)) != cudaSuccess)
+        if (cudaMalloc((void**)&nr, std::max<uint64_t>(ncap * pitch * esz(), 16)) != cudaSuccess)
             return fail(OTTERS_ERR_NOMEM, "device allocation for vectors failed");
         if (cudaMalloc((void**)&ni, std::max<uint64_t>(ncap, 4) * sizeof(float)) != cudaSuccess) {
             cudaFree(nr);
             return fail(OTTERS_ERR_NOMEM, "device allocation for inverse norms failed");
         }
         if (n) {
-            OTTERS_CUDA(cudaMemcpyAsync(nr, d_rows, n * pitch * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+            OTTERS_CUDA(cudaMemcpyAsync(nr, d_rows, n * pitch * esz(), cudaMemcpyDeviceToDevice, ctx->stream));
             OTTERS_CUDA(cudaMemcpyAsync(ni, d_inv, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
         }
         OTTERS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -418,6 +428,25 @@ struct VecStorage {
         d_inv = ni;
         cap = ncap;
         return OTTERS_OK;
+    }
+    // bf16 stores: rows arrive as fp32 (host, device or generated), pass through an fp32 staging slab and are rounded to
+    // nearest even on the device; the inverse norms are those of the ROUNDED rows (what the store holds is what is scored)
+    template <typename Fill>
+    int add_half(uint64_t cnt, Fill fill) {
+        const uint64_t pitch4 = round_up(std::max<uint32_t>(dim, 1), 4);
+        const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(cnt, ((uint64_t)256 << 20) / (pitch4 * 4)));
+        float* tmp = nullptr;
+        if (cudaMalloc((void**)&tmp, slab * pitch4 * 4) != cudaSuccess) return fail(OTTERS_ERR_NOMEM, "device allocation for the staging slab failed");
+        int rc = OTTERS_OK;
+        for (uint64_t done = 0; done < cnt && !rc; done += slab) {
+            const uint64_t m = std::min(slab, cnt - done);
+            rc = fill(tmp, pitch4, done, m);
+            if (!rc) rc = launch_convert_bf16(tmp, pitch4, m, dim, reinterpret_cast<uint16_t*>(d_rows) + (n + done) * pitch, pitch, m, ctx->stream);
+        }
+        if (!rc) rc = launch_inv_norms_bf16(reinterpret_cast<const uint16_t*>(d_rows), pitch, dim, n, cnt, d_inv, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp);
+        return rc;
     }
     int add(const float* rows, uint64_t cnt, cudaMemcpyKind kind) {
         if (cnt == 0) return OTTERS_OK;
@@ -436,6 +465,18 @@ struct VecStorage {
         if (kind == cudaMemcpyHostToDevice && in_bytes >= ((size_t)64 << 20) && !getenv("OTTERS_NO_PIN")) {
             if (cudaHostRegister((void*)rows, in_bytes, cudaHostRegisterDefault) == cudaSuccess) pin.p = (void*)rows;
             else cudaGetLastError();
+        }
+        if (half) {
+            rc = add_half(cnt, [&](float* tmp, uint64_t pitch4, uint64_t first, uint64_t m) -> int {
+                OTTERS_CUDA(cudaMemcpy2DAsync(tmp, pitch4 * sizeof(float), rows + first * dim, dim * sizeof(float), dim * sizeof(float), m, kind,
+                                              ctx->stream));
+                return OTTERS_OK;
+            });
+            if (rc) return rc;
+            n += cnt;
+            minv_valid = false;
+            h_valid = false;
+            return OTTERS_OK;
         }
         if (pitch == dim) {
             OTTERS_CUDA(cudaMemcpyAsync(d_rows + n * pitch, rows, cnt * dim * sizeof(float), kind, ctx->stream));
@@ -457,6 +498,18 @@ struct VecStorage {
         if (n + cnt >= 0xFFFFFFF0ull) return fail(OTTERS_ERR_UNSUPPORTED, "a store shard is limited to 2^32-16 rows");
         int rc = reserve(n + cnt);
         if (rc) return rc;
+        if (half) {
+            // generated row ids continue where the store ends: slab `first` rows further into the map
+            rc = add_half(cnt, [&](float* tmp, uint64_t pitch4, uint64_t first, uint64_t m) -> int {
+                ShardMap mm = gen_map;
+                return launch_synth_fill_at(tmp, pitch4, dim, mm, first, m, seed, ctx->stream);
+            });
+            if (rc) return rc;
+            n += cnt;
+            minv_valid = false;
+            h_valid = false;
+            return OTTERS_OK;
+        }
         rc = launch_synth_fill(d_rows, pitch, dim, n, gen_map, cnt, seed, ctx->stream);
         if (rc) return rc;
         rc = launch_inv_norms(d_rows, pitch, dim, n, cnt, d_inv, ctx->stream);
@@ -471,6 +524,24 @@ struct VecStorage {
     int set_rows(const uint64_t* rows, const float* data, uint64_t cnt) {
         for (uint64_t i = 0; i < cnt; ++i)
             if (rows[i] >= n) return fail(OTTERS_ERR_INVALID, "row index out of bounds");
+        if (half) {
+            const uint64_t pitch4 = round_up(std::max<uint32_t>(dim, 1), 4);
+            float* tmp = nullptr;
+            if (cnt && cudaMalloc((void**)&tmp, cnt * pitch4 * 4) != cudaSuccess) return fail(OTTERS_ERR_NOMEM, "device allocation for the staging slab failed");
+            int rc = OTTERS_OK;
+            if (cnt && cudaMemcpy2DAsync(tmp, pitch4 * sizeof(float), data, dim * sizeof(float), dim * sizeof(float), cnt, cudaMemcpyHostToDevice,
+                                         ctx->stream) != cudaSuccess)
+                rc = fail(OTTERS_ERR_CUDA, "copy of the replacement rows failed");
+            for (uint64_t i = 0; i < cnt && !rc; ++i) {
+                rc = launch_convert_bf16(tmp + i * pitch4, pitch4, 1, dim, reinterpret_cast<uint16_t*>(d_rows) + rows[i] * pitch, pitch, 1, ctx->stream);
+                if (!rc) rc = launch_inv_norms_bf16(reinterpret_cast<const uint16_t*>(d_rows), pitch, dim, rows[i], 1, d_inv, ctx->stream);
+            }
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(tmp);
+            minv_valid = false;
+            h_valid = false;
+            return rc;
+        }
         for (uint64_t i = 0; i < cnt; ++i) {
             OTTERS_CUDA(cudaMemcpyAsync(d_rows + rows[i] * pitch, data + i * dim, (size_t)dim * sizeof(float), cudaMemcpyHostToDevice,
                                         ctx->stream));
@@ -507,7 +578,7 @@ struct ScanPlan {
 };
 
 static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uint32_t k_fused, size_t filter_bytes, bool fuse_select,
-                     ScanPlan* out) {
+                     ScanPlan* out, bool half = false) {
     ScanPlan pl{};
     const otters_scan_tuning& t = c->tuning;
     pl.cap = k_fused ? (uint32_t)pow2_at_least(std::max<uint32_t>(2 * k_fused, 64)) : 0;
@@ -518,13 +589,14 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     // automatic choice (profiles/r1_planner_ab.log): the planner front-end wins where rows are wide or no predicate has to
     // be evaluated (10Mx768 unfiltered 4.07 vs 4.18 ms, 5Mx1536 filtered 2.17 vs 2.26 ms) and loses on narrow filtered rows
     // (10Mx128: 0.79 vs 0.50 ms), where the per-tile ring handshake and the planners' metadata round trips dominate
-    const bool planner_auto = filter_bytes == 0 ? dim_pad >= 256 : dim_pad >= 1024;
+    const uint32_t row_words = half ? dim_pad / 2 : dim_pad;  // row length in 4-byte words: what the front-end choices depend on
+    const bool planner_auto = filter_bytes == 0 ? row_words >= 256 : row_words >= 1024;
     const bool planner = k_fused && t.scan_mode != 1 && (t.scan_mode == 2 || planner_auto);
     pl.off_ring = (uint32_t)(pl.off_filter + filter_bytes);
     pl.off_warps = pl.off_ring + (planner ? kPlannerRingBytes : 0);
     // planner warps per CTA: a filtered unit costs a planner one memory round trip (~2 µs under load); narrow rows are
     // consumed faster, so they need more planners to stay ahead of the workers
-    if (planner) pl.planners = t.planners ? std::min<uint32_t>(t.planners, 4) : (filter_bytes ? (dim_pad <= 256 ? 4 : 2) : 1);
+    if (planner) pl.planners = t.planners ? std::min<uint32_t>(t.planners, 4) : (filter_bytes ? (row_words <= 256 ? 4 : 2) : 1);
     static const size_t margin = getenv("OTTERS_SMEM_MARGIN") ? (size_t)atoi(getenv("OTTERS_SMEM_MARGIN")) : 128;
     // shared memory of one CTA: the opt-in maximum, or an equal share of the SM (minus the 1 KB the system reserves per
     // CTA) when several CTAs are to be co-resident per SM (ctas_per_sm)
@@ -537,14 +609,15 @@ static int plan_scan(const otters_ctx* c, uint32_t dim_pad, uint64_t n_rows, uin
     uint32_t dim8 = (uint32_t)round_up(dim_pad, 8);
     // Measured on B200 (profiles/r1_sweep_*.log): many autonomous warps with one small slot each beat
     // fewer warps with deep rings — 12-16 warps x 1 slot x 256 columns reads 7.1-7.3 TB/s at dim 768.
-    uint32_t kc_target = t.kc_floats ? (uint32_t)round_up(t.kc_floats, 8) : 256;
+    // (bf16 rows: twice the columns per slot, the same 1 KB per staged row)
+    uint32_t kc_target = t.kc_floats ? (uint32_t)round_up(t.kc_floats, 8) : (half ? 512 : 256);
     uint32_t nkc = (dim_pad + kc_target - 1) / kc_target;
     if (nkc < 1) nkc = 1;
     uint32_t kc = (uint32_t)round_up((dim8 + nkc - 1) / nkc, 8);
     nkc = (dim_pad + kc - 1) / kc;
     pl.kc = kc;
     pl.nkc = nkc;
-    pl.pitch_s = (uint32_t)round_up(kc, 32) + 8;
+    pl.pitch_s = (uint32_t)round_up(half ? kc / 2 : kc, 32) + 8;
     const uint32_t slot_bytes = kTileRows * pl.pitch_s * 4;
 
     auto warp_bytes_for = [&](uint32_t S, uint32_t* o_rows, uint32_t* o_info, uint32_t* o_inv, uint32_t* o_list, uint32_t* o_slots) {
@@ -955,6 +1028,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     run->k_eff = k_eff;
     run->result_list = 0;
     c->last_dim = st->dim;
+    c->last_esz = (uint32_t)st->esz();
     c->last_metric = q->metric;
     cudaStream_t s = c->stream;
 
@@ -962,7 +1036,8 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     int rc = io_flush(c);
     if (rc) return rc;
 
-    if (!c->ex_active && batch_eligible(c, q, n_rows, k_eff)) {
+    // (bf16 stores answer batches query by query on the streaming kernel: K2's exact re-scoring reads fp32 rows)
+    if (!c->ex_active && !st->half && batch_eligible(c, q, n_rows, k_eff)) {
         // selection runs single-pass tf32 first (a third of the MMAs and of the operand traffic; error bound 2^-9 |q||v|);
         // when its certificate fails the batch is redone with the 3xTF32 split (2^-15), and only then query by query.
         // A store whose single-pass certificate failed goes straight to 3xTF32 for its next kSinglePassBackoff batches.
@@ -1015,13 +1090,14 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     // single queries: the selection (K3) runs in the last CTA of the scan kernel — one launch per query
     const bool fuse_select = fused && q->nq == 1 && !c->tuning.separate_select;
     ScanPlan pl;
-    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, ff ? ff->smem_bytes() : 0, fuse_select, &pl);
+    rc = plan_scan(c, dim_pad, n_rows, fused ? (uint32_t)k_eff : 0, ff ? ff->smem_bytes() : 0, fuse_select, &pl, st->half);
     if (rc) return rc;
 
     ScanParams sp{};
     sp.vectors = st->d_rows;
     sp.inv_norms = st->d_inv;
     sp.pitch_g = st->pitch;
+    sp.half = st->half ? 1u : 0u;
     sp.dim = st->dim;
     sp.dim_pad = dim_pad;
     sp.n_rows = (uint32_t)n_rows;
@@ -1240,7 +1316,7 @@ static void finish_work_stats(otters_ctx* c) {
         else if (elapsed_ms(c->ev[2], c->ev[5], &ms)) c->last.scan_ms = ms;
         if (c->timed_single && elapsed_ms(c->ev[4], c->ev[5], &ms)) c->last.select_ms = ms;
     }
-    const uint64_t per_row = (uint64_t)c->last_dim * 4 + (c->last_metric == OTTERS_METRIC_COSINE ? 4 : 0);
+    const uint64_t per_row = (uint64_t)c->last_dim * c->last_esz + (c->last_metric == OTTERS_METRIC_COSINE ? 4 : 0);
     c->last.scan_bytes = c->last.rows_scored * per_row;
 }
 
@@ -1404,14 +1480,23 @@ struct otters_vecstore {
     VecStorage st;
 };
 
-extern "C" int otters_vecstore_create(otters_ctx* c, uint32_t dim, otters_vecstore** out) {
+extern "C" int otters_vecstore_create_fmt(otters_ctx* c, uint32_t dim, int32_t vector_format, otters_vecstore** out) {
     if (!c || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    if (vector_format != OTTERS_VECTORS_FMT_F32 && vector_format != OTTERS_VECTORS_FMT_BF16)
+        return fail(OTTERS_ERR_INVALID, "unknown vector format");
     auto* vs = new otters_vecstore();
     vs->st.ctx = c;
-    vs->st.dim = dim;
-    vs->st.pitch = (uint32_t)round_up(std::max<uint32_t>(dim, 1), 4);
+    vs->st.set_format(dim, vector_format == OTTERS_VECTORS_FMT_BF16);
     *out = vs;
     return OTTERS_OK;
+}
+
+extern "C" int otters_vecstore_create(otters_ctx* c, uint32_t dim, otters_vecstore** out) {
+    return otters_vecstore_create_fmt(c, dim, OTTERS_VECTORS_FMT_F32, out);
+}
+
+extern "C" int32_t otters_vecstore_format(const otters_vecstore* vs) {
+    return vs && vs->st.half ? OTTERS_VECTORS_FMT_BF16 : OTTERS_VECTORS_FMT_F32;
 }
 
 extern "C" int otters_vecstore_destroy(otters_vecstore* vs) {
@@ -2022,9 +2107,10 @@ extern "C" int otters_metastore_build(otters_ctx* c, const otters_build_params* 
     } else {
         bits = std::max<uint64_t>(bits, 64);  // src/meta.rs:106-110
     }
+    if (p->vector_format != OTTERS_VECTORS_FMT_F32 && p->vector_format != OTTERS_VECTORS_FMT_BF16)
+        return fail(OTTERS_ERR_INVALID, "unknown vector format");
     ms->st.ctx = c;
-    ms->st.dim = p->dim;
-    ms->st.pitch = (uint32_t)round_up(std::max<uint32_t>(p->dim, 1), 4);
+    ms->st.set_format(p->dim, p->vector_format == OTTERS_VECTORS_FMT_BF16);
 
     auto cleanup = [&](int rc) {
         otters_metastore_destroy(ms.release());
@@ -2306,7 +2392,7 @@ static int meta_enqueue(otters_ctx* c, otters_metastore* ms, const otters_vec_qu
         if (rc) return rc;
     }
     // the batched tensor-core kernel gates rows with a precomputed mask (K0b) instead of the fused predicate
-    const bool batched = scan && !c->ex_active && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
+    const bool batched = scan && !c->ex_active && !ms->st.half && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
     const uint32_t n_leaves = filter && filter->clause_offsets ? filter->clause_offsets[filter->n_clauses] : 0;
     // Row predicate: by default its own kernel (K0b writes the surviving-row bitmask at HBM bandwidth, the scan's producer then
     // reads one mask word per 32 rows); the scan kernel can also evaluate the CNF itself per work unit (fused K0b:

@@ -107,11 +107,12 @@ inline uint32_t& smem_limit_slot(uint32_t (&slots)[64]) {
 
 // ---- scan kernel ------------------------------------------------------------------------------
 struct ScanParams {
-    const float* vectors;       // [n_rows][pitch_g]
+    const float* vectors;       // [n_rows][pitch_g] fp32 — or bf16 (half != 0: the pointer is then a uint16_t array)
     const float* inv_norms;     // [n_rows]
     const float* query;         // [dim_pad] zero padded, device
     float q_inv;                // 1/|q| (0 for a zero query), computed like src/vec.rs:390-397
-    uint64_t pitch_g;           // floats per stored row (dim rounded up to 4)
+    uint64_t pitch_g;           // elements per stored row (dim rounded up to 4 floats / 8 bf16: 16-byte rows)
+    uint32_t half;              // rows are bf16 (OTTERS_VECTORS_FMT_BF16)
     uint32_t dim;
     uint32_t dim_pad;
     uint32_t n_rows;
@@ -269,8 +270,11 @@ int launch_convert_bf16(const float* src, uint64_t src_pitch, uint64_t n_src, ui
 // ---- store kernels ----------------------------------------------------------------------------
 int launch_inv_norms(const float* rows, uint64_t pitch_g, uint32_t dim, uint64_t first, uint64_t n, float* out,
                      cudaStream_t s);
+int launch_inv_norms_bf16(const uint16_t* rows, uint64_t pitch_g, uint32_t dim, uint64_t first, uint64_t n, float* out, cudaStream_t s);
 int launch_synth_fill(float* rows, uint64_t pitch_g, uint32_t dim, uint64_t dst_first, ShardMap gen_map, uint64_t n,
                       uint64_t seed, cudaStream_t s);
+int launch_synth_fill_at(float* rows, uint64_t pitch_g, uint32_t dim, ShardMap gen_map, uint64_t gen_first, uint64_t n, uint64_t seed,
+                         cudaStream_t s);
 
 // ---- device-side MetaStore build: build.cu ---------------------------------------------------------------------------
 int launch_zonemap(int dtype, const void* values, const uint32_t* null_words, uint64_t n_rows, uint64_t chunk_size, uint64_t n_chunks,

@@ -31,7 +31,7 @@ namespace {
 
 using namespace scan_detail;
 
-template <int METRIC, bool EMIT_ALL>
+template <int METRIC, bool EMIT_ALL, bool HALF>
 __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         if (lane < (int)kTileRows) slot_rows[slot * kTileRows + lane] = row;
         const uint32_t c0 = kc_i * p.kc;
         const uint32_t ncols = p.dim_pad - c0 < p.kc ? p.dim_pad - c0 : p.kc;
-        const uint32_t bytes = ncols * 4u;
+        const uint32_t bytes = ncols * (HALF ? 2u : 4u);
         if (lane == 0) {
             slot_info[slot] = tile_cnt | (kc_i << 8);
             mbar_arrive_expect_tx(&bars[slot], tile_cnt * bytes);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         __syncwarp();
         if (lane < (int)tile_cnt) {
             bulk_g2s_hint(slot_base + (size_t)slot * slot_floats + (size_t)lane * p.pitch_s,
-                          p.vectors + (size_t)row * p.pitch_g + c0, bytes, &bars[slot], l2pol);
+                          row_src<HALF>(p.vectors, p.pitch_g, row, c0), bytes, &bars[slot], l2pol);
             // the row's precomputed inverse norm rides along as a 4-byte cp.async (LDGSTS): its latency
             // overlaps the bulk copy instead of being exposed in the epilogue
             if (METRIC == OTTERS_METRIC_COSINE && kc_i == 0) cp_async_4(&slot_inv[slot * kTileRows + lane], p.inv_norms + row);
@@ -276,11 +276,10 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
         const uint32_t cend = c0 + p.kc < dim8 ? c0 + p.kc : dim8;
         const uint32_t nblk = cend > c0 ? (cend - c0) >> 3 : 0;
         const float* vrow = slot_base + (size_t)slot * slot_floats + (size_t)r * p.pitch_s;
-        const float4* vp = reinterpret_cast<const float4*>(vrow) + h;
         const float4* qp = reinterpret_cast<const float4*>(qs + c0) + h;
 #pragma unroll 4
         for (uint32_t j = 0; j < nblk; ++j) {
-            const float4 v = vp[2 * j];
+            const float4 v = load_row4<HALF>(vrow, 2 * j + h);
             const float4 q = qp[2 * j];
             if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
                 // src/vec_compute.rs:35-54: diff = query - row; acc += diff*diff
@@ -305,14 +304,14 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
             // serial remainder (src/vec_compute.rs:15-21), Rust's f32 Sum starts at -0.0
             float tail = -0.0f;
             if (ntail) {
-                const float* vt = vrow + (dim8 - c0);
                 const float* qt = qs + dim8;
                 for (uint32_t e = 0; e < ntail; ++e) {
+                    const float ve = load_row1<HALF>(vrow, dim8 - c0 + e);
                     if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
-                        float d = __fsub_rn(qt[e], vt[e]);
+                        float d = __fsub_rn(qt[e], ve);
                         tail = __fadd_rn(tail, __fmul_rn(d, d));
                     } else {
-                        tail = __fadd_rn(tail, __fmul_rn(qt[e], vt[e]));
+                        tail = __fadd_rn(tail, __fmul_rn(qt[e], ve));
                     }
                 }
             }
@@ -400,9 +399,9 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const __grid_constant__ Sc
     }
 }
 
-template <int METRIC, bool EMIT>
-int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
-    auto kern = scan_kernel<METRIC, EMIT>;
+template <int METRIC, bool EMIT, bool HALF>
+int launch_one_fmt(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
+    auto kern = scan_kernel<METRIC, EMIT, HALF>;
     // the opt-in shared-memory limit is sticky per function and device: raise it only when it grows
     static uint32_t limits[64];
     uint32_t& have = smem_limit_slot(limits);
@@ -414,6 +413,11 @@ int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configur
     kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
+}
+
+template <int METRIC, bool EMIT>
+int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
+    return p.half ? launch_one_fmt<METRIC, EMIT, true>(p, l, smem_configured, s) : launch_one_fmt<METRIC, EMIT, false>(p, l, smem_configured, s);
 }
 
 }  // namespace

@@ -41,7 +41,7 @@ static_assert(sizeof(Ring) <= kPlannerRingBytes, "ring does not fit its shared-m
 
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
-template <int METRIC>
+template <int METRIC, bool HALF>
 __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x;
@@ -267,11 +267,11 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
             for (uint32_t kci = 0; kci < p.nkc; ++kci) {
                 const uint32_t c0 = kci * p.kc;
                 const uint32_t ncols = p.dim_pad - c0 < p.kc ? p.dim_pad - c0 : p.kc;
-                const uint32_t bytes = ncols * 4u;
+                const uint32_t bytes = ncols * (HALF ? 2u : 4u);
                 if (lane == 0) mbar_arrive_expect_tx(bar, cnt * bytes);
                 __syncwarp();
                 if (lane < (int)cnt) {
-                    bulk_g2s_hint(slot + (size_t)lane * p.pitch_s, p.vectors + (size_t)row * p.pitch_g + c0, bytes, bar, l2pol);
+                    bulk_g2s_hint(slot + (size_t)lane * p.pitch_s, row_src<HALF>(p.vectors, p.pitch_g, row, c0), bytes, bar, l2pol);
                     if (METRIC == OTTERS_METRIC_COSINE && kci == 0) cp_async_4(&slot_inv[lane], p.inv_norms + row);
                 }
                 mbar_wait(bar, phase);
@@ -284,11 +284,10 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
                 const uint32_t cend = c0 + p.kc < dim8 ? c0 + p.kc : dim8;
                 const uint32_t nblk = cend > c0 ? (cend - c0) >> 3 : 0;
                 const float* vrow = slot + (size_t)r * p.pitch_s;
-                const float4* vp = reinterpret_cast<const float4*>(vrow) + h;
                 const float4* qp = reinterpret_cast<const float4*>(qs + c0) + h;
 #pragma unroll 4
                 for (uint32_t j = 0; j < nblk; ++j) {
-                    const float4 v = vp[2 * j];
+                    const float4 v = load_row4<HALF>(vrow, 2 * j + h);
                     const float4 q = qp[2 * j];
                     if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
                         // src/vec_compute.rs:35-54: diff = query - row; acc += diff*diff
@@ -313,14 +312,14 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
                     // serial remainder (src/vec_compute.rs:15-21), Rust's f32 Sum starts at -0.0
                     float tail = -0.0f;
                     if (ntail) {
-                        const float* vt = vrow + (dim8 - c0);
                         const float* qt = qs + dim8;
                         for (uint32_t e = 0; e < ntail; ++e) {
+                            const float ve = load_row1<HALF>(vrow, dim8 - c0 + e);
                             if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
-                                const float d = __fsub_rn(qt[e], vt[e]);
+                                const float d = __fsub_rn(qt[e], ve);
                                 tail = __fadd_rn(tail, __fmul_rn(d, d));
                             } else {
-                                tail = __fadd_rn(tail, __fmul_rn(qt[e], vt[e]));
+                                tail = __fadd_rn(tail, __fmul_rn(qt[e], ve));
                             }
                         }
                     }
@@ -367,9 +366,9 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
     }
 }
 
-template <int METRIC>
-int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
-    auto kern = scan_planner_kernel<METRIC>;
+template <int METRIC, bool HALF>
+int launch_one_fmt(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
+    auto kern = scan_planner_kernel<METRIC, HALF>;
     static uint32_t limits[64];
     uint32_t& have = smem_limit_slot(limits);
     (void)smem_configured;
@@ -380,6 +379,11 @@ int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configur
     kern<<<l.grid, l.block, l.smem_bytes, s>>>(p);
     OTTERS_CUDA(cudaGetLastError());
     return OTTERS_OK;
+}
+
+template <int METRIC>
+int launch_one(const ScanParams& p, const ScanLaunch& l, uint32_t* smem_configured, cudaStream_t s) {
+    return p.half ? launch_one_fmt<METRIC, true>(p, l, smem_configured, s) : launch_one_fmt<METRIC, false>(p, l, smem_configured, s);
 }
 
 }  // namespace

@@ -19,6 +19,31 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const unsigned long long* p)
 }
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
+// Staged rows are fp32, or — stores created with OTTERS_VECTORS_FMT_BF16 — bf16 widened to fp32 on the way into the same
+// arithmetic (a bf16 value IS the fp32 value with sixteen zero bits appended, so the widening is exact).
+// load_row4: elements [4*idx4, 4*idx4 + 4) of a staged row; load_row1: element e.
+template <bool HALF>
+__device__ __forceinline__ float4 load_row4(const float* vrow, uint32_t idx4) {
+    if constexpr (HALF) {
+        const uint2 w = reinterpret_cast<const uint2*>(vrow)[idx4];
+        return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                           __uint_as_float(w.y & 0xFFFF0000u));
+    } else {
+        return reinterpret_cast<const float4*>(vrow)[idx4];
+    }
+}
+template <bool HALF>
+__device__ __forceinline__ float load_row1(const float* vrow, uint32_t e) {
+    if constexpr (HALF) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(vrow)[e] << 16);
+    else return vrow[e];
+}
+// address of column c0 of stored row `row` (pitch_g counts elements)
+template <bool HALF>
+__device__ __forceinline__ const void* row_src(const float* vectors, uint64_t pitch_g, uint32_t row, uint32_t c0) {
+    if constexpr (HALF) return reinterpret_cast<const uint16_t*>(vectors) + (size_t)row * pitch_g + c0;
+    else return vectors + (size_t)row * pitch_g + c0;
+}
+
 // one warp: sort buf[0..cap) best-first (entries >= cnt are zeroed first); the best min(cnt,k) end up in front
 __device__ inline void warp_sort(uint64_t* buf, uint32_t cnt, uint32_t cap, int lane) {
     for (uint32_t i = cnt + lane; i < cap; i += 32) buf[i] = 0ull;

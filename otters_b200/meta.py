@@ -18,7 +18,7 @@ from . import _ffi
 from .column import Column
 from .context import Context, check, default_context
 from .expr import CompiledFilter, Expr, ExprError
-from .types import Cmp, DataType, Metric, OttersError, TakeType, infer_default_take_type
+from .types import Cmp, DataType, Metric, OttersError, TakeType, VectorFormat, infer_default_take_type
 from .vec import _as_query_batch
 
 
@@ -113,6 +113,27 @@ class MetaStoreBuilder:
         self._chunk_size = 1024
         self._bloom = ("fpr", 0.01)
         self._ctx: Optional[Context] = None
+        self._vector_format = VectorFormat.F32
+        self._row_order = None  # (columns, method) — see with_row_order
+
+    def with_vector_format(self, vector_format: VectorFormat) -> "MetaStoreBuilder":
+        """Extension (the reference's roadmap item "Quantization for vectors", README.md:208): ``VectorFormat.Bf16`` keeps the
+        rows as bf16 — half the bytes every scan streams; scores are the reference's arithmetic on the rounded rows."""
+        self._vector_format = VectorFormat(vector_format)
+        return self
+
+    def with_row_order(self, by, method: str = "sort") -> "MetaStoreBuilder":
+        """Extension (the reference's roadmap item "reorder metadata for better pruning (Something like Z-ordering)",
+        README.md:154,212): the store keeps its rows clustered on the filter columns ``by`` (``method`` "sort" or "zorder",
+        otters_b200/reorder.py), so that zonemaps and Bloom filters prune more chunks.  Results keep reporting the caller's
+        row ids; among rows with EQUAL scores the order follows the store position (the reference leaves it undefined)."""
+        from .reorder import METHODS
+
+        by = [by] if isinstance(by, str) else list(by)
+        if method not in METHODS:
+            raise OttersError(f"unknown row order method '{method}' (expected one of {', '.join(METHODS)})")
+        self._row_order = (by, method)
+        return self
 
     def with_vectors(self, vectors) -> "MetaStoreBuilder":
         self._vectors = vectors
@@ -185,11 +206,23 @@ class MetaStoreBuilder:
             if colobj.len() != n_rows:
                 raise OttersError(f"column '{name}' length {colobj.len()} does not match vectors length {n_rows}")
 
+        # row order (extension): cluster the rows on the filter columns before anything is chunked
+        perm = None
+        columns = self._columns
+        if self._row_order is not None:
+            from .reorder import compute_row_order
+
+            if vec_arr is None:
+                raise OttersError("with_row_order needs host vectors (synthetic vectors are generated in row order)")
+            perm = compute_row_order(columns, self._row_order[0], self._row_order[1])
+            columns = {name: c.gather(perm) for name, c in columns.items()}
+            vec_arr = np.ascontiguousarray(vec_arr[perm.astype(np.int64)]) if n_rows else vec_arr
+
         ctx = self._ctx or default_context()
         keep = []  # keeps numpy buffers alive during the call
         ccols = (_ffi.Column * max(len(self._order), 1))()
         for i, name in enumerate(self._order):
-            colobj = self._columns[name]
+            colobj = columns[name]
             cc = ccols[i]
             nb = name.encode("utf-8")
             keep.append(nb)
@@ -226,17 +259,22 @@ class MetaStoreBuilder:
             bp.vectors_kind = _ffi.VECTORS_HOST
             bp.vectors = vec_arr.ctypes.data if vec_arr.size else None
         bp.columns, bp.n_columns = ccols, len(self._order)
+        bp.vector_format = int(self._vector_format)
         h = C.c_void_p()
         bs = _ffi.BuildStats()
         check(_ffi.otters_metastore_build(ctx.handle, C.byref(bp), C.byref(h), C.byref(bs)))
         stats = MetaBuildStats(bs.n_rows, bs.dim, bs.n_chunks, bs.vectors_ingest_s, bs.zonemap_build_s, bs.build_total_s)
-        return MetaStore(ctx, h, dict(self._schema), dict(self._columns), list(self._order), self._chunk_size, dim, n_rows, stats)
+        return MetaStore(ctx, h, dict(self._schema), dict(columns), list(self._order), self._chunk_size, dim, n_rows, stats, perm,
+                         self._vector_format)
 
 
 class MetaStore:
     """src/meta.rs:48-60, :308-577."""
 
-    def __init__(self, ctx, handle, schema, columns, order, chunk_size, dim, n_rows, build_stats):
+    def __init__(self, ctx, handle, schema, columns, order, chunk_size, dim, n_rows, build_stats, perm=None,
+                 vector_format=VectorFormat.F32):
+        self._perm = perm  # store position -> caller's row id (with_row_order); None = identity
+        self._vector_format = vector_format
         self._ctx = ctx
         self._h = handle
         self._schema = schema
@@ -281,7 +319,15 @@ class MetaStore:
         return self._schema
 
     def columns(self) -> Dict[str, Column]:
+        """The columns in STORE order (the input order unless the store was built with_row_order)."""
         return self._columns
+
+    def row_order(self) -> Optional[np.ndarray]:
+        """perm[i] = caller's row id of store position i, or None when the store keeps the input order."""
+        return self._perm
+
+    def vector_format(self) -> VectorFormat:
+        return self._vector_format
 
     def column_index(self) -> Dict[str, int]:
         return self._col_index
@@ -487,7 +533,9 @@ class MetaQueryPlan:
         )
         indices = [int(i) for i in idx[:m]]
         names = sorted(store.schema().keys())  # src/meta.rs:723-724
-        data = {n: store.gather(n, indices) for n in names}  # gathered on the device
+        data = {n: store.gather(n, indices) for n in names}  # gathered on the device (store positions)
+        if store._perm is not None:  # with_row_order: report the caller's row ids
+            indices = [int(store._perm[i]) for i in indices]
         return MetaQueryResults(names, data, indices, [float(s) for s in score[:m]], [int(x) for x in qid[:m]])
 
     def collect_per_query(self) -> List[MetaQueryResults]:

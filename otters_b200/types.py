@@ -49,6 +49,26 @@ class DataType(enum.IntEnum):
     DateTime = 5
 
 
+class VectorFormat(enum.IntEnum):
+    """How a store keeps its rows in HBM (include/otters_b200.h OTTERS_VECTORS_FMT_*; the reference's roadmap item
+    "Quantization for vectors", README.md:208).  Bf16 rounds every element to nearest even when it is added; scores are the
+    reference's arithmetic applied to the rounded rows."""
+
+    F32 = 0
+    Bf16 = 1
+
+
+def round_to_bf16(x):
+    """f32(bf16_rn(x)) on a numpy array: the values a Bf16 store holds (round to nearest even; NaN stays NaN)."""
+    import numpy as np
+
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    b = a.view(np.uint32).astype(np.uint64)
+    r = ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    r = np.where(np.isnan(a), (a.view(np.uint32) & np.uint32(0x80000000)) | np.uint32(0x7FFF0000), r).astype(np.uint32)
+    return r.view(np.float32).reshape(a.shape)
+
+
 def infer_default_take_type(metric: Metric) -> TakeType:
     """src/vec.rs:92-98."""
     return TakeType.Min if metric == Metric.Euclidean else TakeType.Max

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _ffi
 from .context import Context, check, default_context
-from .types import Cmp, Metric, OttersError, TakeType, infer_default_take_type
+from .types import Cmp, Metric, OttersError, TakeType, VectorFormat, infer_default_take_type
 
 
 @dataclass(frozen=True)
@@ -52,10 +52,12 @@ def pack_mask_words(mask) -> np.ndarray:
 
 
 class VecStore:
-    """Flat row-major f32 vectors resident in HBM (src/vec.rs:338-411)."""
+    """Flat row-major f32 vectors resident in HBM (src/vec.rs:338-411).  `vector_format=VectorFormat.Bf16` keeps the rows
+    as bf16 (half the bytes per scan; results are the reference's on the rounded rows, see include/otters_b200.h)."""
 
-    def __init__(self, dim: int, ctx: Optional[Context] = None):
+    def __init__(self, dim: int, ctx: Optional[Context] = None, vector_format: VectorFormat = VectorFormat.F32):
         self.dim = int(dim)
+        self.vector_format = VectorFormat(vector_format)
         self._ctx = ctx
         self._h = None
         self._pending: List[np.ndarray] = []
@@ -67,7 +69,7 @@ class VecStore:
             if self._ctx is None:
                 self._ctx = default_context()
             h = C.c_void_p()
-            check(_ffi.otters_vecstore_create(self._ctx.handle, self.dim, C.byref(h)))
+            check(_ffi.otters_vecstore_create_fmt(self._ctx.handle, self.dim, int(self.vector_format), C.byref(h)))
             self._h = h
         return self._h
 

@@ -34,6 +34,8 @@ pub const OTTERS_DTYPE_DATETIME: c_int = 5;
 pub const OTTERS_LIT_I64: c_int = 0;
 pub const OTTERS_LIT_F64: c_int = 1;
 pub const OTTERS_LIT_STR: c_int = 2;
+pub const OTTERS_VECTORS_FMT_F32: c_int = 0;
+pub const OTTERS_VECTORS_FMT_BF16: c_int = 1;
 pub const OTTERS_VECTORS_HOST: c_int = 0;
 pub const OTTERS_VECTORS_DEVICE: c_int = 1;
 pub const OTTERS_VECTORS_SYNTHETIC: c_int = 2;
@@ -130,6 +132,7 @@ pub struct otters_build_params {
     pub synthetic_map: *const c_void,
     pub columns: *const otters_column,
     pub n_columns: u32,
+    pub vector_format: i32,
 }
 
 #[repr(C)]
@@ -213,6 +216,8 @@ extern "C" {
     pub fn otters_ctx_set_tuning(ctx: *mut otters_ctx, t: *const otters_scan_tuning) -> c_int;
     pub fn otters_ctx_last_work(ctx: *mut otters_ctx, out: *mut otters_last_work) -> c_int;
     pub fn otters_vecstore_create(ctx: *mut otters_ctx, dim: u32, out: *mut *mut otters_vecstore) -> c_int;
+    pub fn otters_vecstore_create_fmt(ctx: *mut otters_ctx, dim: u32, vector_format: i32, out: *mut *mut otters_vecstore) -> c_int;
+    pub fn otters_vecstore_format(vs: *const otters_vecstore) -> i32;
     pub fn otters_vecstore_destroy(vs: *mut otters_vecstore) -> c_int;
     pub fn otters_vecstore_reserve(vs: *mut otters_vecstore, n_rows: u64) -> c_int;
     pub fn otters_vecstore_add(vs: *mut otters_vecstore, rows: *const f32, n: u64) -> c_int;
