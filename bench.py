@@ -165,6 +165,7 @@ class CpuSample:
             pos = np.searchsorted(self.global_rows, prow)
             hit = (pos < self.n) & (self.global_rows[np.minimum(pos, self.n - 1)] == prow)
             self.vectors[pos[hit]] = pvec[hit]
+        self.vectors = wl.stored(self.vectors)
         self.queries = wl.queries()
         self.cores_all = usable_cores()
         self.kept_fraction = None
@@ -281,7 +282,7 @@ def parity_check(wl, results, sample):
             pos = np.searchsorted(prow, rows)
             hit = (pos < len(prow)) & (prow[np.minimum(pos, len(prow) - 1)] == rows)
             v[hit] = pvec[pos[hit]]
-        return v
+        return wl.stored(v)
 
     queries = wl.queries()
     tt = 1 if wl.take_max else 0
@@ -337,7 +338,7 @@ def parity_check(wl, results, sample):
                 break
         # (4) C5: the answer is known by construction — the best k planted rows that pass both filters
         if len(prow):
-            pidx, psc, _ = ora.vecstore_query(pvec, qv[:1], wl.metric_code, 1, len(prow), wl.vec_filter, None, ora.CANONICAL)
+            pidx, psc, _ = ora.vecstore_query(wl.stored(pvec), qv[:1], wl.metric_code, 1, len(prow), wl.vec_filter, None, ora.CANONICAL)
             keep = wl.row_mask(wl.columns(prow))[np.asarray(pidx, np.int64)] if wl.meta else np.ones(len(pidx), bool)
             exp_rows, exp_sc = prow[np.asarray(pidx, np.int64)][keep][: wl.k], np.asarray(psc)[keep][: wl.k]
             if not (np.array_equal(exp_rows, rows) and np.array_equal(exp_sc.view(np.uint32), scores.view(np.uint32))):
@@ -398,15 +399,16 @@ def run_ours(args, wl):
     n_local = bw.cyclic_local_rows(rows, block, world, rank)
     t_build = time.perf_counter()
     fp = None
+    vfmt = ob.VectorFormat.Bf16 if wl.vector_format == "bf16" else ob.VectorFormat.F32
     if wl.meta:
         cols = [c.to_ob(ob) for c in wl.columns(bw.cyclic_global_rows(rows, block, world, rank))]
         store = (ob.MetaStore.from_columns(cols).with_synthetic_vectors(n_local, dim, DATA_SEED, 0, (world, rank, block))
-                 .with_chunk_size(chunk).with_context(ctx).build())
+                 .with_chunk_size(chunk).with_vector_format(vfmt).with_context(ctx).build())
         from otters_b200.meta import FilterPack
 
         fp = FilterPack(wl.expr(ob).compile(store.schema()), store.column_index())
     else:
-        store = ob.VecStore(dim, ctx)
+        store = ob.VecStore(dim, ctx, vfmt)
         store.add_synthetic_sharded(world, rank, block, n_local, DATA_SEED)
     prow, pvec = wl.planted()
     if len(prow):
@@ -597,7 +599,7 @@ def run_ours(args, wl):
         # bytes the library copied for one step (one input image: control block + lowered filter + queries; one result read)
         h2d, d2h = io_bytes
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
-                "traffic": measured_traffic(args.workload, world), "peak_source": peak_src,
+                "traffic": measured_traffic(args.workload, world) if wl.vector_format == "f32" else None, "peak_source": peak_src,
                 "kernel": "scan_kernel (K1: lazy chunk pruning + row predicate + scan + selection in its last CTA)",
                 "scan_ms": float(np.mean(scan_ms)) if scan_ms else None,
                 "algorithmic_bytes_per_launch": float(np.mean(scan_bytes)) if scan_bytes else None}
@@ -624,7 +626,7 @@ def run_ours(args, wl):
         line = {
             "metric": "queries_per_sec", "value": nq * 1e3 / dev_ms, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if wl.vector_format == "f32" else "f32 arithmetic on bf16 rows", "data": "synthetic",
             "config": dict(wl.config(), l2=l2_note(wl)),
             "parallelism": f"rows block-cyclic ({block}-row blocks) over {world} GPU(s)" + (
                 "" if world == 1 else (" + exchange fused into the query kernel (peer stores over NVLink, flags, merge)" if fused
@@ -669,9 +671,11 @@ def main():
     ap.add_argument("--lazy-prune", dest="lazy_prune", type=int, default=0, help="1: chunk pruning inside the scan kernel (A/B)")
     ap.add_argument("--unfused-predicate", dest="disable_fused_predicate", type=int, default=0,
                     help="1: row predicate in its own kernel (K0b row bitmask) instead of inside the scan (A/B)")
+    ap.add_argument("--vector-format", dest="vector_format", default="f32", choices=["f32", "bf16"],
+                    help="bf16: the store keeps bf16 rows (half the bytes per scan); both arms and the parity check score the rounded rows")
     ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"], help="N > 1: fused peer-memory exchange when available, or force NCCL")
     args = ap.parse_args()
-    wl = Workload(args.workload, args.rows)
+    wl = Workload(args.workload, args.rows, args.vector_format)
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -188,10 +188,18 @@ def _columns_mixed(row: np.ndarray, chunk: int) -> List[SpecColumn]:
             SpecColumn("brand", DT_STRING, None, u01(row, 19) < 0.01, [f"brand_{i:02d}" for i in range(20)], brand)]
 
 
+def round_bf16_np(x: np.ndarray) -> np.ndarray:
+    """f32(bf16_rn(x)): the values a store built with --vector-format bf16 holds (round to nearest even)."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    b = a.view(np.uint32).astype(np.uint64)
+    return ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32).reshape(a.shape)
+
+
 class Workload:
-    def __init__(self, name: str, rows_override: int = 0):
+    def __init__(self, name: str, rows_override: int = 0, vector_format: str = "f32"):
         w = dict(WORKLOADS[name])
         self.name = name
+        self.vector_format = vector_format  # "bf16": the store keeps bf16 rows; both arms score the ROUNDED rows
         self.rows = int(rows_override or w["rows"])
         self.dim, self.chunk, self.k = w["dim"], w["chunk"], w["k"]
         self.metric = w["metric"]
@@ -278,7 +286,11 @@ class Workload:
         return {"workload": f"{self.name}: {self.desc}", "rows": self.rows, "dim": self.dim, "k": self.k, "nq": self.nq,
                 "chunk_size": self.chunk, "metric": self.metric, "filter": self.filter_desc(),
                 "vec_filter": ([self.vec_filter[0], ["Lt", "Gt", "Lte", "Gte", "Eq"][self.vec_filter[1]]] if self.vec_filter else None),
-                "planted_rows": self.n_planted}
+                "planted_rows": self.n_planted, "vector_format": self.vector_format}
+
+    def stored(self, vectors: np.ndarray) -> np.ndarray:
+        """The rows as the store holds them (rounded to bf16 for a bf16 store)."""
+        return round_bf16_np(vectors) if self.vector_format == "bf16" else vectors
 
 
 # ---- block-cyclic sharding (same formulas as otters_shard_map) ---------------------------------------------
