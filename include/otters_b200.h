@@ -370,6 +370,21 @@ OTTERS_API int otters_query_exchange(otters_vecstore *vs, otters_metastore *ms, 
                           uint64_t seq, uint64_t *out_idx, float *out_score, uint32_t *out_qid, uint64_t cap,
                           uint64_t *out_len, otters_query_stats *stats /* nullable */);
 
+/* Persistence — the reference's roadmap item "Persistence (save/load MetaStore to/from disk)" (README.md:206).  The file is
+ * the store's HBM image (rows as stored — fp32 or bf16 —, inverse norms, column values, null words, zonemap tables, Bloom
+ * filters, dictionaries) plus `user_bytes` opaque bytes of the caller (the host mirrors keep their row-order permutation
+ * there); otters_metastore_load allocates and copies, nothing is recomputed: a loaded store returns the same bytes and the
+ * same statistics.  Little-endian, versioned ("OTTERSB2", 1); a file whose size does not match its header is rejected
+ * before anything is allocated.  otters_metastore_user_blob / _n_columns / _column_info / _dim / _format describe a loaded
+ * store to the host side (pointers valid while the store lives). */
+OTTERS_API int otters_metastore_save(otters_metastore *ms, const char *path, const void *user /* nullable */, uint64_t user_bytes);
+OTTERS_API int otters_metastore_load(otters_ctx *ctx, const char *path, otters_metastore **out);
+OTTERS_API int otters_metastore_user_blob(const otters_metastore *ms, const void **bytes, uint64_t *len);
+OTTERS_API uint32_t otters_metastore_n_columns(const otters_metastore *ms);
+OTTERS_API int otters_metastore_column_info(const otters_metastore *ms, uint32_t col, const char **name, int32_t *dtype);
+OTTERS_API uint32_t otters_metastore_dim(const otters_metastore *ms);
+OTTERS_API int32_t otters_metastore_format(const otters_metastore *ms);
+
 /* Non-blocking queries.  otters_query_submit enqueues ONE query — chunk pruning, row predicate, scan, selection, and the peer
  * exchange when `ex` is given — on one of the two lanes of the store's context (a lane = its own CUDA stream + scratch +
  * pinned input / result buffers) and returns at once with a ticket; otters_query_wait blocks until that query has finished

@@ -215,6 +215,13 @@ otters_vecstore_query = _sig(
 otters_metastore_build = _sig(
     "otters_metastore_build", C.c_int, _p, C.POINTER(BuildParams), C.POINTER(_p), C.POINTER(BuildStats)
 )
+otters_metastore_save = _sig("otters_metastore_save", C.c_int, _p, C.c_char_p, _p, C.c_uint64)
+otters_metastore_load = _sig("otters_metastore_load", C.c_int, _p, C.c_char_p, C.POINTER(_p))
+otters_metastore_user_blob = _sig("otters_metastore_user_blob", C.c_int, _p, C.POINTER(_p), c_u64p)
+otters_metastore_n_columns = _sig("otters_metastore_n_columns", C.c_uint32, _p)
+otters_metastore_column_info = _sig("otters_metastore_column_info", C.c_int, _p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32))
+otters_metastore_dim = _sig("otters_metastore_dim", C.c_uint32, _p)
+otters_metastore_format = _sig("otters_metastore_format", C.c_int32, _p)
 otters_metastore_destroy = _sig("otters_metastore_destroy", C.c_int, _p)
 otters_metastore_n_chunks = _sig("otters_metastore_n_chunks", C.c_uint64, _p)
 otters_metastore_chunk_size = _sig("otters_metastore_chunk_size", C.c_uint64, _p)

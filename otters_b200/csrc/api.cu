@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libotters_b200.so (include/otters_b200.h): contexts, device-resident stores,
 // query orchestration.  Everything that touches rows runs in the CUDA kernels of scan.cu / select.cu
 // / meta.cu / store.cu; there is no CPU fallback.
+#include <errno.h>
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
@@ -1696,6 +1697,7 @@ struct otters_metastore {
     DevColumn* d_cols = nullptr;
     bool has_stats = false;
     otters_query_stats last{};
+    std::vector<uint8_t> user_blob;  // opaque caller bytes of the file this store was loaded from (otters_metastore_load)
 };
 
 extern "C" int otters_metastore_destroy(otters_metastore* ms) {
@@ -2939,6 +2941,310 @@ extern "C" int otters_metastore_dict_entry(const otters_metastore* ms, uint32_t 
     if (mc.dtype != OTTERS_DTYPE_STRING || code >= mc.dict_strings.size()) return fail(OTTERS_ERR_INVALID, "not a dictionary code of this column");
     *bytes = reinterpret_cast<const uint8_t*>(mc.dict_strings[code].data());
     *len = mc.dict_strings[code].size();
+    return OTTERS_OK;
+}
+
+// =================================================================================================
+// Persistence — the reference's roadmap item "Persistence (save/load MetaStore to/from disk)" (README.md:206;
+// SURVEY.md §8f rank 3).  A built MetaStore is immutable, so the file is simply its HBM image: the rows (fp32 or bf16 as
+// stored), the inverse norms, every column's values / null words / zonemap tables / Bloom filters / dictionary, plus an
+// opaque caller blob (the host mirror keeps its row-order permutation there).  Loading allocates and copies — nothing is
+// recomputed, so a loaded store answers with the same bytes, statistics included.
+// =================================================================================================
+namespace otters {
+namespace {
+
+constexpr char kFileMagic[8] = {'O', 'T', 'T', 'E', 'R', 'S', 'B', '2'};
+constexpr uint32_t kFileVersion = 1;
+constexpr size_t kIoSlab = (size_t)64 << 20;
+
+struct FileHeader {
+    char magic[8];
+    uint32_t version, half;
+    uint64_t n_rows;
+    uint32_t dim, pitch;
+    uint64_t chunk_size, n_chunks;
+    uint32_t n_cols, reserved;
+    uint64_t user_bytes;
+    uint64_t total_bytes;  // of the whole file: a truncated or padded file is rejected before anything is allocated
+};
+
+struct FileIo {
+    FILE* f = nullptr;
+    std::vector<uint8_t> slab;
+    uint64_t pos = 0;
+    ~FileIo() {
+        if (f) fclose(f);
+    }
+    int put(const void* p, size_t n) {
+        if (n && fwrite(p, 1, n, f) != n) return fail(OTTERS_ERR_INVALID, std::string("write failed: ") + strerror(errno));
+        pos += n;
+        return OTTERS_OK;
+    }
+    int get(void* p, size_t n) {
+        if (n && fread(p, 1, n, f) != n) return fail(OTTERS_ERR_INVALID, "store file is truncated");
+        pos += n;
+        return OTTERS_OK;
+    }
+    template <typename T>
+    int put_pod(const T& v) { return put(&v, sizeof(T)); }
+    template <typename T>
+    int get_pod(T* v) { return get(v, sizeof(T)); }
+    int put_dev(const void* d, size_t n) {  // device -> file through a bounce slab
+        if (n && !d) return fail(OTTERS_ERR_INVALID, "store is missing a device array");
+        if (slab.empty()) slab.resize(kIoSlab);
+        for (size_t done = 0; done < n; done += kIoSlab) {
+            const size_t m = std::min(kIoSlab, n - done);
+            OTTERS_CUDA(cudaMemcpy(slab.data(), (const uint8_t*)d + done, m, cudaMemcpyDeviceToHost));
+            int rc = put(slab.data(), m);
+            if (rc) return rc;
+        }
+        return OTTERS_OK;
+    }
+    int get_dev(void* d, size_t n) {
+        if (slab.empty()) slab.resize(kIoSlab);
+        for (size_t done = 0; done < n; done += kIoSlab) {
+            const size_t m = std::min(kIoSlab, n - done);
+            int rc = get(slab.data(), m);
+            if (rc) return rc;
+            OTTERS_CUDA(cudaMemcpy((uint8_t*)d + done, slab.data(), m, cudaMemcpyHostToDevice));
+        }
+        return OTTERS_OK;
+    }
+    template <typename T>
+    int put_vec(const std::vector<T>& v) {
+        const uint64_t n = v.size();
+        int rc = put_pod(n);
+        return rc ? rc : put(v.data(), n * sizeof(T));
+    }
+    template <typename T>
+    int get_vec(std::vector<T>* v, uint64_t max_elems) {
+        uint64_t n = 0;
+        int rc = get_pod(&n);
+        if (rc) return rc;
+        if (n > max_elems) return fail(OTTERS_ERR_INVALID, "store file is corrupt (table larger than the store)");
+        v->resize(n);
+        return get(v->data(), n * sizeof(T));
+    }
+};
+
+struct ColHeader {
+    int32_t dtype;
+    uint32_t has_nulls, has_zonemap, has_bloom;
+    uint64_t value_bytes, bloom_stride;
+    uint32_t bloom_k0, name_len;
+};
+
+template <typename T>
+int dev_new(T** dptr, size_t bytes) {
+    *dptr = nullptr;
+    if (cudaMalloc((void**)dptr, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OTTERS_ERR_NOMEM, "device allocation for the loaded store failed");
+    }
+    return OTTERS_OK;
+}
+
+}  // namespace
+}  // namespace otters
+
+extern "C" int otters_metastore_save(otters_metastore* ms, const char* path, const void* user, uint64_t user_bytes) {
+    if (!ms || !path) return fail(OTTERS_ERR_INVALID, "null argument");
+    if (user_bytes && !user) return fail(OTTERS_ERR_INVALID, "null user blob");
+    DeviceGuard g(ms->ctx->device);
+    if (otters_ctx_synchronize(ms->ctx) != OTTERS_OK) return OTTERS_ERR_CUDA;
+    FileIo io;
+    io.f = fopen(path, "wb");
+    if (!io.f) return fail(OTTERS_ERR_INVALID, std::string("cannot open '") + path + "' for writing: " + strerror(errno));
+    const VecStorage& st = ms->st;
+    const uint64_t n = st.n, nc = ms->n_chunks;
+    FileHeader h{};
+    memcpy(h.magic, kFileMagic, 8);
+    h.version = kFileVersion;
+    h.half = st.half ? 1u : 0u;
+    h.n_rows = n;
+    h.dim = st.dim;
+    h.pitch = st.pitch;
+    h.chunk_size = ms->chunk_size;
+    h.n_chunks = nc;
+    h.n_cols = (uint32_t)ms->cols.size();
+    h.user_bytes = user_bytes;
+    int rc = io.put_pod(h);  // total_bytes is patched at the end
+    if (!rc) rc = io.put(user, user_bytes);
+    if (!rc) rc = io.put_dev(st.d_rows, (size_t)n * st.pitch * st.esz());
+    if (!rc) rc = io.put_dev(st.d_inv, (size_t)n * 4);
+    for (size_t i = 0; i < ms->cols.size() && !rc; ++i) {
+        const MetaColumn& mc = ms->cols[i];
+        ColHeader ch{};
+        ch.dtype = mc.dtype;
+        ch.has_nulls = mc.d_nulls ? 1u : 0u;
+        ch.has_zonemap = (mc.d_zmin && mc.d_zmax) ? 1u : 0u;
+        ch.has_bloom = mc.d_bloom ? 1u : 0u;
+        ch.value_bytes = mc.value_bytes;
+        ch.bloom_stride = mc.bloom_stride;
+        ch.bloom_k0 = mc.bloom_k0;
+        ch.name_len = (uint32_t)mc.name.size();
+        rc = io.put_pod(ch);
+        if (!rc) rc = io.put(mc.name.data(), mc.name.size());
+        if (!rc) rc = io.put_dev(mc.d_values, (size_t)n * mc.value_bytes);
+        if (!rc && ch.has_nulls) rc = io.put_dev(mc.d_nulls, (size_t)((n + 63) / 64) * 8);
+        if (!rc && ch.has_zonemap) rc = io.put_dev(mc.d_zmin, (size_t)nc * mc.value_bytes);
+        if (!rc && ch.has_zonemap) rc = io.put_dev(mc.d_zmax, (size_t)nc * mc.value_bytes);
+        if (!rc) rc = io.put_dev(mc.d_non_null, (size_t)nc * 4);
+        if (!rc && ch.has_bloom) rc = io.put_dev(mc.d_bloom, (size_t)nc * mc.bloom_stride * 8);
+        if (!rc && ch.has_bloom) rc = io.put_dev(mc.d_bloom_mbits, (size_t)nc * 8);
+        if (!rc && ch.has_bloom) rc = io.put_dev(mc.d_bloom_k, (size_t)nc * 4);
+        if (!rc) rc = io.put_vec(mc.zmin_i);
+        if (!rc) rc = io.put_vec(mc.zmax_i);
+        if (!rc) rc = io.put_vec(mc.zmin_f);
+        if (!rc) rc = io.put_vec(mc.zmax_f);
+        if (!rc) rc = io.put_vec(mc.non_null);
+        const uint64_t nd = mc.dict_strings.size();
+        if (!rc) rc = io.put_pod(nd);
+        for (uint64_t d = 0; d < nd && !rc; ++d) {
+            const uint64_t len = mc.dict_strings[d].size();
+            rc = io.put_pod(len);
+            if (!rc) rc = io.put(mc.dict_strings[d].data(), len);
+        }
+    }
+    if (!rc) {
+        h.total_bytes = io.pos;
+        if (fseek(io.f, 0, SEEK_SET) != 0 || fwrite(&h, 1, sizeof(h), io.f) != sizeof(h)) rc = fail(OTTERS_ERR_INVALID, "write failed");
+    }
+    if (fclose(io.f) != 0 && !rc) rc = fail(OTTERS_ERR_INVALID, std::string("write failed: ") + strerror(errno));
+    io.f = nullptr;
+    if (rc) remove(path);
+    return rc;
+}
+
+extern "C" int otters_metastore_load(otters_ctx* c, const char* path, otters_metastore** out) {
+    if (!c || !path || !out) return fail(OTTERS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    DeviceGuard g(c->device);
+    FileIo io;
+    io.f = fopen(path, "rb");
+    if (!io.f) return fail(OTTERS_ERR_INVALID, std::string("cannot open '") + path + "': " + strerror(errno));
+    FileHeader h{};
+    int rc = io.get_pod(&h);
+    if (rc) return rc;
+    if (memcmp(h.magic, kFileMagic, 8) != 0) return fail(OTTERS_ERR_INVALID, "not an otters_b200 store file");
+    if (h.version != kFileVersion) return fail(OTTERS_ERR_UNSUPPORTED, "store file version " + std::to_string(h.version) + " is not supported");
+    if (fseek(io.f, 0, SEEK_END) != 0) return fail(OTTERS_ERR_INVALID, "cannot seek in the store file");
+    const uint64_t actual = (uint64_t)ftell(io.f);
+    if (actual != h.total_bytes) return fail(OTTERS_ERR_INVALID, "store file is truncated or corrupt (size does not match its header)");
+    fseek(io.f, (long)sizeof(h), SEEK_SET);
+    const uint64_t want_pitch = round_up(std::max<uint32_t>(h.dim, 1), h.half ? 8 : 4);
+    const uint64_t cs = std::max<uint64_t>(h.chunk_size, 1);
+    if (h.half > 1 || h.pitch != want_pitch || h.n_chunks != (h.n_rows + cs - 1) / cs || h.n_rows >= 0xFFFFFFF0ull || h.n_cols > 65536 ||
+        h.user_bytes > actual)
+        return fail(OTTERS_ERR_INVALID, "store file is corrupt (inconsistent header)");
+
+    std::unique_ptr<otters_metastore> ms(new otters_metastore());
+    auto cleanup = [&](int r) {
+        otters_metastore_destroy(ms.release());
+        return r;
+    };
+    ms->ctx = c;
+    ms->chunk_size = cs;
+    ms->n_chunks = h.n_chunks;
+    ms->st.ctx = c;
+    ms->st.set_format(h.dim, h.half != 0);
+    ms->user_blob.resize(h.user_bytes);
+    if ((rc = io.get(ms->user_blob.data(), h.user_bytes))) return cleanup(rc);
+    const uint64_t n = h.n_rows, nc = h.n_chunks;
+    if ((rc = ms->st.reserve(n))) return cleanup(rc);
+    if ((rc = io.get_dev(ms->st.d_rows, (size_t)n * ms->st.pitch * ms->st.esz()))) return cleanup(rc);
+    if ((rc = io.get_dev(ms->st.d_inv, (size_t)n * 4))) return cleanup(rc);
+    ms->st.n = n;
+    ms->cols.resize(h.n_cols);
+    std::vector<DevColumn> dcols(h.n_cols);
+    for (uint32_t i = 0; i < h.n_cols; ++i) {
+        MetaColumn& mc = ms->cols[i];
+        ColHeader ch{};
+        if ((rc = io.get_pod(&ch))) return cleanup(rc);
+        const bool is_str = ch.dtype == OTTERS_DTYPE_STRING;
+        if (ch.dtype < 0 || ch.dtype > OTTERS_DTYPE_DATETIME || (ch.value_bytes != 4 && ch.value_bytes != 8) || ch.name_len > 4096 ||
+            (ch.has_bloom && (ch.bloom_stride == 0 || ch.bloom_stride > ((uint64_t)1 << 24))) || (is_str && ch.value_bytes != 4))
+            return cleanup(fail(OTTERS_ERR_INVALID, "store file is corrupt (column header)"));
+        mc.dtype = ch.dtype;
+        mc.value_bytes = ch.value_bytes;
+        mc.bloom_stride = ch.bloom_stride;
+        mc.bloom_k0 = ch.bloom_k0;
+        mc.name.resize(ch.name_len);
+        if ((rc = io.get(&mc.name[0], ch.name_len))) return cleanup(rc);
+        if ((rc = dev_new((uint8_t**)&mc.d_values, (size_t)n * mc.value_bytes))) return cleanup(rc);
+        if ((rc = io.get_dev(mc.d_values, (size_t)n * mc.value_bytes))) return cleanup(rc);
+        if (ch.has_nulls) {
+            if ((rc = dev_new(&mc.d_nulls, (size_t)((n + 63) / 64) * 8))) return cleanup(rc);
+            if ((rc = io.get_dev(mc.d_nulls, (size_t)((n + 63) / 64) * 8))) return cleanup(rc);
+        }
+        if (ch.has_zonemap) {
+            if ((rc = dev_new((uint8_t**)&mc.d_zmin, (size_t)nc * mc.value_bytes))) return cleanup(rc);
+            if ((rc = io.get_dev(mc.d_zmin, (size_t)nc * mc.value_bytes))) return cleanup(rc);
+            if ((rc = dev_new((uint8_t**)&mc.d_zmax, (size_t)nc * mc.value_bytes))) return cleanup(rc);
+            if ((rc = io.get_dev(mc.d_zmax, (size_t)nc * mc.value_bytes))) return cleanup(rc);
+        }
+        if ((rc = dev_new(&mc.d_non_null, (size_t)nc * 4))) return cleanup(rc);
+        if ((rc = io.get_dev(mc.d_non_null, (size_t)nc * 4))) return cleanup(rc);
+        if (ch.has_bloom) {
+            if ((rc = dev_new(&mc.d_bloom, (size_t)nc * mc.bloom_stride * 8))) return cleanup(rc);
+            if ((rc = io.get_dev(mc.d_bloom, (size_t)nc * mc.bloom_stride * 8))) return cleanup(rc);
+            if ((rc = dev_new(&mc.d_bloom_mbits, (size_t)nc * 8))) return cleanup(rc);
+            if ((rc = io.get_dev(mc.d_bloom_mbits, (size_t)nc * 8))) return cleanup(rc);
+            if ((rc = dev_new(&mc.d_bloom_k, (size_t)nc * 4))) return cleanup(rc);
+            if ((rc = io.get_dev(mc.d_bloom_k, (size_t)nc * 4))) return cleanup(rc);
+        }
+        if ((rc = io.get_vec(&mc.zmin_i, nc))) return cleanup(rc);
+        if ((rc = io.get_vec(&mc.zmax_i, nc))) return cleanup(rc);
+        if ((rc = io.get_vec(&mc.zmin_f, nc))) return cleanup(rc);
+        if ((rc = io.get_vec(&mc.zmax_f, nc))) return cleanup(rc);
+        if ((rc = io.get_vec(&mc.non_null, nc))) return cleanup(rc);
+        uint64_t nd = 0;
+        if ((rc = io.get_pod(&nd))) return cleanup(rc);
+        if (nd > n + 1) return cleanup(fail(OTTERS_ERR_INVALID, "store file is corrupt (dictionary larger than the store)"));
+        mc.dict_strings.resize(nd);
+        for (uint64_t d = 0; d < nd; ++d) {
+            uint64_t len = 0;
+            if ((rc = io.get_pod(&len))) return cleanup(rc);
+            if (len > actual) return cleanup(fail(OTTERS_ERR_INVALID, "store file is corrupt (dictionary entry)"));
+            mc.dict_strings[d].resize(len);
+            if ((rc = io.get(&mc.dict_strings[d][0], len))) return cleanup(rc);
+            mc.dict.emplace(mc.dict_strings[d], (uint32_t)d);
+        }
+        DevColumn& d = dcols[i];
+        d.dtype = mc.dtype;
+        d.values = mc.d_values;
+        d.null_words = mc.d_nulls;
+        d.zmin = mc.d_zmin;
+        d.zmax = mc.d_zmax;
+        d.non_null = mc.d_non_null;
+        d.bloom = mc.d_bloom;
+        d.bloom_stride = mc.bloom_stride;
+        d.bloom_mbits = mc.d_bloom_mbits;
+        d.bloom_k = mc.d_bloom_k;
+    }
+    if (io.pos != actual) return cleanup(fail(OTTERS_ERR_INVALID, "store file is corrupt (trailing bytes)"));
+    if ((rc = upload(&ms->d_cols, dcols.data(), dcols.size() * sizeof(DevColumn)))) return cleanup(rc);
+    *out = ms.release();
+    return OTTERS_OK;
+}
+
+extern "C" int otters_metastore_user_blob(const otters_metastore* ms, const void** bytes, uint64_t* len) {
+    if (!ms || !bytes || !len) return fail(OTTERS_ERR_INVALID, "null argument");
+    *bytes = ms->user_blob.data();
+    *len = ms->user_blob.size();
+    return OTTERS_OK;
+}
+
+extern "C" uint32_t otters_metastore_n_columns(const otters_metastore* ms) { return ms ? (uint32_t)ms->cols.size() : 0; }
+extern "C" uint32_t otters_metastore_dim(const otters_metastore* ms) { return ms ? ms->st.dim : 0; }
+extern "C" int32_t otters_metastore_format(const otters_metastore* ms) {
+    return ms && ms->st.half ? OTTERS_VECTORS_FMT_BF16 : OTTERS_VECTORS_FMT_F32;
+}
+extern "C" int otters_metastore_column_info(const otters_metastore* ms, uint32_t col, const char** name, int32_t* dtype) {
+    if (!ms || col >= ms->cols.size() || !name || !dtype) return fail(OTTERS_ERR_INVALID, "unknown column");
+    *name = ms->cols[col].name.c_str();
+    *dtype = ms->cols[col].dtype;
     return OTTERS_OK;
 }
 

@@ -307,6 +307,34 @@ class MetaStore:
             cols[name] = Column(name, DataType(dt))
         return MetaStoreBuilder(sch, cols, order)
 
+    # ---- persistence (extension: the reference's roadmap item "save/load MetaStore to/from disk", README.md:206) ----------
+    def save(self, path: str) -> None:
+        """Writes the store's HBM image to ``path`` (``otters_metastore_save``); a row order (with_row_order) travels in the
+        file's caller blob, so a loaded store keeps reporting the caller's row ids."""
+        blob = np.ascontiguousarray(self._perm, dtype=np.uint64) if self._perm is not None else None
+        check(_ffi.otters_metastore_save(self._h, str(path).encode("utf-8"), C.c_void_p(blob.ctypes.data) if blob is not None else None,
+                                         blob.nbytes if blob is not None else 0))
+
+    @staticmethod
+    def load(path: str, ctx: Optional[Context] = None) -> "MetaStore":
+        """Loads a store written by ``save`` (``otters_metastore_load``): device arrays are copied back as they were, nothing is
+        rebuilt.  The host-side Column objects are not part of the file: ``columns()`` is empty, result columns come from the
+        device gather as always."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(_ffi.otters_metastore_load(ctx.handle, str(path).encode("utf-8"), C.byref(h)))
+        schema, order = {}, []
+        for i in range(_ffi.otters_metastore_n_columns(h)):
+            name, dt = C.c_char_p(), C.c_int32(0)
+            check(_ffi.otters_metastore_column_info(h, i, C.byref(name), C.byref(dt)))
+            schema[name.value.decode("utf-8")] = DataType(dt.value)
+            order.append(name.value.decode("utf-8"))
+        p, ln = C.c_void_p(), C.c_uint64(0)
+        check(_ffi.otters_metastore_user_blob(h, C.byref(p), C.byref(ln)))
+        perm = np.frombuffer(C.string_at(p, ln.value), dtype=np.uint64).copy() if ln.value else None
+        return MetaStore(ctx, h, schema, {}, order, int(_ffi.otters_metastore_chunk_size(h)), int(_ffi.otters_metastore_dim(h)),
+                         int(_ffi.otters_metastore_len(h)), None, perm, VectorFormat(_ffi.otters_metastore_format(h)))
+
     @property
     def ctx(self) -> Context:
         return self._ctx

@@ -91,6 +91,14 @@ fn flatten(r: &ResolvedQuery<'_>) -> FlatQuery {
 // =====================================================================================================================
 // VecStore
 // =====================================================================================================================
+/// How a store keeps its rows in HBM (OTTERS_VECTORS_FMT_* of include/otters_b200.h).
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+#[repr(i32)]
+pub enum VectorFormat {
+    F32 = 0,
+    Bf16 = 1,
+}
+
 pub struct DeviceVecStore<'c> {
     ctx: &'c DeviceContext,
     vs: *mut sys::otters_vecstore,
@@ -100,8 +108,13 @@ pub struct DeviceVecStore<'c> {
 impl<'c> DeviceVecStore<'c> {
     /// VecStore::new (src/vec.rs:346-355)
     pub fn new(ctx: &'c DeviceContext, dim: usize) -> Result<Self, String> {
+        Self::with_format(ctx, dim, VectorFormat::F32)
+    }
+
+    /// A store whose rows are kept as `format` (see VectorFormat).
+    pub fn with_format(ctx: &'c DeviceContext, dim: usize, format: VectorFormat) -> Result<Self, String> {
         let mut vs = ptr::null_mut();
-        check(unsafe { sys::otters_vecstore_create(ctx.raw, dim as u32, &mut vs) })?;
+        check(unsafe { sys::otters_vecstore_create_fmt(ctx.raw, dim as u32, format as i32, &mut vs) })?;
         Ok(Self { ctx, vs, dim })
     }
 
@@ -311,6 +324,13 @@ impl<'c> DeviceMetaStore<'c> {
     /// The body of MetaStoreBuilder::build (src/meta.rs:151-305) after its own validation: vectors and columns go to HBM,
     /// zonemaps / Bloom filters / dictionary codes are built there (otters_b200/csrc/build.cu).  `columns` in schema order.
     pub fn build(ctx: &'c DeviceContext, vectors: &[Vec<f32>], columns: &[&Column], chunk_size: usize, bloom: BloomSpec) -> Result<Self, String> {
+        Self::build_with_format(ctx, vectors, columns, chunk_size, bloom, VectorFormat::F32)
+    }
+
+    /// Same, with the rows kept in HBM as `format` (VectorFormat::Bf16: half the bytes per scan; scores are the
+    /// reference's arithmetic on the rounded rows — the roadmap's "Quantization for vectors", README.md:208).
+    pub fn build_with_format(ctx: &'c DeviceContext, vectors: &[Vec<f32>], columns: &[&Column], chunk_size: usize, bloom: BloomSpec,
+                             format: VectorFormat) -> Result<Self, String> {
         let dim = vectors.first().map_or(0, |v| v.len());
         let mut flat = Vec::with_capacity(vectors.len() * dim);
         for v in vectors {
@@ -385,6 +405,7 @@ impl<'c> DeviceMetaStore<'c> {
             synthetic_map: ptr::null(),
             columns: ffi_cols.as_ptr(),
             n_columns: ffi_cols.len() as u32,
+            vector_format: format as i32,
         };
         let mut ms = ptr::null_mut();
         let mut st = sys::otters_build_stats::default();

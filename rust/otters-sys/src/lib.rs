@@ -247,6 +247,13 @@ extern "C" {
     pub fn otters_metastore_inv_norms(ms: *const otters_metastore, first: u64, n: u64, out: *mut f32) -> c_int;
     pub fn otters_query_local_device(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, map: *const otters_shard_map, d_records: *mut c_void, stats: *mut otters_query_stats) -> c_int;
     pub fn otters_query_exchange(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, map: *const otters_shard_map, ex: *const otters_peer_exchange, seq: u64, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
+    pub fn otters_metastore_save(ms: *mut otters_metastore, path: *const c_char, user: *const c_void, user_bytes: u64) -> c_int;
+    pub fn otters_metastore_load(ctx: *mut otters_ctx, path: *const c_char, out: *mut *mut otters_metastore) -> c_int;
+    pub fn otters_metastore_user_blob(ms: *const otters_metastore, bytes: *mut *const c_void, len: *mut u64) -> c_int;
+    pub fn otters_metastore_n_columns(ms: *const otters_metastore) -> u32;
+    pub fn otters_metastore_column_info(ms: *const otters_metastore, col: u32, name: *mut *const c_char, dtype: *mut i32) -> c_int;
+    pub fn otters_metastore_dim(ms: *const otters_metastore) -> u32;
+    pub fn otters_metastore_format(ms: *const otters_metastore) -> i32;
     pub fn otters_query_submit(vs: *mut otters_vecstore, ms: *mut otters_metastore, q: *const otters_vec_query, filter: *const otters_filter, map: *const otters_shard_map, ex: *const otters_peer_exchange, seq: u64, ticket: *mut u64) -> c_int;
     pub fn otters_query_wait(ctx: *mut otters_ctx, ticket: u64, out_idx: *mut u64, out_score: *mut f32, out_qid: *mut u32, cap: u64, out_len: *mut u64, stats: *mut otters_query_stats) -> c_int;
     pub fn otters_vecstore_add_synthetic_sharded(vs: *mut otters_vecstore, map: *const otters_shard_map, n_local: u64, seed: u64) -> c_int;
