@@ -908,8 +908,10 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     {
         static const int kps = getenv("OTTERS_K2_KPS") ? atoi(getenv("OTTERS_K2_KPS")) : 3;  // clamped in the kernel to leave two stages
         static const int direct = getenv("OTTERS_K2_DIRECT") ? atoi(getenv("OTTERS_K2_DIRECT")) : 1;
+        static const int epi = getenv("OTTERS_K2_EPI_WARPS") ? atoi(getenv("OTTERS_K2_EPI_WARPS")) : 8;  // A/B: 4 = one epilogue warp per scheduler
         bp.kps = (uint32_t)kps;
         bp.pair_direct = (uint32_t)direct;
+        bp.epi_warps = epi == 4 ? 4u : 8u;
     }
 #ifdef OTTERS_K2_EXPERIMENTS
     // timing experiments only (role-by-role timing of K2, scripts/dbg_passes_roles.py): results are garbage, so the hooks are

@@ -47,7 +47,8 @@ constexpr uint32_t kAuxTmemSlot = 448, kAuxHdr = 512, kAuxCand = 640;
 constexpr uint32_t UK = 8;              // K of one tcgen05.mma kind::tf32
 constexpr uint32_t A_BYTES = BM * BK * 4;  // 16 KB: the V tile of one CTA and one k-block
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t NUM_THREADS = 384;
+constexpr uint32_t NUM_THREADS = 512;   // launch bound; the kernel is launched with 384 + 32 * (extra epilogue warps) threads
+constexpr uint32_t BASE_WARPS = 8;      // warps 0-7: producer, MMA issuer, TMEM allocator, relay, four split warps
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -656,7 +657,14 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
         }
     } else if (warp >= 8) {
         // ===== epilogue: TMEM -> metric -> loosened filter -> per-CTA top-k of approximate scores =====
+        // Four or EIGHT warps (blockDim): a warp may only read the TMEM lanes of its quarter (warp % 4), so with eight warps the
+        // two warps of a quarter take the even / odd 32-column chunks.  One epilogue warp per scheduler runs its dependent
+        // chains at ~0.25 instructions per cycle (ncu: 330 instructions and ~1400 cycles per chunk, profiles/r2b_batch_c2_bf16_*):
+        // once the bf16 rung halved the MMA time the epilogue became the bound, and a second warp per scheduler hides that latency.
         const uint32_t quarter = (uint32_t)warp & 3u;  // TMEM lanes [32*quarter, 32*quarter+32)
+        const uint32_t epi_threads = blockDim.x - BASE_WARPS * 32u;       // 128 or 256
+        const uint32_t cstep = epi_threads >> 7;                          // column chunks are dealt round-robin to 1 or 2 warps per quarter
+        const uint32_t cfirst = ((uint32_t)warp - BASE_WARPS) >> 2;       // 0 or 1
         const bool take_max = p.take_max != 0;
         unsigned long long scored = 0;
         uint32_t tn = 0;
@@ -681,11 +689,11 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
             }
             const uint32_t q_base = qt * BN;
             const uint32_t nq_tile = p.nq - q_base < BN ? p.nq - q_base : BN;
-            if (live) scored += nq_tile;
+            if (live && cfirst == 0) scored += nq_tile;  // (one warp of the quarter accounts the row)
             mbar_wait(&bar_tfull[buf], bph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * BN;
-            for (uint32_t c = 0; c < BN / 32; ++c) {
+            for (uint32_t c = cfirst; c < BN / 32; c += cstep) {
                 if (c * 32 >= nq_tile || (p.dbg & 4u)) break;  // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c * 32, v);
@@ -750,7 +758,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                 }
             }
             tc_fence_before();
-            named_bar_sync(3, 128);  // every epilogue thread has drained its TMEM lanes; one thread signals
+            named_bar_sync(3, epi_threads);  // every epilogue thread has drained its TMEM lanes; one thread signals
             if (warp == 8 && lane == 0) {
                 if (CG == 2 && rank != 0) mbar_arrive_remote(&bar_tempty[buf], 0);
                 else mbar_arrive(&bar_tempty[buf]);
@@ -769,7 +777,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) scored += __shfl_xor_sync(FULL, scored, d);
         if (lane == 0 && scored) atomicAdd(p.pairs_scored, scored);
-        named_bar_sync(1, 128);  // the four epilogue warps: every push has completed
+        named_bar_sync(1, epi_threads);  // the epilogue warps: every push has completed
         if (warp == 8) {
             const uint32_t cnt = hdr->count;
             warp_sort_pairs(cand_keys, cand_qids, cnt, p.cap, lane);
@@ -1048,7 +1056,7 @@ int launch_batch_one(const CUtensorMap& tv, const CUtensorMap& tqh, const CUtens
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3((BASE_WARPS + (p.epi_warps == 4u ? 4u : 8u)) * 32u);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
