@@ -147,8 +147,8 @@ OTTERS_API int otters_vecstore_create(otters_ctx *ctx, uint32_t dim, otters_vecs
  * OTTERS_VECTORS_FMT_BF16: every element is rounded to bf16 (nearest even) when it is added and the store keeps 2 bytes per
  * element — half the bytes of a scan that runs at the HBM limit.  The parity contract is the reference's arithmetic applied
  * to the ROUNDED rows: scores, inverse norms and results are bit-identical to the CPU path run on f32(bf16(x)) (queries
- * stay fp32; widening a bf16 value to fp32 is exact).  Rows are still passed in as fp32.  Query batches on a bf16 store are
- * answered query by query on the streaming kernel. */
+ * stay fp32; widening a bf16 value to fp32 is exact).  Rows are still passed in as fp32.  Query batches on a bf16 store run on the
+ * tensor cores with the stored rows as the bf16 operand (one rung; exact re-scoring from the same rows). */
 #define OTTERS_VECTORS_FMT_F32 0
 #define OTTERS_VECTORS_FMT_BF16 1
 OTTERS_API int otters_vecstore_create_fmt(otters_ctx *ctx, uint32_t dim, int32_t vector_format, otters_vecstore **out);

@@ -762,7 +762,7 @@ static int store_min_inv_norm(otters_ctx* c, VecStorage* st) {
 // The bf16 shadow costs half of the store again; in automatic mode it is built only when that leaves the device half empty.
 static int ensure_bf16_shadow(otters_ctx* c, VecStorage* st, bool force, bool* ok) {
     *ok = false;
-    if (st->h_valid) {
+    if (st->half || st->h_valid) {  // a bf16 store IS its own bf16 operand
         *ok = true;
         return OTTERS_OK;
     }
@@ -852,7 +852,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     if (rc) return rc;
     const uint32_t q_pitch_h = (uint32_t)round_up(st->dim, 8);
     if (passes == 2) {
-        if (!st->h_valid) return fail(OTTERS_ERR_INVALID, "the bf16 rung was requested without its shadow rows");
+        if (!st->half && !st->h_valid) return fail(OTTERS_ERR_INVALID, "the bf16 rung was requested without its shadow rows");
         rc = ensure_dev(&c->d_qb, &c->d_qb_elems, (size_t)nq_pad * q_pitch_h, s);
         if (rc) return rc;
         rc = launch_convert_bf16(c->d_query, dim_pad, q->nq, st->dim, c->d_qb, q_pitch_h, nq_pad, s);
@@ -876,8 +876,8 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     bl.dim_pad = dim_pad;
     bl.q_hi = c->d_qh;
     bl.q_lo = c->d_ql;
-    bl.v_half = st->d_rows_h;
-    bl.pitch_h = st->pitch_h;
+    bl.v_half = st->half ? reinterpret_cast<const uint16_t*>(st->d_rows) : st->d_rows_h;
+    bl.pitch_h = st->half ? st->pitch : st->pitch_h;
     bl.q_half = c->d_qb;
     bl.q_pitch_h = q_pitch_h;
     bl.nq_pad = nq_pad;
@@ -940,6 +940,7 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     rc = ensure_list0(c, k_eff);
     if (rc) return rc;
     RescoreParams rp{};
+    rp.half = st->half ? 1u : 0u;
     rp.vectors = st->d_rows;
     rp.inv_norms = st->d_inv;
     rp.queries = c->d_query;
@@ -1039,16 +1040,20 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
     int rc = io_flush(c);
     if (rc) return rc;
 
-    // (bf16 stores answer batches query by query on the streaming kernel: K2's exact re-scoring reads fp32 rows)
-    if (!c->ex_active && !st->half && batch_eligible(c, q, n_rows, k_eff)) {
+    if (!c->ex_active && batch_eligible(c, q, n_rows, k_eff)) {
         // selection runs single-pass tf32 first (a third of the MMAs and of the operand traffic; error bound 2^-9 |q||v|);
         // when its certificate fails the batch is redone with the 3xTF32 split (2^-15), and only then query by query.
         // A store whose single-pass certificate failed goes straight to 3xTF32 for its next kSinglePassBackoff batches.
         // The bf16 rung (a bf16 shadow of the rows, half the operand bytes and twice the MMA rate, bound 2^-7 |q||v|) goes first
         // when the shadow exists or can be built; every rung is selection only and carries the same kind of certificate.
-        const uint32_t want = c->tuning.batch_passes;
+        // A bf16 STORE has one rung: its rows are the bf16 operand (no shadow, no operand error on the row side) and the exact
+        // re-scoring reads the same rows; the tf32 rungs would need fp32 rows, so a declined certificate goes to K1.
+        const bool half_auto = st->half && c->tuning.batch_passes != 2;  // (its declined certificates back off like the ladder's)
+        const uint32_t want = st->half ? 2u : c->tuning.batch_passes;
         bool accepted = false;
-        if (want == 2 || (want == 0 && st->bf16_backoff == 0)) {
+        if (half_auto && st->bf16_backoff) {
+            st->bf16_backoff -= 1;
+        } else if (want == 2 || (want == 0 && st->bf16_backoff == 0)) {
             bool have = false;
             rc = ensure_bf16_shadow(c, st, want == 2, &have);
             if (rc) return rc;
@@ -1057,7 +1062,7 @@ static int run_queries(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
                 rc = run_batched(c, st, q, d_row_mask, row_mask_words, d_records_out, map, stats_src, run, 2, &accepted);
                 if (rc) return rc;
                 if (accepted) return OTTERS_OK;
-                if (want == 0) st->bf16_backoff = kSinglePassBackoff;
+                if (want == 0 || half_auto) st->bf16_backoff = kSinglePassBackoff;
                 rc = reset_scan_state(c);
                 if (rc) return rc;
                 c->last.batch_fallback = want == 2 ? 1 : 0;
@@ -2396,7 +2401,7 @@ static int meta_enqueue(otters_ctx* c, otters_metastore* ms, const otters_vec_qu
         if (rc) return rc;
     }
     // the batched tensor-core kernel gates rows with a precomputed mask (K0b) instead of the fused predicate
-    const bool batched = scan && !c->ex_active && !ms->st.half && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
+    const bool batched = scan && !c->ex_active && batch_eligible(c, q, ms->st.n, std::min<uint64_t>(q->k, ms->st.n * (uint64_t)q->nq));
     const uint32_t n_leaves = filter && filter->clause_offsets ? filter->clause_offsets[filter->n_clauses] : 0;
     // Row predicate: by default its own kernel (K0b writes the surviving-row bitmask at HBM bandwidth, the scan's producer then
     // reads one mask word per 32 rows); the scan kernel can also evaluate the CNF itself per work unit (fused K0b:

@@ -870,7 +870,8 @@ __global__ void batch_delta_kernel(int metric, uint32_t dim, uint32_t passes, co
 // Two threads per pair hold the eight f32x8 lane accumulators (4 each) exactly like K1 (scan.cu): multiply and
 // add are separate round-to-nearest operations, 8-column blocks in order, wide's non-AVX reduce_add order,
 // serial dim%8 tail added last, cosine as (dot * q_inv) * row_inv (reference src/vec_compute.rs:9-54).
-template <int METRIC>
+// HALF: the store's rows are bf16 (OTTERS_VECTORS_FMT_BF16): widened exactly, same arithmetic (as K1's load_row4<HALF>).
+template <int METRIC, bool HALF>
 __global__ void __launch_bounds__(256) rescore_kernel(const __grid_constant__ RescoreParams p) {
     const uint32_t slot = blockIdx.x * (blockDim.x >> 1) + (threadIdx.x >> 1);
     const int h = threadIdx.x & 1;
@@ -887,16 +888,25 @@ __global__ void __launch_bounds__(256) rescore_kernel(const __grid_constant__ Re
     }
     const bool take_max = p.take_max != 0;
     const uint32_t dim8 = p.dim & ~7u, ntail = p.dim & 7u;
-    const float* vrow = p.vectors + (size_t)row * p.pitch_g;
+    const float* vrow = p.vectors + (size_t)row * p.pitch_g;                                      // fp32 rows
+    const uint16_t* vrow_h = reinterpret_cast<const uint16_t*>(p.vectors) + (size_t)row * p.pitch_g;  // bf16 rows
     const float* qrow = p.queries + (size_t)qid * p.dim_pad;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if (valid) {
         const float4* vp = reinterpret_cast<const float4*>(vrow) + h;
+        const uint2* vph = reinterpret_cast<const uint2*>(vrow_h) + h;
         const float4* qp = reinterpret_cast<const float4*>(qrow) + h;
         const uint32_t nblk = dim8 >> 3;
 #pragma unroll 4
         for (uint32_t j = 0; j < nblk; ++j) {
-            const float4 v = __ldg(vp + 2 * j);
+            float4 v;
+            if constexpr (HALF) {
+                const uint2 w = __ldg(vph + 2 * j);
+                v = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u), __uint_as_float(w.y << 16),
+                                __uint_as_float(w.y & 0xFFFF0000u));
+            } else {
+                v = __ldg(vp + 2 * j);
+            }
             const float4 q = __ldg(qp + 2 * j);
             if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
                 const float d0 = __fsub_rn(q.x, v.x), d1 = __fsub_rn(q.y, v.y), d2 = __fsub_rn(q.z, v.z), d3 = __fsub_rn(q.w, v.w);
@@ -918,11 +928,12 @@ __global__ void __launch_bounds__(256) rescore_kernel(const __grid_constant__ Re
     float tail = -0.0f;
     if (valid && ntail) {
         for (uint32_t e = 0; e < ntail; ++e) {
+            const float ve = HALF ? __uint_as_float((uint32_t)vrow_h[dim8 + e] << 16) : vrow[dim8 + e];
             if (METRIC == OTTERS_METRIC_EUCLIDEAN) {
-                const float d = __fsub_rn(qrow[dim8 + e], vrow[dim8 + e]);
+                const float d = __fsub_rn(qrow[dim8 + e], ve);
                 tail = __fadd_rn(tail, __fmul_rn(d, d));
             } else {
-                tail = __fadd_rn(tail, __fmul_rn(qrow[dim8 + e], vrow[dim8 + e]));
+                tail = __fadd_rn(tail, __fmul_rn(qrow[dim8 + e], ve));
             }
         }
     }
@@ -1133,11 +1144,17 @@ int launch_batch(const BatchLaunch& l, BatchParams p, int metric, uint32_t* smem
 int launch_rescore(const RescoreParams& p, int metric, uint32_t n_sort, cudaStream_t s) {
     const uint32_t total = p.n_lists * p.k;
     const unsigned blocks = (total + 127) / 128;
-    if (blocks) {
+    if (blocks && p.half) {
         switch (metric) {
-        case OTTERS_METRIC_COSINE: rescore_kernel<OTTERS_METRIC_COSINE><<<blocks, 256, 0, s>>>(p); break;
-        case OTTERS_METRIC_EUCLIDEAN: rescore_kernel<OTTERS_METRIC_EUCLIDEAN><<<blocks, 256, 0, s>>>(p); break;
-        default: rescore_kernel<OTTERS_METRIC_DOT><<<blocks, 256, 0, s>>>(p); break;
+        case OTTERS_METRIC_COSINE: rescore_kernel<OTTERS_METRIC_COSINE, true><<<blocks, 256, 0, s>>>(p); break;
+        case OTTERS_METRIC_EUCLIDEAN: rescore_kernel<OTTERS_METRIC_EUCLIDEAN, true><<<blocks, 256, 0, s>>>(p); break;
+        default: rescore_kernel<OTTERS_METRIC_DOT, true><<<blocks, 256, 0, s>>>(p); break;
+        }
+    } else if (blocks) {
+        switch (metric) {
+        case OTTERS_METRIC_COSINE: rescore_kernel<OTTERS_METRIC_COSINE, false><<<blocks, 256, 0, s>>>(p); break;
+        case OTTERS_METRIC_EUCLIDEAN: rescore_kernel<OTTERS_METRIC_EUCLIDEAN, false><<<blocks, 256, 0, s>>>(p); break;
+        default: rescore_kernel<OTTERS_METRIC_DOT, false><<<blocks, 256, 0, s>>>(p); break;
         }
     }
     if (n_sort > total) pad_cands_kernel<<<64, 256, 0, s>>>(p.out, total, n_sort);

@@ -239,6 +239,7 @@ struct BatchLaunch {
     uint32_t cta_group;          // 1: one CTA per 128-row tile; 2: CTA pairs (tcgen05 cta_group::2) on 256-row tiles
 };
 struct RescoreParams {
+    uint32_t half;               // the store's rows are bf16 (vectors then points at uint16_t elements, pitch_g counts them)
     const float* vectors;
     const float* inv_norms;
     const float* queries;        // [nq][dim_pad] raw fp32

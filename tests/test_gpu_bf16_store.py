@@ -72,7 +72,7 @@ def test_bf16_both_front_ends_filters_masks_and_batches(mode, ctx):
             thr = 0.02
             got = store.query(q[1], ob.Metric.Cosine).filter(thr, cmp).take(64).collect_arrays()
             assert_same_results(got, run_oracle(v, q[1:2], ob.Metric.Cosine, ob.TakeType.Max, 64, (thr, cmp)), f"filter {cmp.name}")
-        # a batch on a bf16 store is answered query by query on the streaming kernel: one merged list, ties to the lower query
+        # five queries are too few for the tensor-core kernel in automatic mode: query by query, one merged list, ties to the lower query
         got = store.query(q, ob.Metric.DotProduct).take(100).collect_arrays()
         assert ctx.last_work()["batch_used"] == 0
         assert_same_results(got, run_oracle(v, q, ob.Metric.DotProduct, ob.TakeType.Max, 100), "merged batch")
@@ -133,6 +133,33 @@ def test_bf16_metastore_filtered_query(pred, ctx):
     finally:
         ctx.set_tuning()
     assert np.array_equal(store.inv_norms().view(np.uint32), ora.inv_norms(ob.round_to_bf16(v)).view(np.uint32))
+
+
+def test_bf16_store_batches_on_the_tensor_cores(ctx):
+    """K2 on a bf16 store: its rows ARE the bf16 operand of the kind::f16 contraction (no shadow copy) and the exact re-scoring
+    reads the same rows; one rung only — a declined certificate goes to the streaming kernel."""
+    v = ora.synth_fill(0, 3000, 768, 0x7735)
+    q = ora.synth_fill(0, 1024, 768, 0xBEEF)
+    store = make_store(v, ctx)
+    ctx.set_tuning(batch_mode=1)
+    try:
+        for metric in METRICS:
+            got = store.query(q, metric).take_max(100).collect_arrays()
+            w = ctx.last_work()
+            assert w["batch_used"] == 1 and w["batch_passes"] == 2 and w["batch_attempts"] == 1 and w["batch_max_err"] <= w["batch_delta"], w
+            assert_same_results(got, run_oracle(v, q, metric, ob.TakeType.Max, 100), f"bf16 store K2 {metric.name}")
+        # small, crowded stores: whatever path answers, the result is the oracle's (dims with a ragged last k-block too)
+        for n, dim, nq in [(300, 24, 2), (1000, 7, 9), (4097, 100, 33), (700, 1536, 16)]:
+            v2 = ora.synth_fill(0, n, dim, 11 + n)
+            q2 = ora.synth_fill(0, nq, dim, 12 + nq)
+            s2 = make_store(v2, ctx)
+            for tt, call in ((ob.TakeType.Max, "take_max"), (ob.TakeType.Min, "take_min")):
+                got = getattr(s2.query(q2, ob.Metric.Cosine), call)(30).collect_arrays()
+                w = ctx.last_work()
+                assert w["batch_used"] == 1 or w["batch_fallback"] == 1, w
+                assert_same_results(got, run_oracle(v2, q2, ob.Metric.Cosine, tt, 30), f"bf16 store K2 n={n} dim={dim} {call}")
+    finally:
+        ctx.set_tuning()
 
 
 def test_bf16_scan_streams_half_the_bytes(ctx):
