@@ -468,6 +468,46 @@ impl<'c> DeviceMetaStore<'c> {
     }
 
     /// MetaStore::last_query_stats (src/meta.rs:395-397)
+    /// Roadmap "Persistence (save/load MetaStore to/from disk)" (README.md:206): writes the store's HBM image.  `user` is an
+    /// opaque blob that comes back from `load` (the crate would keep its Columns or a row-order permutation there).
+    pub fn save(&self, path: &str, user: &[u8]) -> Result<(), String> {
+        let p = CString::new(path).map_err(|e| e.to_string())?;
+        let up = if user.is_empty() { ptr::null() } else { user.as_ptr() as *const c_void };
+        check(unsafe { sys::otters_metastore_save(self.ms, p.as_ptr(), up, user.len() as u64) })
+    }
+
+    /// Loads a store written by `save`: device arrays are copied back as they were, nothing is rebuilt.  Returns the store
+    /// and the caller blob.
+    pub fn load(ctx: &'c DeviceContext, path: &str) -> Result<(Self, Vec<u8>), String> {
+        let p = CString::new(path).map_err(|e| e.to_string())?;
+        let mut ms = ptr::null_mut();
+        check(unsafe { sys::otters_metastore_load(ctx.raw, p.as_ptr(), &mut ms) })?;
+        let mut col_index = HashMap::new();
+        let mut dtypes = Vec::new();
+        for i in 0..unsafe { sys::otters_metastore_n_columns(ms) } {
+            let (mut name, mut dt) = (ptr::null(), 0i32);
+            check(unsafe { sys::otters_metastore_column_info(ms, i, &mut name, &mut dt) })?;
+            let name = unsafe { std::ffi::CStr::from_ptr(name) }.to_string_lossy().into_owned();
+            col_index.insert(name, i as usize);
+            dtypes.push(match dt {
+                sys::OTTERS_DTYPE_INT32 => DataType::Int32,
+                sys::OTTERS_DTYPE_INT64 => DataType::Int64,
+                sys::OTTERS_DTYPE_FLOAT32 => DataType::Float32,
+                sys::OTTERS_DTYPE_FLOAT64 => DataType::Float64,
+                sys::OTTERS_DTYPE_STRING => DataType::String,
+                _ => DataType::DateTime,
+            });
+        }
+        let (mut bp, mut bl) = (ptr::null(), 0u64);
+        check(unsafe { sys::otters_metastore_user_blob(ms, &mut bp, &mut bl) })?;
+        let blob = if bl == 0 { Vec::new() } else { unsafe { std::slice::from_raw_parts(bp as *const u8, bl as usize) }.to_vec() };
+        let n_rows = unsafe { sys::otters_metastore_len(ms) } as usize;
+        let n_chunks = unsafe { sys::otters_metastore_n_chunks(ms) } as usize;
+        let dim = unsafe { sys::otters_metastore_dim(ms) } as usize;
+        Ok((Self { ctx, ms, col_index, dtypes, n_rows,
+                   build_stats: DeviceBuildStats { n_rows, dim, n_chunks, ..Default::default() } }, blob))
+    }
+
     pub fn last_query_stats(&self) -> Option<DeviceQueryStats> {
         let mut st = sys::otters_query_stats::default();
         if unsafe { sys::otters_metastore_last_stats(self.ms, &mut st) } == sys::OTTERS_OK { Some(st.into()) } else { None }
