@@ -912,6 +912,8 @@ static int run_batched(otters_ctx* c, VecStorage* st, const otters_vec_query* q,
         bp.kps = (uint32_t)kps;
         bp.pair_direct = (uint32_t)direct;
         bp.epi_warps = epi == 4 ? 4u : 8u;
+        static const int redo = getenv("OTTERS_K2_REDO") ? atoi(getenv("OTTERS_K2_REDO")) : 0;  // A/B: 1 = redo chunks on the general path
+        bp.redo_general = redo ? 1u : 0u;
     }
 #ifdef OTTERS_K2_EXPERIMENTS
     // timing experiments only (role-by-role timing of K2, scripts/dbg_passes_roles.py): results are garbage, so the hooks are

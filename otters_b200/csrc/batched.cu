@@ -719,7 +719,11 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                         if (live) xbest = fmaxf(xbest, cmax);
                         continue;
                     }
-                    // some lane has a candidate (or an odd value): column by column, re-read from TMEM, exact bookkeeping
+                    // some lane has a candidate (or an odd value).  redo_general: take the general path below — straight-line
+                    // scoring of the 32 columns already in registers, then only the columns where some lane passed are
+                    // re-read from TMEM; otherwise column by column, every column re-read from TMEM (32 dependent tcgen05.ld
+                    // round trips: ~3 µs per chunk, which made tiles with several such chunks outlast their MMAs)
+                    if (p.redo_general) goto general_path;
 #pragma unroll 1
                     for (uint32_t j = 0; j < 32; ++j) {
                         const uint32_t qi = q_base + c * 32 + j;
@@ -734,6 +738,7 @@ batch_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ C
                     continue;
                 }
                 // general path (vec_filter, ragged last chunk): straight-line scoring of the 32 columns, one bit per passing column
+            general_path:
                 uint32_t pass = 0;
 #pragma unroll
                 for (uint32_t j = 0; j < 32; ++j) {

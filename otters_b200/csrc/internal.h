@@ -221,6 +221,7 @@ struct BatchParams {
                                  // error bound) or 2 (one bf16 MMA per product on the bf16 shadow arrays: widest bound, fastest)
     uint32_t kps;                // single pass: k-blocks per pipeline stage (1 or 2: one barrier round trip and one commit for two)
     uint32_t pair_direct;        // CTA pairs, single pass: both CTAs' TMA loads credit the leader's barrier themselves (no relay warp)
+    uint32_t redo_general;       // lean epilogue: a chunk holding a candidate is redone on the general straight-line path (1) or column by column (0)
     uint32_t epi_warps;          // epilogue warps per CTA: 8 (default: two per TMEM lane quarter, even / odd column chunks) or 4
     uint32_t dbg;                // timing experiments only (OTTERS_BATCH_DBG): 1 no loads, 2 no split, 4 no epilogue, 8 no MMAs
 };
