@@ -195,6 +195,21 @@ def synth_fill(row0: int, n_rows: int, dim: int, seed: int) -> np.ndarray:
     return out
 
 
+def round_bf16(x) -> np.ndarray:
+    """f32(bf16(x)) with round-to-nearest-even — the values a store created with OTTERS_VECTORS_FMT_BF16 holds.  The reference
+    has no reduced-precision rows (they are a roadmap item, README.md:208); the parity contract of such a store is the
+    reference's arithmetic on these rounded rows, so the oracle rounds its INPUT here and everything after is unchanged.
+    IEEE rule restated directly: keep the upper 16 bits, round on the lower 16 (ties to the even upper half); NaN stays NaN."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    bits = a.view(np.uint32).astype(np.uint64)
+    upper, lower = bits >> 16, bits & 0xFFFF
+    up = (lower > 0x8000) | ((lower == 0x8000) & ((upper & 1) == 1))
+    out = ((upper + up.astype(np.uint64)) << 16).astype(np.uint32)
+    nan = np.isnan(a)
+    out = np.where(nan, (a.view(np.uint32) & np.uint32(0xFFFF0000)) | np.uint32(0x00400000), out).astype(np.uint32)
+    return out.view(np.float32).reshape(a.shape)
+
+
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
 

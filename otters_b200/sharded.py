@@ -84,6 +84,11 @@ class CudaShard:
         self._torch, self._dist, self._ffi = torch, dist, _ffi
         self.store = store
         self.is_meta = isinstance(store, MetaStore)
+        if self.is_meta and store.row_order() is not None:
+            from .types import OttersError
+
+            # the shard map turns store positions into global row ids on the device; a row order would need its own id map there
+            raise OttersError("row-sharded search does not support stores built with_row_order")
         self.ctx = store.ctx
         self.row_base = int(row_base)
         self.group = group

@@ -20,7 +20,7 @@ def make_store(vectors, ctx=None):
 
 
 def run_oracle(vectors, q, metric, tt, k, flt=None, mask=None):
-    return ora.vecstore_query(ob.round_to_bf16(vectors), q, metric, tt, k, flt, mask, ora.CANONICAL)
+    return ora.vecstore_query(ora.round_bf16(vectors), q, metric, tt, k, flt, mask, ora.CANONICAL)
 
 
 def test_round_to_bf16_is_nearest_even():
@@ -38,7 +38,7 @@ def test_inv_norms_are_those_of_the_rounded_rows(ctx):
         v = ora.synth_fill(0, n, dim, 11 + dim)
         v[3 % n] = 0.0
         got = make_store(v).inv_norms()
-        assert np.array_equal(got.view(np.uint32), ora.inv_norms(ob.round_to_bf16(v)).view(np.uint32))
+        assert np.array_equal(got.view(np.uint32), ora.inv_norms(ora.round_bf16(v)).view(np.uint32))
 
 
 @pytest.mark.parametrize("metric", METRICS, ids=lambda m: m.name)
@@ -91,7 +91,7 @@ def test_bf16_synthetic_rows_and_set_rows(ctx):
     s.add_synthetic(3100, 500, 0x7735)  # appended: the generator continues at the absolute row id
     v = ora.synth_fill(100, 3500, dim, 0x7735)
     q = ora.synth_fill(0, 1, dim, 5)
-    assert np.array_equal(s.inv_norms().view(np.uint32), ora.inv_norms(ob.round_to_bf16(v)).view(np.uint32))
+    assert np.array_equal(s.inv_norms().view(np.uint32), ora.inv_norms(ora.round_bf16(v)).view(np.uint32))
     got = s.query(q[0], ob.Metric.Cosine).take(50).collect_arrays()
     assert_same_results(got, run_oracle(v, q, ob.Metric.Cosine, ob.TakeType.Max, 50), "synthetic bf16")
     # planted rows are rounded like every other row
@@ -101,7 +101,7 @@ def test_bf16_synthetic_rows_and_set_rows(ctx):
     got = s.query(q[0], ob.Metric.Cosine).take(3).collect_arrays()
     assert got[0][0] == 17
     assert_same_results(got, run_oracle(v, q, ob.Metric.Cosine, ob.TakeType.Max, 3), "set_rows bf16")
-    assert np.array_equal(s.inv_norms().view(np.uint32), ora.inv_norms(ob.round_to_bf16(v)).view(np.uint32))
+    assert np.array_equal(s.inv_norms().view(np.uint32), ora.inv_norms(ora.round_bf16(v)).view(np.uint32))
 
 
 @pytest.mark.parametrize("pred", [0, 2], ids=["rowmask_kernel", "predicate_in_scan"])
@@ -115,7 +115,7 @@ def test_bf16_metastore_filtered_query(pred, ctx):
     assert store.vector_format() == BF16
     q = ora.synth_fill(0, 3, dim, 0xBEEF)
     expr = ob.col("price").lt(50.0) & ob.col("version").gte(2)
-    ost = ora.MetaStore(ob.round_to_bf16(v), [price, version], cs)
+    ost = ora.MetaStore(ora.round_bf16(v), [price, version], cs)
     fp = ora.FilterPack.from_compiled(expr.compile(store.schema()), store.column_index())
     ctx.set_tuning(disable_fused_predicate=pred)
     try:
@@ -132,7 +132,7 @@ def test_bf16_metastore_filtered_query(pred, ctx):
         assert_same_results((res.indices, res.scores, res.query_ids), (oi, os_, oq), "bf16 metastore batch")
     finally:
         ctx.set_tuning()
-    assert np.array_equal(store.inv_norms().view(np.uint32), ora.inv_norms(ob.round_to_bf16(v)).view(np.uint32))
+    assert np.array_equal(store.inv_norms().view(np.uint32), ora.inv_norms(ora.round_bf16(v)).view(np.uint32))
 
 
 def test_bf16_store_batches_on_the_tensor_cores(ctx):

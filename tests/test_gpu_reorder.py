@@ -43,7 +43,7 @@ def test_row_order_same_results_more_pruning(method, fmt, ctx):
             for j, row in enumerate(b.indices[:10]):
                 assert b.data[name].get(j) == colobj.get(row), (name, j, row)
     # the oracle on the caller's data agrees as well
-    vv = ob.round_to_bf16(v) if fmt == ob.VectorFormat.Bf16 else v
+    vv = ora.round_bf16(v) if fmt == ob.VectorFormat.Bf16 else v
     ost = ora.MetaStore(vv, cols, cs)
     fp = ora.FilterPack.from_compiled(expr.compile(plain.schema()), plain.column_index())
     oi, os_, _, _ = ost.query(q[None, :], ob.Metric.Cosine, ob.TakeType.Max, 50, None, fp)
