@@ -21,7 +21,7 @@ from typing import Dict, List, Sequence
 
 import numpy as np
 
-from .column import Column
+from .column import Column, _CatSeq
 from .types import DataType, OttersError
 
 METHODS = ("sort", "zorder")
@@ -30,6 +30,10 @@ METHODS = ("sort", "zorder")
 def _sort_key(col: Column) -> np.ndarray:
     """An int64 / float64 / uint32 array whose order is the column's value order (strings: lexicographic by code point)."""
     dt = col.dtype()
+    if dt == DataType.String and isinstance(col._vals, _CatSeq):  # vocabulary + codes: rank the vocabulary, not the rows
+        vocab = np.asarray(col._vals.vocab, dtype=object).astype(str)
+        _, inv = np.unique(vocab, return_inverse=True)
+        return inv.astype(np.int64)[col._vals.codes]
     if dt == DataType.String:
         vals = np.asarray(col.string_values(), dtype=object)
         if len(vals) == 0:
