@@ -77,3 +77,22 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_scores_the_rounded_rows_for_bf16_stores():
+    """--vector-format bf16: the config says so in both arms and the CPU arm works on f32(bf16(x)) rows (Workload.stored)."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+
+    import bench_workloads as bw
+    from oracle import oracle as ora
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "target", "--rows", "40960",
+                          "--vector-format", "bf16", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["config"]["vector_format"] == "bf16" and d["value"] > 0
+    wl = bw.Workload("c1", 1000, "bf16")
+    v = bw.synth_fill_np(0, 64, wl.dim, bw.DATA_SEED)
+    assert np.array_equal(wl.stored(v).view(np.uint32), ora.round_bf16(v).view(np.uint32))
+    assert bw.Workload("c1", 1000).stored(v) is v and bw.Workload("c1", 1000).config()["vector_format"] == "f32"
