@@ -99,7 +99,7 @@ typedef struct {
                                          scan reads mask words), 2 = evaluated per work unit inside the scan kernel */
     uint32_t batch_mode;   /* query batches: 0 = automatic, 1 = always the tensor-core kernel (when k <= 1024), 2 = never */
     uint32_t batch_cta_group; /* tensor-core kernel: 0 = automatic (single CTAs), 1 = single CTAs, 2 = CTA pairs (tcgen05 cta_group::2) */
-    uint32_t scan_mode;    /* K1 front-end: 0 = automatic, 1 = autonomous warps (scan.cu), 2 = planner + worker warps (scan_planner.cu) */
+    uint32_t scan_mode;    /* K1 front-end: 0 = automatic, 1 = autonomous warps (scan_kernel.cuh), 2 = planner + worker warps (scan_planner.cu) */
     uint32_t planners;     /* planner front-end: planner warps per CTA (0 = automatic: 2 for filtered stores up to 256-d, else 1) */
     uint32_t timing;       /* per-phase CUDA events (otters_last_work *_ms, otters_query_stats durations): 0 = automatic (only
                               for blocking MetaStore queries that ask for stats), 1 = always, 2 = never */

@@ -1,5 +1,5 @@
 // api.cu — the C ABI of libotters_b200.so (include/otters_b200.h): contexts, device-resident stores,
-// query orchestration.  Everything that touches rows runs in the CUDA kernels of scan.cu / select.cu
+// query orchestration.  Everything that touches rows runs in the CUDA kernels of scan_kernel.cuh / select.cu
 // / meta.cu / store.cu; there is no CPU fallback.
 #include <errno.h>
 #include <float.h>

@@ -174,7 +174,7 @@ __device__ void warp_sort_pairs(uint64_t* keys, uint32_t* qids, uint32_t cnt, ui
     }
 }
 
-// Lock-free append (same protocol as K1's warp_push, scan.cu) with a query-id payload.  After a compaction
+// Lock-free append (same protocol as K1's warp_push, scan_shared.cuh) with a query-id payload.  After a compaction
 // the CTA's new threshold is published to the grid-wide threshold (any key below some CTA's k-th best key
 // cannot be among the global best k), and the grid-wide value is adopted when it is higher.
 __device__ __noinline__ void warp_push_pairs(CtaHdr* hdr, uint64_t* keys, uint32_t* qids, uint32_t cap, uint32_t k, bool has, uint64_t key,
@@ -872,7 +872,7 @@ __global__ void batch_delta_kernel(int metric, uint32_t dim, uint32_t passes, co
 }
 
 // ---- exact re-scoring of the selected (row, query) pairs ---------------------------------------------------
-// Two threads per pair hold the eight f32x8 lane accumulators (4 each) exactly like K1 (scan.cu): multiply and
+// Two threads per pair hold the eight f32x8 lane accumulators (4 each) exactly like K1 (scan_kernel.cuh): multiply and
 // add are separate round-to-nearest operations, 8-column blocks in order, wide's non-AVX reduce_add order,
 // serial dim%8 tail added last, cosine as (dot * q_inv) * row_inv (reference src/vec_compute.rs:9-54).
 // HALF: the store's rows are bf16 (OTTERS_VECTORS_FMT_BF16): widened exactly, same arithmetic (as K1's load_row4<HALF>).

@@ -1,5 +1,5 @@
 // predicate.cuh — per-row evaluation of one lowered filter leaf, shared by the row-mask kernel (meta.cu)
-// and the fused predicate stage of the scan kernel (scan.cu).
+// and the fused predicate stage of the scan kernel (scan_kernel.cuh).
 //
 // Semantics follow the reference's row kernels (src/type_utils.rs:306-444,586-736) and leaf helpers
 // (src/meta_compute.rs:235-318): IEEE compares (NaN satisfies only Neq), a NULL row fails every leaf

@@ -1,8 +1,8 @@
 // scan_planner.cu — K1, planner front-end: the streaming exact-order scan with the row selection done AHEAD of the
 // streaming warps (sm_100a).
 //
-// Same contract, arithmetic and outputs as scan.cu (reference src/vec.rs:222-303, src/vec_compute.rs:9-294): the
-// difference is who decides which rows are read.  In scan.cu every warp is autonomous: it claims a 128-row unit,
+// Same contract, arithmetic and outputs as scan_kernel.cuh (reference src/vec.rs:222-303, src/vec_compute.rs:9-294): the
+// difference is who decides which rows are read.  In scan_kernel.cuh every warp is autonomous: it claims a 128-row unit,
 // evaluates the row mask / CNF predicate for it, then streams the survivors; while it evaluates, its TMA slot is
 // idle, and the last units of the dynamic schedule are finished by single warps.  Here one or two PLANNER warps per
 // CTA claim the units, evaluate the chunk bit + predicate (all metadata loads of a unit in flight together) and
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
                 if (!claims.phase && p.g_tau) g_pref = *reinterpret_cast<volatile unsigned long long*>(p.g_tau);
             }
             claims.advance(p.claim_depth);
-            // guided schedule (see scan.cu): big units first, small units for the tail of the store
+            // guided schedule (see scan_kernel.cuh): big units first, small units for the tail of the store
             const bool big = u < p.n_big;
             const uint32_t urows = big ? p.unit_rows : p.unit_small;
             const uint32_t row0 = big ? u * p.unit_rows : p.n_big * p.unit_rows + (u - p.n_big) * p.unit_small;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
                         }
                     }
                 } else {
-                    // lazy pruning (see scan.cu): zonemap / Bloom rules of the chunks of this lane's rows, evaluated here; the
+                    // lazy pruning (see scan_kernel.cuh): zonemap / Bloom rules of the chunks of this lane's rows, evaluated here; the
                     // lane holding a chunk's first row accounts it in the statistics
                     uint32_t ch_prev = 0xFFFFFFFFu;
                     bool keep_ch = false;
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(640, 1) scan_planner_kernel(const __grid_const
         if (lane == 0) p.cta_counts[blockIdx.x] = n;
     }
     if (p.fuse_select) {
-        // K3 fused into the scan (see scan.cu): the CTA that publishes its list last selects the final top-k
+        // K3 fused into the scan (see scan_kernel.cuh): the CTA that publishes its list last selects the final top-k
         __shared__ uint32_t s_last;
         __threadfence();
         __syncthreads();

@@ -1,4 +1,4 @@
-// scan_shared.cuh — pieces shared by the two front-ends of K1 (scan.cu: autonomous warps; scan_planner.cu: planner
+// scan_shared.cuh — pieces shared by the two front-ends of K1 (scan_kernel.cuh: autonomous warps; scan_planner.cu: planner
 // warps feeding worker warps): the per-CTA lock-free candidate buffer and its compaction.
 #pragma once
 #include "internal.h"

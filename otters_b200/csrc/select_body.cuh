@@ -87,7 +87,7 @@ __device__ __forceinline__ uint64_t ld_key_cg(const uint64_t* p) { return __ldcg
 
 // WITH_PREV = false is the single-query hot path: no running list, all keys distinct, keys sorted alone.
 // One CTA of any size runs this: either the stand-alone select_kernel (select.cu) or the LAST CTA of a scan kernel
-// (scan.cu / scan_planner.cu), which re-uses its dynamic shared memory (`sm`, at least kSelectSmemBytes).  The per-CTA
+// (scan_kernel.cuh / scan_planner.cu), which re-uses its dynamic shared memory (`sm`, at least kSelectSmemBytes).  The per-CTA
 // lists were written by other CTAs (of this or an earlier kernel): they are read through L2 (ld.global.cg).
 template <bool WITH_PREV>
 __device__ __forceinline__ void select_body(const SelectParams& p, uint8_t* sm) {
