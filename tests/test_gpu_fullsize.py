@@ -20,19 +20,21 @@ pytestmark = pytest.mark.gpu
 SEED = 0x07735
 
 
-def oracle_rows(rows, dim, q, metric):
-    """Exact scores of individual store rows (regenerated on the host) against one query."""
+def oracle_rows(rows, dim, q, metric, bf16=False):
+    """Exact scores of individual store rows (regenerated on the host; rounded like the store's for a bf16 store) against one query."""
     v = np.concatenate([ora.synth_fill(int(r), 1, dim, SEED) for r in rows], axis=0)
+    if bf16:
+        v = ora.round_bf16(v)
     idx, score, _ = ora.vecstore_query(v, q[None, :], metric, ob.TakeType.Max, len(rows), None, None, ora.CANONICAL)
     out = np.zeros(len(rows), np.float32)
     out[np.asarray(idx, np.int64)] = score
     return out
 
 
-def check_against_row_oracle(got, dim, q, metric):
+def check_against_row_oracle(got, dim, q, metric, bf16=False):
     idx, score = np.asarray(got[0], np.int64), np.asarray(got[1], np.float32)
     assert len(set(idx.tolist())) == len(idx), "rows must be unique in a single-query result"
-    want = oracle_rows(idx, dim, q, metric)
+    want = oracle_rows(idx, dim, q, metric, bf16)
     same = (want.view(np.uint32) == score.view(np.uint32)) | ((want == 0) & (score == 0))
     assert same.all(), f"scores differ from the per-row oracle at {np.nonzero(~same)[0][:5]}"
 
@@ -87,6 +89,38 @@ def test_fullsize_vecstore_properties(metric, big_vecstore, ctx):
         ctx.set_tuning(scan_mode=mode)
         assert_same_results(big_vecstore.query(q, metric).take(k).collect_arrays(), got, f"scan_mode {mode}")
     ctx.set_tuning()
+
+
+def test_fullsize_bf16_vecstore_properties(ctx):
+    """10M x 768 kept as bf16 rows (15.4 GB): the same properties, the oracle working on the rounded rows."""
+    n, dim, k = 10_000_000, 768, 100
+    s = ob.VecStore(dim, ctx, ob.VectorFormat.Bf16)
+    s.add_synthetic(0, n, SEED)
+    planted = 7_654_321
+    q = ora.round_bf16(ora.synth_fill(planted, 1, dim, SEED))[0]  # the query is a (rounded) row of the store
+    for metric in (ob.Metric.Cosine, ob.Metric.Euclidean):
+        take_max = metric != ob.Metric.Euclidean
+        got = s.query(q, metric).take(k).collect_arrays()
+        sc = got[1]
+        assert len(got[0]) == k and (np.all(sc[:-1] >= sc[1:]) if take_max else np.all(sc[:-1] <= sc[1:]))
+        assert int(got[0][0]) == planted and (metric != ob.Metric.Euclidean or float(sc[0]) == 0.0)
+        check_against_row_oracle(got, dim, q, metric, bf16=True)
+        assert ctx.last_work()["scan_bytes"] == n * (dim * 2 + (4 if metric == ob.Metric.Cosine else 0))
+        rng = np.random.default_rng(6)
+        sample = np.setdiff1d(rng.integers(0, n, 400), np.asarray(got[0], np.int64))
+        others = oracle_rows(sample, dim, q, metric, bf16=True)
+        assert np.all(others <= sc[-1]) if take_max else np.all(others >= sc[-1])
+        mask = np.zeros(n, bool)
+        mask[0::2] = True
+        even = s.query(q, metric).with_row_mask(mask).take(k).collect_arrays()
+        odd = s.query(q, metric).with_row_mask(~mask).take(k).collect_arrays()
+        assert_same_results(merge_host([even, odd], k, take_max), got[:2], "partition")
+        for mode in (1, 2):
+            ctx.set_tuning(scan_mode=mode)
+            assert_same_results(s.query(q, metric).take(k).collect_arrays(), got, f"scan_mode {mode}")
+        ctx.set_tuning()
+    s.close()
+    gc.collect()
 
 
 def test_fullsize_metastore_target(ctx):
